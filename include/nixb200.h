@@ -1,0 +1,126 @@
+/* nixb200.h -- C ABI of the B200-native per-chunk PIC step for amanotk/nix.
+ *
+ * This is the drop-in boundary: a C-ABI shared library (libnixb200.so) whose entry points are what
+ * a `GpuChunk : nix::Chunk` / `GpuApplication : nix::Application` pair would bind (see
+ * INTEGRATION.md).  The reference has no FFI of its own -- its extension API is C++ inheritance
+ * (application.hpp:45-48,343-346; chunk.hpp:139-192,399-432) -- so every entry point cites the
+ * reference interface it stands behind.  Plain pointers and sizes only; no C++ or torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; nixb200_last_error() gives the text
+ *     (the reference logs with ERROR and carries on; no exceptions cross this boundary)
+ *   - axis order is (z, y, x) everywhere; the 27 directions are indexed 9*iz + 3*iy + ix with
+ *     0/1/2 = -/centre/+ (chunk.hpp:11-41)
+ *   - particles cross the boundary in the reference's AoS layout xu[np][7] =
+ *     (x, y, z, ux, uy, uz, id-bits) (xtensor_particle.hpp:15, particle.hpp:18); on the device they
+ *     are SoA
+ *   - fields cross as uf[Mz][My][Mx][6] (Ex Ey Ez Bx By Bz) and uj[Mz][My][Mx][4] (rho Jx Jy Jz),
+ *     M = N + 2*nb, exactly the reference's xtensor arrays
+ *   - all work is enqueued on the domain's stream (nixb200_domain_set_stream); calls that return
+ *     data to the host synchronise that stream
+ *   - there is NO CPU fallback: every entry point fails if no sm_100 device is present
+ */
+#ifndef NIXB200_H
+#define NIXB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NIXB200_MODE_FIELD 0    /* XtensorHaloField3D    xtensor_halo3d.hpp:19-71   */
+#define NIXB200_MODE_CURRENT 1  /* XtensorHaloCurrent3D  xtensor_halo3d.hpp:77-129  */
+#define NIXB200_MODE_PARTICLE 2 /* XtensorHaloParticle3D xtensor_halo3d.hpp:251-557 */
+
+#define NIXB200_FIELD_UF 0
+#define NIXB200_FIELD_UJ 1
+
+/* error bits accumulated on the device, see nixb200_domain_check() */
+#define NIXB200_ERR_UNSORTED 1 /* push found a particle outside the cell it is binned in */
+#define NIXB200_ERR_CFL 2      /* a particle moved more than one cell (c*dt > dx)          */
+#define NIXB200_ERR_CAPACITY 4 /* a particle / message buffer overflowed                   */
+
+typedef struct nixb200_domain nixb200_domain;
+
+/* A domain = the chunks of ONE rank (one GPU): a contiguous range of chunk ids along the
+ * space-filling curve, exactly ChunkMap::get_rank semantics (chunkmap.cpp:156-164).  The host keeps
+ * ChunkMap / Balancer / SFC; it hands us the id -> (cz,cy,cx) table and the rank boundaries. */
+typedef struct {
+  int    cdims[3];   /* chunks per axis of the global periodic box (Cz, Cy, Cx)  cfgparser.hpp:187  */
+  int    dims[3];    /* cells per chunk (Nz, Ny, Nx)                             chunk.cpp:6-16     */
+  int    nb;         /* boundary margin                                          chunk.hpp:260-264  */
+  int    order;      /* shape order 1..3                                         primitives.hpp:519 */
+  int    ns;         /* number of species                                                           */
+  double del[3];     /* delz, dely, delx                                         chunk.cpp:210-237  */
+  double cc;         /* speed of light                                                              */
+  int    id_begin;   /* first chunk id owned by this rank   (boundary[rank])     chunkmap.cpp:156   */
+  int    id_end;     /* one past the last chunk id owned    (boundary[rank+1])                      */
+  int    device;     /* CUDA device ordinal                                                         */
+  int    strict_fp;  /* 1: push arithmetic without FMA contraction, bit-identical to the reference's
+                        scalar templates; 0: contracted (<=1e-12 relative)                           */
+  double capacity_factor; /* particle storage = factor * initial count (>=1; 0 -> 1.25)            */
+} nixb200_domain_desc;
+
+const char* nixb200_last_error(void);
+const char* nixb200_version(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+int64_t nixb200_launch_count(void);
+
+/* coord: [ncid][3] chunk id -> (cz,cy,cx) for ALL chunk ids of the box (ChunkMap::get_coordinate,
+ * chunkmap.cpp:176-191); q, m: [ns] charge and mass per species (particle.hpp:24-25). */
+int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, const double* q,
+                          const double* m, nixb200_domain** out);
+int nixb200_domain_destroy(nixb200_domain* d);
+int nixb200_domain_set_stream(nixb200_domain* d, void* cuda_stream);
+int nixb200_domain_synchronize(nixb200_domain* d);
+/* returns and clears the device error bits (NIXB200_ERR_*) */
+int nixb200_domain_check(nixb200_domain* d, int* errbits);
+
+/* ---- data in / out (backs Chunk::pack/unpack, chunk.cpp:18-116; XtensorParticle::pack/unpack,
+ *      xtensor_particle.hpp:128-218; and the diagnostics download path) ---- */
+/* local chunk index k = id - id_begin */
+int nixb200_chunk_field_upload(nixb200_domain* d, int k, int which, const double* host);
+int nixb200_chunk_field_download(nixb200_domain* d, int k, int which, double* host);
+/* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each */
+int nixb200_domain_set_particles(nixb200_domain* d, int is, const double* xu_aos,
+                                 const int64_t* np_chunk);
+int nixb200_domain_get_np(nixb200_domain* d, int is, int64_t* np_chunk /* [nchunk] */);
+int nixb200_chunk_get_particles(nixb200_domain* d, int k, int is, double* xu_aos, int64_t max_np,
+                                int64_t* np);
+/* pindex[Ng+1] / pcount[Ng+1][8] in the reference's layout (xtensor_particle.hpp:18-19): pcount is
+ * the state count() leaves (before sort() turns it into cursors); pindex the state sort() leaves */
+int nixb200_chunk_get_pindex(nixb200_domain* d, int k, int is, int32_t* pindex);
+int nixb200_chunk_get_pcount(nixb200_domain* d, int k, int is, int32_t* pcount);
+
+/* ---- the per-step hot path, batched over every chunk of the domain ---- */
+/* XtensorParticle::count + sort for every chunk/species (xtensor_particle.hpp:260-357); drops
+ * out-of-bounds particles exactly as the reference does.  Needed once after set_particles. */
+int nixb200_domain_sort(nixb200_domain* d);
+int nixb200_domain_clear_current(nixb200_domain* d);
+/* gather (interp3d) + push_boris + position update + Esirkepov deposit3d/append_current3d for every
+ * species; also produces the per-cell counts of the NEW positions (count(0,Np-1,true,order)) */
+int nixb200_domain_push_deposit(nixb200_domain* d, double delt);
+/* set_boundary_{pack,begin,end,unpack}(mode) for all local chunk pairs (chunk.hpp:435-586) */
+int nixb200_domain_exchange_current(nixb200_domain* d);
+int nixb200_domain_exchange_field(nixb200_domain* d);
+/* XtensorHaloParticle3D pack -> exchange -> unpack (append, periodic wrap, count, sort) */
+int nixb200_domain_migrate_sort(nixb200_domain* d);
+/* clear J, push+deposit, J halo, E/B halo, migrate+sort: one Application::push() worth of work */
+int nixb200_domain_step(nixb200_domain* d, double delt);
+
+/* ---- per-chunk halo buffers in the reference's MpiBuffer layout (chunk.cpp:257-286), for
+ *      neighbours that live on another rank and for drop-in use behind Chunk::set_boundary_* ---- */
+int nixb200_halo_layout(nixb200_domain* d, int mode, int* bufsize27, int* bufaddr27);
+int nixb200_chunk_halo_pack(nixb200_domain* d, int k, int mode, void* host_sendbuf);
+int nixb200_chunk_halo_unpack(nixb200_domain* d, int k, int mode, const void* host_recvbuf,
+                              const int* nbvalid27);
+
+/* Chunk::get_total_load (chunk.hpp:189-192): device milliseconds of the last push_deposit */
+int nixb200_domain_get_load(nixb200_domain* d, double* ms);
+int64_t nixb200_domain_total_particles(nixb200_domain* d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

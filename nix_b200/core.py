@@ -1,0 +1,290 @@
+"""ctypes binding of libnixb200.so (include/nixb200.h) and the host-side `Domain` object.
+
+The CUDA library is the product; this module is plumbing.  There is no CPU fallback: loading fails
+loudly when the library has not been built, and every entry point fails when no sm_100 device is
+present.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libnixb200.so")
+
+MODE_FIELD, MODE_CURRENT, MODE_PARTICLE = 0, 1, 2
+FIELD_UF, FIELD_UJ = 0, 1
+ERR_UNSORTED, ERR_CFL, ERR_CAPACITY = 1, 2, 4
+
+# every symbol include/nixb200.h declares (tests check the library exports all of them)
+SYMBOLS = [
+    "nixb200_last_error", "nixb200_version", "nixb200_launch_count", "nixb200_domain_create",
+    "nixb200_domain_destroy", "nixb200_domain_set_stream", "nixb200_domain_synchronize",
+    "nixb200_domain_check", "nixb200_chunk_field_upload", "nixb200_chunk_field_download",
+    "nixb200_domain_set_particles", "nixb200_domain_get_np", "nixb200_chunk_get_particles",
+    "nixb200_chunk_get_pindex", "nixb200_chunk_get_pcount", "nixb200_domain_sort",
+    "nixb200_domain_clear_current", "nixb200_domain_push_deposit", "nixb200_domain_exchange_current",
+    "nixb200_domain_exchange_field", "nixb200_domain_migrate_sort", "nixb200_domain_step",
+    "nixb200_halo_layout", "nixb200_chunk_halo_pack", "nixb200_chunk_halo_unpack",
+    "nixb200_domain_get_load", "nixb200_domain_total_particles",
+]
+
+
+class DomainDesc(C.Structure):
+    _fields_ = [
+        ("cdims", C.c_int * 3),
+        ("dims", C.c_int * 3),
+        ("nb", C.c_int),
+        ("order", C.c_int),
+        ("ns", C.c_int),
+        ("del_", C.c_double * 3),
+        ("cc", C.c_double),
+        ("id_begin", C.c_int),
+        ("id_end", C.c_int),
+        ("device", C.c_int),
+        ("strict_fp", C.c_int),
+        ("capacity_factor", C.c_double),
+    ]
+
+
+class NixB200Error(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Load libnixb200.so; raises if the CUDA extension has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NixB200Error(
+            f"{LIB_PATH} is missing: build it with `python -m nix_b200.build` "
+            "(there is no CPU fallback for this path)")
+    lib = C.CDLL(LIB_PATH)
+    P, I, D = C.c_void_p, C.c_int, C.c_double
+    PI, PD, PL = C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_int64)
+
+    def sig(fn, res, *args):
+        f = getattr(lib, fn)
+        f.restype = res
+        f.argtypes = list(args)
+
+    sig("nixb200_last_error", C.c_char_p)
+    sig("nixb200_version", C.c_char_p)
+    sig("nixb200_launch_count", C.c_int64)
+    sig("nixb200_domain_create", I, C.POINTER(DomainDesc), PI, PD, PD, C.POINTER(P))
+    sig("nixb200_domain_destroy", I, P)
+    sig("nixb200_domain_set_stream", I, P, P)
+    sig("nixb200_domain_synchronize", I, P)
+    sig("nixb200_domain_check", I, P, PI)
+    sig("nixb200_chunk_field_upload", I, P, I, I, PD)
+    sig("nixb200_chunk_field_download", I, P, I, I, PD)
+    sig("nixb200_domain_set_particles", I, P, I, PD, PL)
+    sig("nixb200_domain_get_np", I, P, I, PL)
+    sig("nixb200_chunk_get_particles", I, P, I, I, PD, C.c_int64, PL)
+    sig("nixb200_chunk_get_pindex", I, P, I, I, C.POINTER(C.c_int32))
+    sig("nixb200_chunk_get_pcount", I, P, I, I, C.POINTER(C.c_int32))
+    for fn in ("sort", "clear_current", "exchange_current", "exchange_field", "migrate_sort"):
+        sig("nixb200_domain_" + fn, I, P)
+    sig("nixb200_domain_push_deposit", I, P, D)
+    sig("nixb200_domain_step", I, P, D)
+    sig("nixb200_halo_layout", I, P, I, PI, PI)
+    sig("nixb200_chunk_halo_pack", I, P, I, I, P)
+    sig("nixb200_chunk_halo_unpack", I, P, I, I, P, PI)
+    sig("nixb200_domain_get_load", I, P, PD)
+    sig("nixb200_domain_total_particles", C.c_int64, P)
+    _lib = lib
+    return lib
+
+
+def launch_count():
+    return int(load_library().nixb200_launch_count())
+
+
+def lexicographic_coords(cdims):
+    """id -> (cz,cy,cx) in plain z-major order (a valid, if not locality-preserving, chunk order)."""
+    cz, cy, cx = cdims
+    return np.array([(z, y, x) for z in range(cz) for y in range(cy) for x in range(cx)], dtype=np.int32)
+
+
+class Domain:
+    """The chunks of one rank, resident on one B200 (mirrors the rank-local ChunkVec of
+    nix::Application, application.hpp:114, behind the Chunk API)."""
+
+    def __init__(self, cdims, dims, nb, order, q, m, delh=(1.0, 1.0, 1.0), cc=1.0, coord=None,
+                 id_range=None, device=0, strict_fp=True, capacity_factor=1.25, stream=None):
+        self.lib = load_library()
+        self.cdims = tuple(int(v) for v in cdims)
+        self.dims = tuple(int(v) for v in dims)
+        self.nb, self.order = int(nb), int(order)
+        self.q = np.ascontiguousarray(q, dtype=np.float64)
+        self.m = np.ascontiguousarray(m, dtype=np.float64)
+        self.ns = len(self.q)
+        self.M = tuple(d + 2 * self.nb for d in self.dims)
+        self.Ng = int(np.prod(self.M))
+        ncid = int(np.prod(self.cdims))
+        self.coord = np.ascontiguousarray(coord if coord is not None else lexicographic_coords(self.cdims),
+                                          dtype=np.int32).reshape(ncid, 3)
+        self.id_begin, self.id_end = (0, ncid) if id_range is None else (int(id_range[0]), int(id_range[1]))
+        self.nchunk = self.id_end - self.id_begin
+        desc = DomainDesc()
+        desc.cdims[:] = self.cdims
+        desc.dims[:] = self.dims
+        desc.nb, desc.order, desc.ns = self.nb, self.order, self.ns
+        desc.del_[:] = [float(v) for v in delh]
+        desc.cc = float(cc)
+        desc.id_begin, desc.id_end = self.id_begin, self.id_end
+        desc.device = int(device)
+        desc.strict_fp = int(bool(strict_fp))
+        desc.capacity_factor = float(capacity_factor)
+        self.h = C.c_void_p()
+        self._ck(self.lib.nixb200_domain_create(
+            C.byref(desc), self.coord.ctypes.data_as(C.POINTER(C.c_int)),
+            self.q.ctypes.data_as(C.POINTER(C.c_double)), self.m.ctypes.data_as(C.POINTER(C.c_double)),
+            C.byref(self.h)))
+        if stream is not None:
+            self.set_stream(stream)
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise NixB200Error(self.lib.nixb200_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.nixb200_domain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.lib.nixb200_domain_set_stream(self.h, C.c_void_p(int(cuda_stream_ptr))))
+
+    def synchronize(self):
+        self._ck(self.lib.nixb200_domain_synchronize(self.h))
+
+    def check(self):
+        e = C.c_int(0)
+        self._ck(self.lib.nixb200_domain_check(self.h, C.byref(e)))
+        return e.value
+
+    # ---- data in / out ----
+    def set_field(self, k, uf):
+        a = np.ascontiguousarray(uf, dtype=np.float64)
+        assert a.shape == self.M + (6,)
+        self._ck(self.lib.nixb200_chunk_field_upload(self.h, k, FIELD_UF, a.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def set_current(self, k, uj):
+        a = np.ascontiguousarray(uj, dtype=np.float64)
+        assert a.shape == self.M + (4,)
+        self._ck(self.lib.nixb200_chunk_field_upload(self.h, k, FIELD_UJ, a.ctypes.data_as(C.POINTER(C.c_double))))
+
+    def get_field(self, k):
+        a = np.empty(self.M + (6,), dtype=np.float64)
+        self._ck(self.lib.nixb200_chunk_field_download(self.h, k, FIELD_UF, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+    def get_current(self, k):
+        a = np.empty(self.M + (4,), dtype=np.float64)
+        self._ck(self.lib.nixb200_chunk_field_download(self.h, k, FIELD_UJ, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+    def set_particles(self, s, per_chunk):
+        """per_chunk: list (one per local chunk) of [n][7] AoS arrays."""
+        assert len(per_chunk) == self.nchunk
+        npc = np.array([len(p) for p in per_chunk], dtype=np.int64)
+        if npc.sum() > 0:
+            flat = np.ascontiguousarray(np.concatenate([np.asarray(p, dtype=np.float64).reshape(-1, 7)
+                                                        for p in per_chunk]))
+        else:
+            flat = np.zeros((0, 7))
+        self.set_particles_flat(s, flat, npc)
+
+    def set_particles_flat(self, s, flat, npc):
+        flat = np.ascontiguousarray(flat, dtype=np.float64)
+        npc = np.ascontiguousarray(npc, dtype=np.int64)
+        self._ck(self.lib.nixb200_domain_set_particles(
+            self.h, s, flat.ctypes.data_as(C.POINTER(C.c_double)), npc.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def get_np(self, s):
+        a = np.zeros(self.nchunk, dtype=np.int64)
+        self._ck(self.lib.nixb200_domain_get_np(self.h, s, a.ctypes.data_as(C.POINTER(C.c_int64))))
+        return a
+
+    def get_particles(self, k, s):
+        n = C.c_int64(0)
+        self._ck(self.lib.nixb200_chunk_get_particles(self.h, k, s, None, 0, C.byref(n)))
+        out = np.empty((n.value, 7), dtype=np.float64)
+        if n.value:
+            self._ck(self.lib.nixb200_chunk_get_particles(
+                self.h, k, s, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n)))
+        return out
+
+    def get_pindex(self, k, s):
+        a = np.empty(self.Ng + 1, dtype=np.int32)
+        self._ck(self.lib.nixb200_chunk_get_pindex(self.h, k, s, a.ctypes.data_as(C.POINTER(C.c_int32))))
+        return a
+
+    def get_pcount(self, k, s):
+        a = np.empty((self.Ng + 1, 8), dtype=np.int32)
+        self._ck(self.lib.nixb200_chunk_get_pcount(self.h, k, s, a.ctypes.data_as(C.POINTER(C.c_int32))))
+        return a
+
+    # ---- the hot path ----
+    def sort(self):
+        self._ck(self.lib.nixb200_domain_sort(self.h))
+
+    def clear_current(self):
+        self._ck(self.lib.nixb200_domain_clear_current(self.h))
+
+    def push_deposit(self, delt):
+        self._ck(self.lib.nixb200_domain_push_deposit(self.h, float(delt)))
+
+    def exchange_current(self):
+        self._ck(self.lib.nixb200_domain_exchange_current(self.h))
+
+    def exchange_field(self):
+        self._ck(self.lib.nixb200_domain_exchange_field(self.h))
+
+    def migrate_sort(self):
+        self._ck(self.lib.nixb200_domain_migrate_sort(self.h))
+
+    def step(self, delt):
+        self._ck(self.lib.nixb200_domain_step(self.h, float(delt)))
+
+    # ---- per-chunk halo buffers in the reference's MpiBuffer layout ----
+    def halo_layout(self, mode):
+        bs = np.zeros(27, dtype=np.int32)
+        ba = np.zeros(27, dtype=np.int32)
+        self._ck(self.lib.nixb200_halo_layout(self.h, mode, bs.ctypes.data_as(C.POINTER(C.c_int)),
+                                              ba.ctypes.data_as(C.POINTER(C.c_int))))
+        return bs, ba
+
+    def halo_pack(self, k, mode):
+        bs, ba = self.halo_layout(mode)
+        buf = np.zeros(int(ba[26] + bs[26]), dtype=np.uint8)
+        self._ck(self.lib.nixb200_chunk_halo_pack(self.h, k, mode, buf.ctypes.data_as(C.c_void_p)))
+        return buf
+
+    def halo_unpack(self, k, mode, buf, nbvalid=None):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        pv = None
+        if nbvalid is not None:
+            v = np.ascontiguousarray(nbvalid, dtype=np.int32)
+            pv = v.ctypes.data_as(C.POINTER(C.c_int))
+        self._ck(self.lib.nixb200_chunk_halo_unpack(self.h, k, mode, buf.ctypes.data_as(C.c_void_p), pv))
+
+    def get_load(self):
+        ms = C.c_double(0)
+        self._ck(self.lib.nixb200_domain_get_load(self.h, C.byref(ms)))
+        return ms.value
+
+    def total_particles(self):
+        return int(self.lib.nixb200_domain_total_particles(self.h))

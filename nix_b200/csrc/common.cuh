@@ -1,0 +1,182 @@
+// common.cuh -- internal types shared by the sm_100a kernels of libnixb200.so
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/nixb200.h"
+
+namespace nixb200
+{
+constexpr int NC    = 7; // particle.hpp:18   components per particle (x y z ux uy uz id)
+constexpr int LANES = 8; // nix.hpp:105-108   NIX_SIMD_WIDTH: lane count of pcount[Ng+1][8]
+
+// ---------------------------------------------------------------------------------------------
+// geometry shared by all chunks of a domain (passed to kernels by value)
+// ---------------------------------------------------------------------------------------------
+struct Geo {
+  int    N[3];    // cells per chunk (z,y,x)
+  int    M[3];    // with ghosts
+  int    R[3];    // N+1: strides of XtensorParticle::flatindex (xtensor_particle.hpp:231-238)
+  int    nc[3];   // cells per axis that can hold particles: N + is_odd
+  int    nb, order, is_odd, half;
+  int    ncell;   // R[0]*R[1]*R[2]  flat indices in use
+  int    nchunk;  // local chunks
+  int    seg;     // cells per push work item along x
+  int    nseg;    // segments per row
+  int    nitem;   // work items per chunk = nc[0]*nc[1]*nseg
+  double del[3], rdel[3];
+  double glo[3], ghi[3], glen[3]; // global box (set_boundary_periodic, xtensor_particle.hpp:359-369)
+  double cc, rc;
+};
+
+// per-chunk constants, all precomputed on the host with the reference's expressions so that the
+// device never re-derives them with a different rounding (chunk.cpp:210-237,
+// xtensor_particle.hpp:332-334)
+struct ChunkGeo {
+  double lo[3], hi[3]; // chunk range [lo, hi)
+  double off[3];       // bin offset       lo - 0.5*del*is_odd
+  double hoff[3];      // half-grid offset lo - 0.5*del*(1-is_odd)
+  double imin[3];      // position of integer node 0 (cell centre): lo + 0.5*del
+  int    nbr[27];      // local index of the neighbour chunk, -1: none, -2-r: on rank r
+};
+
+// one species on one device: SoA particle store, double-buffered like xu/xv of the reference
+struct SpeciesDev {
+  double*  xu;    // [7][cap]
+  double*  xv;    // [7][cap]
+  int32_t* key;   // [cap]   (chunk*ncell + cell)*8 + lane, -1 = dropped / leaver
+  int32_t* ordl;  // [cap]   per-bin list of pre-sort local indices (for the stable rank)
+  int32_t* hist;  // [nchunk*ncell*8]      counts -> consumed as cursors by place
+  int32_t* start; // [nchunk*ncell*8 + 1]  exclusive scan of hist (global particle index)
+  int32_t* oob;   // [nchunk][8]  row Ng of the reference's pcount
+  int32_t* cbase; // [nchunk+1]   first particle of each chunk in xu
+  int32_t* cbase_new;
+  // migration
+  int32_t* blockdir; // [nchunk][nitem][27] leavers per push work item and direction
+  int32_t* sendcnt;  // [nchunk][27]
+  int32_t* msgoff;   // [nchunk][27]  first message slot of (chunk, dir)
+  int32_t* recvoff;  // [nchunk][27]  pre-sort local index of the first particle received in slot e
+  int32_t* nleave;   // [1] number of leaver records
+  int32_t* nmsg;     // [1] total message particles
+  int4*    lrec;     // [lcap] leaver records {i, chunk, item<<8|dir, rank in item}
+  double*  msg;      // [7][lcap] message payload (wrapped positions), SoA
+  int32_t* msgkey;   // [lcap]
+  int32_t* msgord;   // [lcap]
+  double   q, m;
+  int64_t  cap, lcap;
+};
+
+inline __host__ __device__ size_t soa(int comp, size_t cap, size_t i)
+{
+  return (size_t)comp * cap + i;
+}
+
+// ---------------------------------------------------------------------------------------------
+// arithmetic helpers.  STRICT = evaluate exactly as written (no FMA contraction) so that push
+// results are bit-identical to the reference's scalar templates compiled without contraction.
+// ---------------------------------------------------------------------------------------------
+template <bool S>
+__device__ __forceinline__ double mul(double a, double b)
+{
+  if constexpr (S) return __dmul_rn(a, b);
+  else return a * b;
+}
+template <bool S>
+__device__ __forceinline__ double add(double a, double b)
+{
+  if constexpr (S) return __dadd_rn(a, b);
+  else return a + b;
+}
+template <bool S>
+__device__ __forceinline__ double sub(double a, double b)
+{
+  if constexpr (S) return __dsub_rn(a, b);
+  else return a - b;
+}
+// a*b + c
+template <bool S>
+__device__ __forceinline__ double mad(double a, double b, double c)
+{
+  if constexpr (S) return __dadd_rn(__dmul_rn(a, b), c);
+  else return fma(a, b, c);
+}
+template <bool S>
+__device__ __forceinline__ double div_(double a, double b)
+{
+  if constexpr (S) return __ddiv_rn(a, b);
+  else return a / b;
+}
+template <bool S>
+__device__ __forceinline__ double sqrt_(double a)
+{
+  if constexpr (S) return __dsqrt_rn(a);
+  else return sqrt(a);
+}
+
+// primitives.hpp:46-58 -- always exact (counts and permutations must be bit-exact)
+__device__ __forceinline__ int digitize(double x, double xmin, double rdx)
+{
+  return (int)floor(__dmul_rn(__dsub_rn(x, xmin), rdx));
+}
+
+// ---------------------------------------------------------------------------------------------
+// host-side error plumbing
+// ---------------------------------------------------------------------------------------------
+void        set_error(const std::string& msg);
+extern int64_t g_launches;
+
+#define NIX_CUDA(call)                                                                           \
+  do {                                                                                           \
+    cudaError_t err__ = (call);                                                                  \
+    if (err__ != cudaSuccess) {                                                                  \
+      nixb200::set_error(std::string(#call) + ": " + cudaGetErrorString(err__) + " (" +          \
+                         __FILE__ + ":" + std::to_string(__LINE__) + ")");                       \
+      return 1;                                                                                  \
+    }                                                                                            \
+  } while (0)
+
+#define NIX_LAUNCHED()                                                                           \
+  do {                                                                                           \
+    nixb200::g_launches++;                                                                       \
+    NIX_CUDA(cudaGetLastError());                                                                \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (one per .cu file); all enqueue on `st` and return 0 / non-zero
+// ---------------------------------------------------------------------------------------------
+struct PushArgs {
+  Geo              geo;
+  const ChunkGeo*  cg;
+  const double*    uf; // [nchunk][Mz][My][Mx][6]
+  double*          uj; // [nchunk][Mz][My][Mx][4]
+  SpeciesDev       sp;
+  double           delt;
+  int*             err;
+};
+
+int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st);
+size_t push_smem_bytes(const Geo& g);
+
+int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
+int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
+int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
+                cudaStream_t st);
+size_t scan_tmp_bytes(size_t n);
+
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, cudaStream_t st);
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, cudaStream_t st);
+int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* buf, cudaStream_t st);
+int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
+                       const int* nbvalid_dev, cudaStream_t st);
+
+int launch_aos_to_soa(const double* aos, double* soa_base, size_t cap, size_t first, size_t n,
+                      cudaStream_t st);
+int launch_soa_to_aos(const double* soa_base, double* aos, size_t cap, size_t first, size_t n,
+                      cudaStream_t st);
+} // namespace nixb200

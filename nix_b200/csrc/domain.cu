@@ -1,0 +1,712 @@
+// domain.cu -- host side of libnixb200.so: the device-resident chunk set of one rank and the
+// extern "C" layer declared in include/nixb200.h.
+//
+// A domain owns, for a contiguous range of chunk ids (ChunkMap::get_rank, chunkmap.cpp:156-164):
+//   uf [nchunk][Mz][My][Mx][6], uj [nchunk][Mz][My][Mx][4]      -- each chunk with its own ghosts,
+//                                                                  exactly the reference's arrays
+//   per species: SoA particles of ALL chunks concatenated in chunk order (xu / xv double buffer),
+//                the global (chunk, cell, lane) histogram and its scan (= pcount / pindex).
+#include "common.cuh"
+
+#include <algorithm>
+#include <cstring>
+#include <mutex>
+
+namespace nixb200
+{
+static thread_local std::string g_error;
+int64_t                         g_launches = 0;
+
+void set_error(const std::string& msg)
+{
+  g_error = msg;
+}
+
+struct Domain {
+  nixb200_domain_desc     desc;
+  Geo                     geo;
+  std::vector<ChunkGeo>   cg_host;
+  ChunkGeo*               cg_dev = nullptr;
+  double*                 uf     = nullptr;
+  double*                 uj     = nullptr;
+  std::vector<SpeciesDev> sp;
+  cudaStream_t            stream = nullptr;
+  CUtensorMap             tmap;
+  void*                   scan_tmp = nullptr;
+  int*                    err_dev  = nullptr;
+  int*                    nbvalid_dev = nullptr;
+  double*                 halo_buf    = nullptr; // device staging for the per-chunk buffer API
+  size_t                  halo_buf_bytes = 0;
+  cudaEvent_t             ev0 = nullptr, ev1 = nullptr;
+  bool                    timed = false;
+  size_t                  cells_per_chunk = 0;
+  bool                    particles_set   = false;
+};
+
+static int required_nb(int order)
+{
+  return (order == 3) ? 3 : 2; // stencil extents of gather and deposit, DESIGN.md section 2
+}
+
+static int make_tensor_map(Domain* d)
+{
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                CUtensorMapFloatOOBfill);
+  void*                            fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  NIX_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return 1;
+  }
+  const Geo&  g       = d->geo;
+  const int   NW      = g.order + 2;
+  cuuint64_t  dims[5] = {6, (cuuint64_t)g.M[2], (cuuint64_t)g.M[1], (cuuint64_t)g.M[0], (cuuint64_t)g.nchunk};
+  cuuint64_t  strides[4] = {48, (cuuint64_t)g.M[2] * 48, (cuuint64_t)g.M[1] * g.M[2] * 48,
+                            (cuuint64_t)g.M[0] * g.M[1] * g.M[2] * 48};
+  cuuint32_t  box[5]  = {6, (cuuint32_t)(g.seg + NW - 1), (cuuint32_t)NW, (cuuint32_t)NW, 1};
+  cuuint32_t  estr[5] = {1, 1, 1, 1, 1};
+  CUresult    r = ((encode_fn)fn)(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, d->uf, dims, strides, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 1;
+  }
+  return 0;
+}
+
+static int free_species(SpeciesDev& s)
+{
+  void* ptrs[] = {s.xu,      s.xv,     s.key,    s.ordl,  s.hist,   s.start, s.oob,    s.cbase, s.cbase_new,
+                  s.blockdir, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey,
+                  s.msgord};
+  for (void* p : ptrs)
+    if (p) cudaFree(p);
+  std::memset(&s, 0, sizeof(s));
+  return 0;
+}
+
+static int alloc_species_fixed(Domain* d, SpeciesDev& s)
+{
+  const Geo&   g = d->geo;
+  const size_t n = (size_t)g.nchunk * g.ncell * LANES;
+  NIX_CUDA(cudaMalloc(&s.hist, sizeof(int32_t) * n));
+  NIX_CUDA(cudaMalloc(&s.start, sizeof(int32_t) * (n + 4)));
+  NIX_CUDA(cudaMalloc(&s.oob, sizeof(int32_t) * g.nchunk * LANES));
+  NIX_CUDA(cudaMalloc(&s.cbase, sizeof(int32_t) * (g.nchunk + 1)));
+  NIX_CUDA(cudaMalloc(&s.cbase_new, sizeof(int32_t) * (g.nchunk + 1)));
+  NIX_CUDA(cudaMalloc(&s.blockdir, sizeof(int32_t) * (size_t)g.nchunk * g.nitem * 27));
+  NIX_CUDA(cudaMalloc(&s.sendcnt, sizeof(int32_t) * g.nchunk * 27));
+  NIX_CUDA(cudaMalloc(&s.msgoff, sizeof(int32_t) * g.nchunk * 27));
+  NIX_CUDA(cudaMalloc(&s.recvoff, sizeof(int32_t) * g.nchunk * 27));
+  NIX_CUDA(cudaMalloc(&s.nleave, sizeof(int32_t)));
+  NIX_CUDA(cudaMalloc(&s.nmsg, sizeof(int32_t)));
+  NIX_CUDA(cudaMemset(s.hist, 0, sizeof(int32_t) * n));
+  NIX_CUDA(cudaMemset(s.start, 0, sizeof(int32_t) * (n + 4)));
+  NIX_CUDA(cudaMemset(s.oob, 0, sizeof(int32_t) * g.nchunk * LANES));
+  NIX_CUDA(cudaMemset(s.cbase, 0, sizeof(int32_t) * (g.nchunk + 1)));
+  NIX_CUDA(cudaMemset(s.cbase_new, 0, sizeof(int32_t) * (g.nchunk + 1)));
+  NIX_CUDA(cudaMemset(s.blockdir, 0, sizeof(int32_t) * (size_t)g.nchunk * g.nitem * 27));
+  NIX_CUDA(cudaMemset(s.sendcnt, 0, sizeof(int32_t) * g.nchunk * 27));
+  NIX_CUDA(cudaMemset(s.nleave, 0, sizeof(int32_t)));
+  NIX_CUDA(cudaMemset(s.nmsg, 0, sizeof(int32_t)));
+  return 0;
+}
+
+static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
+{
+  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.msgord};
+  for (void* p : old)
+    if (p) cudaFree(p);
+  double f = d->desc.capacity_factor > 0 ? d->desc.capacity_factor : 1.25;
+  if (f < 1.0) f = 1.0;
+  int64_t cap = (int64_t)((double)ntot * f) + 1024;
+  cap         = (cap + 127) / 128 * 128;
+  if (cap >= (int64_t)1 << 31) {
+    set_error("more than 2^31 particles of one species on one device");
+    return 1;
+  }
+  int64_t lcap = std::max<int64_t>(4096, cap / 4);
+  lcap         = (lcap + 127) / 128 * 128;
+  s.cap        = cap;
+  s.lcap       = lcap;
+  NIX_CUDA(cudaMalloc(&s.xu, sizeof(double) * NC * cap));
+  NIX_CUDA(cudaMalloc(&s.xv, sizeof(double) * NC * cap));
+  NIX_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * cap));
+  NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * cap));
+  NIX_CUDA(cudaMalloc(&s.lrec, sizeof(int4) * lcap));
+  NIX_CUDA(cudaMalloc(&s.msg, sizeof(double) * NC * lcap));
+  NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
+  NIX_CUDA(cudaMalloc(&s.msgord, sizeof(int32_t) * lcap));
+  NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
+  NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
+  return 0;
+}
+
+static int check_chunk(Domain* d, int k)
+{
+  if (!d) {
+    set_error("null domain");
+    return 1;
+  }
+  if (k < 0 || k >= d->geo.nchunk) {
+    set_error("chunk index out of range");
+    return 1;
+  }
+  return 0;
+}
+
+static int check_species(Domain* d, int is)
+{
+  if (!d) {
+    set_error("null domain");
+    return 1;
+  }
+  if (is < 0 || is >= (int)d->sp.size()) {
+    set_error("species index out of range");
+    return 1;
+  }
+  return 0;
+}
+
+static int do_sort_species(Domain* d, SpeciesDev& s)
+{
+  if (launch_sort(d->geo, d->cg_dev, s, d->err_dev, d->scan_tmp, d->stream)) return 1;
+  std::swap(s.xu, s.xv);           // XtensorParticle::swap, xtensor_particle.hpp:120-123
+  std::swap(s.cbase, s.cbase_new); // Np = pindex(Ng), xtensor_particle.hpp:320
+  return 0;
+}
+} // namespace nixb200
+
+using namespace nixb200;
+
+static Domain* D(nixb200_domain* d)
+{
+  return reinterpret_cast<Domain*>(d);
+}
+
+extern "C" {
+
+const char* nixb200_last_error(void)
+{
+  return g_error.c_str();
+}
+
+const char* nixb200_version(void)
+{
+  return "nixb200 0.1 (sm_100a)";
+}
+
+int64_t nixb200_launch_count(void)
+{
+  return g_launches;
+}
+
+int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, const double* q,
+                          const double* m, nixb200_domain** out)
+{
+  if (!desc || !coord || !q || !m || !out) {
+    set_error("null argument");
+    return 1;
+  }
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libnixb200 has no CPU fallback");
+    return 1;
+  }
+  NIX_CUDA(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  NIX_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) {
+    set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+              "; this library is built for sm_100a only");
+    return 1;
+  }
+  if (desc->order < 1 || desc->order > 3) {
+    set_error("order must be 1, 2 or 3");
+    return 1;
+  }
+  if (desc->nb < required_nb(desc->order)) {
+    set_error("boundary margin too small for this order (need 2 for order 1-2, 3 for order 3)");
+    return 1;
+  }
+  if (desc->ns < 1 || desc->id_end <= desc->id_begin) {
+    set_error("empty domain");
+    return 1;
+  }
+  for (int a = 0; a < 3; a++) {
+    if (desc->dims[a] < desc->nb || desc->cdims[a] < 1) {
+      set_error("chunk dims must be >= boundary margin and cdims >= 1");
+      return 1;
+    }
+  }
+
+  Domain* d = new Domain();
+  d->desc   = *desc;
+  Geo& g    = d->geo;
+  std::memset(&g, 0, sizeof(g));
+  g.nb     = desc->nb;
+  g.order  = desc->order;
+  g.is_odd = desc->order % 2;
+  g.half   = desc->order / 2;
+  g.nchunk = desc->id_end - desc->id_begin;
+  for (int a = 0; a < 3; a++) {
+    g.N[a]    = desc->dims[a];
+    g.M[a]    = desc->dims[a] + 2 * desc->nb;
+    g.R[a]    = desc->dims[a] + 1;
+    g.nc[a]   = g.R[a];
+    g.del[a]  = desc->del[a];
+    g.rdel[a] = 1 / desc->del[a];
+    // chunk.cpp:220-236 and xtensor_particle.hpp:361-369
+    g.glo[a]  = 0.0;
+    g.ghi[a]  = (desc->cdims[a] * desc->dims[a]) * desc->del[a];
+    g.glen[a] = 1 * (g.ghi[a] - g.glo[a]);
+  }
+  g.cc    = desc->cc;
+  g.rc    = 1 / desc->cc;
+  g.ncell = g.R[0] * g.R[1] * g.R[2];
+  {
+    int r  = g.R[2];
+    int ns = (r + 39) / 40;
+    g.seg  = (r + ns - 1) / ns;
+    g.nseg = (r + g.seg - 1) / g.seg;
+  }
+  g.nitem = g.R[0] * g.R[1] * g.nseg;
+  if ((double)g.nchunk * g.ncell * LANES >= 2147483000.0) {
+    delete d;
+    set_error("key space (nchunk*ncell*8) exceeds int32");
+    return 1;
+  }
+  if (push_smem_bytes(g) > 200 * 1024) {
+    delete d;
+    set_error("push tile does not fit shared memory");
+    return 1;
+  }
+
+  // neighbour table from the id -> coordinate map (ChunkVector::set_neighbors, chunkvector.hpp:56-81;
+  // periodic neighbour coordinates, chunkmap.cpp:142-154)
+  const int* cd  = desc->cdims;
+  const int  ncid = cd[0] * cd[1] * cd[2];
+  std::vector<int> grid2id(ncid, -1);
+  for (int id = 0; id < ncid; id++) {
+    const int* c = &coord[3 * id];
+    if (c[0] < 0 || c[0] >= cd[0] || c[1] < 0 || c[1] >= cd[1] || c[2] < 0 || c[2] >= cd[2]) {
+      delete d;
+      set_error("chunk coordinate out of range");
+      return 1;
+    }
+    grid2id[(c[0] * cd[1] + c[1]) * cd[2] + c[2]] = id;
+  }
+  d->cg_host.resize(g.nchunk);
+  for (int k = 0; k < g.nchunk; k++) {
+    const int* c  = &coord[3 * (desc->id_begin + k)];
+    ChunkGeo&  cg = d->cg_host[k];
+    for (int a = 0; a < 3; a++) {
+      int    off = c[a] * g.N[a];
+      double del = g.del[a];
+      cg.lo[a]   = off * del;                  // chunk.cpp:217,224,231
+      cg.hi[a]   = off * del + g.N[a] * del;   // chunk.cpp:218,225,232
+      cg.off[a]  = cg.lo[a] - 0.5 * del * g.is_odd;       // xtensor_particle.hpp:332-334
+      cg.hoff[a] = cg.lo[a] - 0.5 * del * (1 - g.is_odd); // ref_driver.cpp
+      cg.imin[a] = cg.lo[a] + 0.5 * del;
+    }
+    for (int s = 0; s < 27; s++) {
+      int e[3] = {s / 9 - 1, (s / 3) % 3 - 1, s % 3 - 1};
+      int n[3];
+      for (int a = 0; a < 3; a++) n[a] = ((c[a] + e[a]) % cd[a] + cd[a]) % cd[a];
+      int id = grid2id[(n[0] * cd[1] + n[1]) * cd[2] + n[2]];
+      if (id < 0) cg.nbr[s] = -1;
+      else if (id >= desc->id_begin && id < desc->id_end) cg.nbr[s] = id - desc->id_begin;
+      else cg.nbr[s] = -2; // lives on another rank
+    }
+  }
+
+  d->cells_per_chunk = (size_t)g.M[0] * g.M[1] * g.M[2];
+  auto fail = [&](const char* what) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(cudaGetLastError()));
+    nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(d));
+    return 1;
+  };
+  if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+  if (cudaMalloc(&d->cg_dev, sizeof(ChunkGeo) * g.nchunk) != cudaSuccess) return fail("cudaMalloc");
+  if (cudaMemcpy(d->cg_dev, d->cg_host.data(), sizeof(ChunkGeo) * g.nchunk, cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail("cudaMemcpy");
+  if (cudaMalloc(&d->uf, sizeof(double) * 6 * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uf");
+  if (cudaMalloc(&d->uj, sizeof(double) * 4 * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uj");
+  cudaMemset(d->uf, 0, sizeof(double) * 6 * d->cells_per_chunk * g.nchunk);
+  cudaMemset(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * g.nchunk);
+  if (cudaMalloc(&d->scan_tmp, scan_tmp_bytes((size_t)g.nchunk * g.ncell * LANES)) != cudaSuccess) return fail("cudaMalloc scan");
+  if (cudaMalloc(&d->err_dev, sizeof(int)) != cudaSuccess) return fail("cudaMalloc err");
+  cudaMemset(d->err_dev, 0, sizeof(int));
+  if (cudaMalloc(&d->nbvalid_dev, sizeof(int) * 27) != cudaSuccess) return fail("cudaMalloc");
+  d->halo_buf_bytes = sizeof(double) * 6 * d->cells_per_chunk;
+  if (cudaMalloc(&d->halo_buf, d->halo_buf_bytes) != cudaSuccess) return fail("cudaMalloc halo");
+  cudaEventCreate(&d->ev0);
+  cudaEventCreate(&d->ev1);
+
+  d->sp.resize(desc->ns);
+  for (int is = 0; is < desc->ns; is++) {
+    std::memset(&d->sp[is], 0, sizeof(SpeciesDev));
+    d->sp[is].q = q[is];
+    d->sp[is].m = m[is];
+    if (alloc_species_fixed(d, d->sp[is]) || alloc_species_particles(d, d->sp[is], 0)) {
+      std::string e = g_error;
+      nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(d));
+      set_error(e);
+      return 1;
+    }
+  }
+  if (make_tensor_map(d)) {
+    std::string e = g_error;
+    nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(d));
+    set_error(e);
+    return 1;
+  }
+  *out = reinterpret_cast<nixb200_domain*>(d);
+  return 0;
+}
+
+int nixb200_domain_destroy(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 0;
+  cudaDeviceSynchronize();
+  for (auto& s : d->sp) free_species(s);
+  if (d->cg_dev) cudaFree(d->cg_dev);
+  if (d->uf) cudaFree(d->uf);
+  if (d->uj) cudaFree(d->uj);
+  if (d->scan_tmp) cudaFree(d->scan_tmp);
+  if (d->err_dev) cudaFree(d->err_dev);
+  if (d->nbvalid_dev) cudaFree(d->nbvalid_dev);
+  if (d->halo_buf) cudaFree(d->halo_buf);
+  if (d->ev0) cudaEventDestroy(d->ev0);
+  if (d->ev1) cudaEventDestroy(d->ev1);
+  if (d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+  return 0;
+}
+
+int nixb200_domain_set_stream(nixb200_domain* dd, void* cuda_stream)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  // the previously owned stream (if any) is leaked on purpose: it may be the caller's
+  d->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  return 0;
+}
+
+int nixb200_domain_synchronize(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_domain_check(nixb200_domain* dd, int* errbits)
+{
+  Domain* d = D(dd);
+  if (!d || !errbits) return 1;
+  NIX_CUDA(cudaMemcpyAsync(errbits, d->err_dev, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaMemsetAsync(d->err_dev, 0, sizeof(int), d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_chunk_field_upload(nixb200_domain* dd, int k, int which, const double* host)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || !host) return 1;
+  int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  double* dst = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
+  NIX_CUDA(cudaMemcpyAsync(dst, host, sizeof(double) * nc * d->cells_per_chunk, cudaMemcpyHostToDevice, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* host)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || !host) return 1;
+  int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const double* src = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
+  NIX_CUDA(cudaMemcpyAsync(host, src, sizeof(double) * nc * d->cells_per_chunk, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_aos, const int64_t* np_chunk)
+{
+  Domain* d = D(dd);
+  if (check_species(d, is) || !np_chunk) return 1;
+  const Geo&           g = d->geo;
+  std::vector<int32_t> cbase(g.nchunk + 1, 0);
+  int64_t              ntot = 0;
+  for (int k = 0; k < g.nchunk; k++) {
+    if (np_chunk[k] < 0) {
+      set_error("negative particle count");
+      return 1;
+    }
+    ntot += np_chunk[k];
+    if (ntot >= ((int64_t)1 << 31) - 4096) {
+      set_error("more than 2^31 particles of one species on one device");
+      return 1;
+    }
+    cbase[k + 1] = (int32_t)ntot;
+  }
+  SpeciesDev& s = d->sp[is];
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  if (alloc_species_particles(d, s, ntot)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(s.cbase, cbase.data(), sizeof(int32_t) * (g.nchunk + 1), cudaMemcpyHostToDevice, d->stream));
+  if (ntot > 0) {
+    if (!xu_aos) {
+      set_error("null particle array");
+      return 1;
+    }
+    // AoS staged in the xv buffer (same byte size), transposed into xu
+    NIX_CUDA(cudaMemcpyAsync(s.xv, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyHostToDevice, d->stream));
+    if (launch_aos_to_soa(s.xv, s.xu, s.cap, 0, (size_t)ntot, d->stream)) return 1;
+  }
+  // start[] of an unsorted container: only the chunk bases are meaningful until domain_sort()
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  d->particles_set = true;
+  return 0;
+}
+
+int nixb200_domain_get_np(nixb200_domain* dd, int is, int64_t* np_chunk)
+{
+  Domain* d = D(dd);
+  if (check_species(d, is) || !np_chunk) return 1;
+  const Geo&           g = d->geo;
+  std::vector<int32_t> cbase(g.nchunk + 1);
+  NIX_CUDA(cudaMemcpyAsync(cbase.data(), d->sp[is].cbase, sizeof(int32_t) * (g.nchunk + 1), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  for (int k = 0; k < g.nchunk; k++) np_chunk[k] = cbase[k + 1] - cbase[k];
+  return 0;
+}
+
+int nixb200_chunk_get_particles(nixb200_domain* dd, int k, int is, double* xu_aos, int64_t max_np, int64_t* np)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || check_species(d, is) || !np) return 1;
+  SpeciesDev& s = d->sp[is];
+  int32_t     cb[2];
+  NIX_CUDA(cudaMemcpyAsync(cb, s.cbase + k, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  int64_t n = cb[1] - cb[0];
+  *np       = n;
+  if (!xu_aos || n == 0) return 0;
+  if (n > max_np) {
+    set_error("output buffer too small");
+    return 1;
+  }
+  // xv is scratch between steps (the reference's "temporary particle array", xtensor_particle.hpp:16)
+  if (launch_soa_to_aos(s.xu, s.xv, s.cap, (size_t)cb[0], (size_t)n, d->stream)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(xu_aos, s.xv, sizeof(double) * NC * n, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// expand the device's compact rows [0, ncell) (+ out-of-bounds row) to the reference's [Ng+1] layout
+int nixb200_chunk_get_pindex(nixb200_domain* dd, int k, int is, int32_t* pindex)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || check_species(d, is) || !pindex) return 1;
+  const Geo&           g = d->geo;
+  SpeciesDev&          s = d->sp[is];
+  const size_t         n = (size_t)g.ncell * LANES;
+  std::vector<int32_t> st(n + 1);
+  NIX_CUDA(cudaMemcpyAsync(st.data(), s.start + (size_t)k * n, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  const int Ng   = (int)d->cells_per_chunk;
+  const int base = st[0];
+  const int npk  = st[n] - base;
+  for (int ii = 0; ii <= Ng; ii++) pindex[ii] = (ii < g.ncell) ? st[(size_t)ii * LANES] - base : npk;
+  return 0;
+}
+
+int nixb200_chunk_get_pcount(nixb200_domain* dd, int k, int is, int32_t* pcount)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || check_species(d, is) || !pcount) return 1;
+  const Geo&           g = d->geo;
+  SpeciesDev&          s = d->sp[is];
+  const size_t         n = (size_t)g.ncell * LANES;
+  std::vector<int32_t> st(n + 1);
+  int32_t              oob[LANES];
+  NIX_CUDA(cudaMemcpyAsync(st.data(), s.start + (size_t)k * n, sizeof(int32_t) * (n + 1), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaMemcpyAsync(oob, s.oob + (size_t)k * LANES, sizeof(int32_t) * LANES, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  const int Ng = (int)d->cells_per_chunk;
+  std::memset(pcount, 0, sizeof(int32_t) * LANES * ((size_t)Ng + 1));
+  for (size_t j = 0; j < n; j++) pcount[j] = st[j + 1] - st[j];
+  for (int l = 0; l < LANES; l++) pcount[(size_t)Ng * LANES + l] = oob[l];
+  return 0;
+}
+
+int nixb200_domain_sort(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  for (auto& s : d->sp) {
+    if (launch_count_only(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
+    if (do_sort_species(d, s)) return 1;
+  }
+  return 0;
+}
+
+int nixb200_domain_clear_current(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  NIX_CUDA(cudaMemsetAsync(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * d->geo.nchunk, d->stream));
+  return 0;
+}
+
+int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  NIX_CUDA(cudaEventRecord(d->ev0, d->stream));
+  for (auto& s : d->sp) {
+    PushArgs a;
+    a.geo  = d->geo;
+    a.cg   = d->cg_dev;
+    a.uf   = d->uf;
+    a.uj   = d->uj;
+    a.sp   = s;
+    a.delt = delt;
+    a.err  = d->err_dev;
+    if (launch_push_deposit(a, &d->tmap, d->desc.strict_fp != 0, d->stream)) return 1;
+  }
+  NIX_CUDA(cudaEventRecord(d->ev1, d->stream));
+  d->timed = true;
+  return 0;
+}
+
+int nixb200_domain_exchange_current(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  return launch_halo_current(d->geo, d->cg_dev, d->uj, d->stream);
+}
+
+int nixb200_domain_exchange_field(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  return launch_halo_field(d->geo, d->cg_dev, d->uf, d->stream);
+}
+
+int nixb200_domain_migrate_sort(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  for (auto& s : d->sp) {
+    if (launch_migrate(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
+    if (do_sort_species(d, s)) return 1;
+  }
+  return 0;
+}
+
+int nixb200_domain_step(nixb200_domain* dd, double delt)
+{
+  if (nixb200_domain_clear_current(dd)) return 1;
+  if (nixb200_domain_push_deposit(dd, delt)) return 1;
+  if (nixb200_domain_exchange_current(dd)) return 1;
+  if (nixb200_domain_exchange_field(dd)) return 1;
+  if (nixb200_domain_migrate_sort(dd)) return 1;
+  return 0;
+}
+
+int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufaddr27)
+{
+  Domain* d = D(dd);
+  if (!d || !bufsize27 || !bufaddr27) return 1;
+  if (mode != NIXB200_MODE_FIELD && mode != NIXB200_MODE_CURRENT) {
+    set_error("halo_layout: fixed layouts exist for field and current only");
+    return 1;
+  }
+  // Chunk::set_mpi_buffer, chunk.cpp:257-286 (headbyte 0, elembyte 8*ncomp)
+  const Geo& g    = d->geo;
+  const int  elem = 8 * ((mode == NIXB200_MODE_FIELD) ? 6 : 4);
+  int        size = 0;
+  for (int s = 0; s < 27; s++) {
+    bufaddr27[s] = size;
+    if (s == 13) {
+      bufsize27[s] = 0;
+      continue;
+    }
+    int e[3] = {s / 9, (s / 3) % 3, s % 3};
+    int cnt  = 1;
+    for (int a = 0; a < 3; a++) cnt *= (e[a] == 1) ? g.N[a] : g.nb;
+    bufsize27[s] = elem * cnt;
+    size += bufsize27[s];
+  }
+  return 0;
+}
+
+int nixb200_chunk_halo_pack(nixb200_domain* dd, int k, int mode, void* host_sendbuf)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || !host_sendbuf) return 1;
+  int bs[27], ba[27];
+  if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
+  size_t total = (size_t)ba[26] + bs[26];
+  const double* data = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
+  if (launch_halo_pack(d->geo, k, mode, data, d->halo_buf, d->stream)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(host_sendbuf, d->halo_buf, total, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_chunk_halo_unpack(nixb200_domain* dd, int k, int mode, const void* host_recvbuf, const int* nbvalid27)
+{
+  Domain* d = D(dd);
+  if (check_chunk(d, k) || !host_recvbuf) return 1;
+  int bs[27], ba[27];
+  if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
+  size_t total = (size_t)ba[26] + bs[26];
+  int    valid[27];
+  for (int s = 0; s < 27; s++) valid[s] = nbvalid27 ? nbvalid27[s] : 1;
+  NIX_CUDA(cudaMemcpyAsync(d->nbvalid_dev, valid, sizeof(valid), cudaMemcpyHostToDevice, d->stream));
+  NIX_CUDA(cudaMemcpyAsync(d->halo_buf, host_recvbuf, total, cudaMemcpyHostToDevice, d->stream));
+  double* data = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
+  if (launch_halo_unpack(d->geo, k, mode, data, d->halo_buf, d->nbvalid_dev, d->stream)) return 1;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_domain_get_load(nixb200_domain* dd, double* ms)
+{
+  Domain* d = D(dd);
+  if (!d || !ms) return 1;
+  *ms = 0.0;
+  if (!d->timed) return 0;
+  NIX_CUDA(cudaEventSynchronize(d->ev1));
+  float t = 0.f;
+  NIX_CUDA(cudaEventElapsedTime(&t, d->ev0, d->ev1));
+  *ms = t;
+  return 0;
+}
+
+int64_t nixb200_domain_total_particles(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return -1;
+  int64_t tot = 0;
+  for (auto& s : d->sp) {
+    int32_t n = 0;
+    if (cudaMemcpyAsync(&n, s.cbase + d->geo.nchunk, sizeof(int32_t), cudaMemcpyDeviceToHost, d->stream) != cudaSuccess) return -1;
+    if (cudaStreamSynchronize(d->stream) != cudaSuccess) return -1;
+    tot += n;
+  }
+  return tot;
+}
+
+} // extern "C"

@@ -1,0 +1,270 @@
+// halo.cu -- E/B and J ghost-cell exchange between chunks (sm_100a)
+//
+// Replaces Chunk::{pack,begin,end,unpack}_bc_exchange (chunk.hpp:435-586) with
+//   XtensorHaloField3D    copy   interior slab of the neighbour -> my ghost slab   xtensor_halo3d.hpp:28-70
+//   XtensorHaloCurrent3D  add    ghost slab of the neighbour    -> my interior slab xtensor_halo3d.hpp:86-128
+// for every pair of chunks living on the same device, without any intermediate buffer: each thread
+// owns one destination cell and GATHERS from the neighbour chunk.  For the current the gather runs
+// over the 26 directions in the reference's unpack order (iz, iy, ix ascending, chunk.hpp:480-499),
+// so every interior cell sees the same sequence of additions as the reference: bit-exact, no atomics.
+//
+// Slab tables (chunk.cpp:171-207), per axis with Lb = nb, Ub = nb+N-1:
+//   send[0] = [Lb, Lb+nb-1]   send[1] = [Lb, Ub]   send[2] = [Ub-nb+1, Ub]
+//   recv[0] = [Lb-nb, Lb-1]   recv[1] = [Lb, Ub]   recv[2] = [Ub+1, Ub+nb]
+// A message sent in direction d is received in slot 26-d of the neighbour (chunk.hpp:532-554).
+//
+// The *_buf kernels move the same slabs to / from one contiguous buffer in the reference's
+// MpiBuffer layout (chunk.cpp:257-286); they serve neighbours on other ranks and the drop-in
+// per-chunk API.
+#include "common.cuh"
+
+namespace nixb200
+{
+namespace
+{
+struct SlotTable {
+  int addr[27]; // offset in doubles of each slot inside the buffer
+};
+
+__device__ __forceinline__ size_t cell_off(const Geo& g, int ch, int iz, int iy, int ix)
+{
+  return (((size_t)ch * g.M[0] + iz) * g.M[1] + iy) * g.M[2] + ix;
+}
+
+// ---- same-device exchange ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __restrict__ cg, double* uf)
+{
+  const int ch    = blockIdx.y;
+  const int ncell = g.M[0] * g.M[1] * g.M[2];
+  const int Lb = g.nb;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += gridDim.x * blockDim.x) {
+    int ix = t % g.M[2];
+    int iy = (t / g.M[2]) % g.M[1];
+    int iz = t / (g.M[2] * g.M[1]);
+    int i[3] = {iz, iy, ix};
+    int e[3], s[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      int Ub = Lb + g.N[a] - 1;
+      e[a]   = (i[a] < Lb) ? 0 : ((i[a] > Ub) ? 2 : 1);
+      s[a]   = i[a] + (1 - e[a]) * g.N[a]; // ghost low <- neighbour's high interior, and vice versa
+    }
+    int slot = 9 * e[0] + 3 * e[1] + e[2];
+    if (slot == 13) continue;
+    int nb = cg[ch].nbr[slot];
+    if (nb < 0) continue;
+    const double2* src = reinterpret_cast<const double2*>(uf + cell_off(g, nb, s[0], s[1], s[2]) * 6);
+    double2*       dst = reinterpret_cast<double2*>(uf + cell_off(g, ch, iz, iy, ix) * 6);
+    double2        a = src[0], b = src[1], c = src[2];
+    dst[0] = a;
+    dst[1] = b;
+    dst[2] = c;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __restrict__ cg, double* uj)
+{
+  const int ch    = blockIdx.y;
+  const int ncell = g.N[0] * g.N[1] * g.N[2];
+  const int Lb = g.nb, nbw = g.nb;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += gridDim.x * blockDim.x) {
+    int i[3];
+    i[2] = t % g.N[2] + Lb;
+    i[1] = (t / g.N[2]) % g.N[1] + Lb;
+    i[0] = t / (g.N[2] * g.N[1]) + Lb;
+    bool lowm[3], higm[3];
+    bool any = false;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      int Ub  = Lb + g.N[a] - 1;
+      lowm[a] = i[a] <= Lb + nbw - 1;
+      higm[a] = i[a] >= Ub - nbw + 1;
+      any     = any || lowm[a] || higm[a];
+    }
+    if (!any) continue;
+    double2* dst = reinterpret_cast<double2*>(uj + cell_off(g, ch, i[0], i[1], i[2]) * 4);
+    double2  v0 = dst[0], v1 = dst[1];
+    for (int slot = 0; slot < 27; slot++) {
+      if (slot == 13) continue;
+      int  e[3] = {slot / 9, (slot / 3) % 3, slot % 3};
+      bool in   = true;
+      int  s[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        in   = in && (e[a] == 1 || (e[a] == 0 && lowm[a]) || (e[a] == 2 && higm[a]));
+        s[a] = i[a] + (1 - e[a]) * g.N[a]; // my low interior <- neighbour's high ghost, and vice versa
+      }
+      if (!in) continue;
+      int nb = cg[ch].nbr[slot];
+      if (nb < 0) continue;
+      const double2* src = reinterpret_cast<const double2*>(uj + cell_off(g, nb, s[0], s[1], s[2]) * 4);
+      double2        a = src[0], b = src[1];
+      // std::plus(buffer, cell)  xtensor_halo3d.hpp:125
+      v0.x = __dadd_rn(a.x, v0.x);
+      v0.y = __dadd_rn(a.y, v0.y);
+      v1.x = __dadd_rn(b.x, v1.x);
+      v1.y = __dadd_rn(b.y, v1.y);
+    }
+    dst[0] = v0;
+    dst[1] = v1;
+  }
+}
+
+// ---- buffer (MpiBuffer layout) pack / unpack of one chunk ----------------------------------------
+__device__ __forceinline__ void slab_bounds(const Geo& g, int a, int e, bool recv, int& lo, int& n)
+{
+  const int Lb = g.nb, Ub = g.nb + g.N[a] - 1;
+  if (e == 1) {
+    lo = Lb;
+    n  = g.N[a];
+  } else if (recv) {
+    lo = (e == 0) ? Lb - g.nb : Ub + 1;
+    n  = g.nb;
+  } else {
+    lo = (e == 0) ? Lb : Ub - g.nb + 1;
+    n  = g.nb;
+  }
+}
+
+// pack: field packs the SEND slabs (interior), current packs the RECV slabs (ghost)
+__global__ void __launch_bounds__(256) k_halo_pack(Geo g, int ch, int ncomp, bool recv_slab,
+                                                   const double* __restrict__ data, SlotTable tab,
+                                                   double* __restrict__ buf)
+{
+  const int slot = blockIdx.y;
+  if (slot == 13) return;
+  int lo[3], n[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) slab_bounds(g, a, (a == 0) ? slot / 9 : (a == 1 ? (slot / 3) % 3 : slot % 3), recv_slab, lo[a], n[a]);
+  const int total = n[0] * n[1] * n[2] * ncomp;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int c  = t % ncomp;
+    int r  = t / ncomp;
+    int ix = r % n[2] + lo[2];
+    int iy = (r / n[2]) % n[1] + lo[1];
+    int iz = r / (n[2] * n[1]) + lo[0];
+    buf[tab.addr[slot] + t] = data[cell_off(g, ch, iz, iy, ix) * ncomp + c];
+  }
+}
+
+// unpack field: one thread per ghost value, reads the unique slot that covers it
+__global__ void __launch_bounds__(256) k_halo_unpack_field(Geo g, int ch, double* __restrict__ uf,
+                                                           SlotTable tab, const double* __restrict__ buf,
+                                                           const int* __restrict__ nbvalid)
+{
+  const int ncell = g.M[0] * g.M[1] * g.M[2];
+  const int Lb = g.nb;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += gridDim.x * blockDim.x) {
+    int i[3] = {t / (g.M[2] * g.M[1]), (t / g.M[2]) % g.M[1], t % g.M[2]};
+    int e[3], lo[3], n[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      int Ub = Lb + g.N[a] - 1;
+      e[a]   = (i[a] < Lb) ? 0 : ((i[a] > Ub) ? 2 : 1);
+      slab_bounds(g, a, e[a], true, lo[a], n[a]);
+    }
+    int slot = 9 * e[0] + 3 * e[1] + e[2];
+    if (slot == 13 || !nbvalid[slot]) continue;
+    size_t r   = ((size_t)(i[0] - lo[0]) * n[1] + (i[1] - lo[1])) * n[2] + (i[2] - lo[2]);
+    double* dst = uf + cell_off(g, ch, i[0], i[1], i[2]) * 6;
+#pragma unroll
+    for (int c = 0; c < 6; c++) dst[c] = buf[tab.addr[slot] + r * 6 + c];
+  }
+}
+
+// unpack current: one thread per interior cell, adds the covering slots in the reference's order
+__global__ void __launch_bounds__(256) k_halo_unpack_current(Geo g, int ch, double* __restrict__ uj,
+                                                             SlotTable tab, const double* __restrict__ buf,
+                                                             const int* __restrict__ nbvalid)
+{
+  const int ncell = g.N[0] * g.N[1] * g.N[2];
+  const int Lb = g.nb;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ncell; t += gridDim.x * blockDim.x) {
+    int i[3] = {t / (g.N[2] * g.N[1]) + Lb, (t / g.N[2]) % g.N[1] + Lb, t % g.N[2] + Lb};
+    double* dst = uj + cell_off(g, ch, i[0], i[1], i[2]) * 4;
+    double  v[4] = {dst[0], dst[1], dst[2], dst[3]};
+    bool    touched = false;
+    for (int slot = 0; slot < 27; slot++) {
+      if (slot == 13 || !nbvalid[slot]) continue;
+      int  e[3] = {slot / 9, (slot / 3) % 3, slot % 3};
+      int  lo[3], n[3];
+      bool in = true;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        slab_bounds(g, a, e[a], false, lo[a], n[a]);
+        in = in && i[a] >= lo[a] && i[a] < lo[a] + n[a];
+      }
+      if (!in) continue;
+      size_t r = ((size_t)(i[0] - lo[0]) * n[1] + (i[1] - lo[1])) * n[2] + (i[2] - lo[2]);
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] = __dadd_rn(buf[tab.addr[slot] + r * 4 + c], v[c]);
+      touched = true;
+    }
+    if (touched) {
+#pragma unroll
+      for (int c = 0; c < 4; c++) dst[c] = v[c];
+    }
+  }
+}
+
+SlotTable make_table(const Geo& g, int ncomp)
+{
+  SlotTable t;
+  int       size = 0;
+  for (int s = 0; s < 27; s++) {
+    t.addr[s] = size;
+    if (s == 13) continue;
+    int e[3] = {s / 9, (s / 3) % 3, s % 3};
+    int cnt  = ncomp;
+    for (int a = 0; a < 3; a++) cnt *= (e[a] == 1) ? g.N[a] : g.nb;
+    size += cnt;
+  }
+  return t;
+}
+} // namespace
+
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, cudaStream_t st)
+{
+  int  ncell = g.M[0] * g.M[1] * g.M[2];
+  dim3 grid((ncell + 255) / 256, g.nchunk);
+  k_halo_field<<<grid, 256, 0, st>>>(g, cg, uf);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, cudaStream_t st)
+{
+  int  ncell = g.N[0] * g.N[1] * g.N[2];
+  dim3 grid((ncell + 255) / 256, g.nchunk);
+  k_halo_current<<<grid, 256, 0, st>>>(g, cg, uj);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* buf, cudaStream_t st)
+{
+  const int ncomp = (mode == NIXB200_MODE_FIELD) ? 6 : 4;
+  SlotTable tab   = make_table(g, ncomp);
+  int       big   = g.nb * g.N[1] * g.N[2] * ncomp;
+  dim3      grid((big + 255) / 256, 27);
+  k_halo_pack<<<grid, 256, 0, st>>>(g, k, ncomp, mode == NIXB200_MODE_CURRENT, data, tab, buf);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
+                       const int* nbvalid_dev, cudaStream_t st)
+{
+  if (mode == NIXB200_MODE_FIELD) {
+    int ncell = g.M[0] * g.M[1] * g.M[2];
+    k_halo_unpack_field<<<(ncell + 255) / 256, 256, 0, st>>>(g, k, data, make_table(g, 6), buf,
+                                                             nbvalid_dev);
+  } else {
+    int ncell = g.N[0] * g.N[1] * g.N[2];
+    k_halo_unpack_current<<<(ncell + 255) / 256, 256, 0, st>>>(g, k, data, make_table(g, 4), buf,
+                                                               nbvalid_dev);
+  }
+  NIX_LAUNCHED();
+  return 0;
+}
+} // namespace nixb200

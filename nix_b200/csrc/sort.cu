@@ -1,0 +1,488 @@
+// sort.cu -- per-cell particle count / sort and particle migration between chunks (sm_100a)
+//
+// Replaces, for every chunk of a device at once:
+//   XtensorParticle::count   xtensor_particle.hpp:324-357
+//   XtensorParticle::sort    xtensor_particle.hpp:260-321
+//   XtensorHaloParticle3D    xtensor_halo3d.hpp:251-557 (classify, pack, append, wrap, count, sort)
+//
+// The reference sorts each chunk with a serial counting sort whose net effect is a STABLE sort of
+// the chunk's pre-sort array by the key  cell*8 + (ip % 8)  (ip = index in the pre-sort array,
+// received particles appended behind the residents in direction order), dropping out-of-bounds
+// particles.  Here ONE global key space covers every chunk of the device:
+//     key = (chunk*ncell + cell)*8 + lane,
+// the histogram over it is the reference's pcount, its exclusive scan gives pindex and the new
+// chunk bases, and stability is obtained without any ordered atomics: `place` drops each
+// particle's pre-sort index `ord` into its bin in arbitrary order, `scatter` then ranks a particle
+// by counting the smaller `ord`s in its (tiny) bin.  All integer work -> bit-exact.
+#include "common.cuh"
+
+namespace nixb200
+{
+namespace
+{
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS   = 16;
+constexpr int SCAN_TILE    = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int find_chunk(const int32_t* __restrict__ cbase, int nchunk, int i)
+{
+  int lo = 0, hi = nchunk; // cbase[lo] <= i < cbase[hi]
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (cbase[mid] <= i) lo = mid;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// direction code 9*dz+3*dy+dx of a position relative to the chunk (xtensor_halo3d.hpp:291-293)
+__device__ __forceinline__ int dir_code(const ChunkGeo& c, double x, double y, double z)
+{
+  int dz = (z >= c.hi[0]) - (z < c.lo[0]) + 1;
+  int dy = (y >= c.hi[1]) - (y < c.lo[1]) + 1;
+  int dx = (x >= c.hi[2]) - (x < c.lo[2]) + 1;
+  return 9 * dz + 3 * dy + dx;
+}
+
+// flat cell index of an in-bounds position (xtensor_particle.hpp:345-348)
+__device__ __forceinline__ int cell_index(const Geo& g, const ChunkGeo& c, double x, double y, double z)
+{
+  int ix = digitize(x, c.off[2], g.rdel[2]);
+  int iy = digitize(y, c.off[1], g.rdel[1]);
+  int iz = digitize(z, c.off[0], g.rdel[0]);
+  return (iz * g.R[1] + iy) * g.R[2] + ix;
+}
+
+// ---------------------------------------------------------------------------------------------
+// count only (initial binning): every particle is a resident or is dropped
+// ---------------------------------------------------------------------------------------------
+__global__ void k_count(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
+{
+  const int ntot = sp.cbase[g.nchunk];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
+    int             ch = find_chunk(sp.cbase, g.nchunk, i);
+    const ChunkGeo& c  = cg[ch];
+    double          x  = sp.xu[soa(0, sp.cap, i)];
+    double          y  = sp.xu[soa(1, sp.cap, i)];
+    double          z  = sp.xu[soa(2, sp.cap, i)];
+    int             lane = (i - sp.cbase[ch]) & (LANES - 1);
+    int             key  = -1;
+    if (dir_code(c, x, y, z) == 13) {
+      key = (ch * g.ncell + cell_index(g, c, x, y, z)) * LANES + lane;
+      atomicAdd(&sp.hist[key], 1);
+    } else {
+      atomicAdd(&sp.oob[ch * LANES + lane], 1);
+    }
+    sp.key[i] = key;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// migration bookkeeping
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of the per-work-item leaver counts inside each chunk (items are in particle order)
+__global__ void k_mig_scan(Geo g, SpeciesDev sp)
+{
+  int ch  = blockIdx.x;
+  int dir = threadIdx.x;
+  if (dir >= 27) return;
+  int32_t* bd      = sp.blockdir + (size_t)ch * g.nitem * 27;
+  int      running = 0;
+  for (int it = 0; it < g.nitem; it++) {
+    int v            = bd[it * 27 + dir];
+    bd[it * 27 + dir] = running;
+    running += v;
+  }
+  sp.sendcnt[ch * 27 + dir] = (dir == 13) ? 0 : running;
+}
+
+// message slots per (chunk, dir) and the append offsets of every receive slot
+// (pre_unpack/unpack order: slots in (iz,iy,ix) order, xtensor_halo3d.hpp:440-461,507-524)
+__global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
+{
+  __shared__ int s_part[1024];
+  const int      n   = g.nchunk * 27;
+  const int      tid = threadIdx.x;
+  const int      per = (n + blockDim.x - 1) / blockDim.x;
+  const int      b = tid * per, e = min(n, b + per);
+  int            sum = 0;
+  for (int f = b; f < e; f++) {
+    int ch = f / 27, dir = f % 27;
+    sum += (cg[ch].nbr[dir] >= 0) ? sp.sendcnt[f] : 0;
+  }
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    int run = 0;
+    for (int t = 0; t < blockDim.x; t++) {
+      int v     = s_part[t];
+      s_part[t] = run;
+      run += v;
+    }
+    *sp.nmsg = run;
+  }
+  __syncthreads();
+  int run = s_part[tid];
+  for (int f = b; f < e; f++) {
+    int ch = f / 27, dir = f % 27;
+    sp.msgoff[f] = run;
+    run += (cg[ch].nbr[dir] >= 0) ? sp.sendcnt[f] : 0;
+  }
+  for (int ch = tid; ch < g.nchunk; ch += blockDim.x) {
+    int running = sp.cbase[ch + 1] - sp.cbase[ch];
+    for (int s = 0; s < 27; s++) {
+      int nb                  = cg[ch].nbr[s];
+      int cnt                 = (s != 13 && nb >= 0) ? sp.sendcnt[nb * 27 + (26 - s)] : 0;
+      sp.recvoff[ch * 27 + s] = running;
+      running += cnt;
+    }
+  }
+}
+
+// one thread per leaver: destination chunk, pre-sort index there, periodic wrap, count
+// (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
+__global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, int* err)
+{
+  const int nl = min(*sp.nleave, (int)sp.lcap);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nl; j += gridDim.x * blockDim.x) {
+    int4 r    = sp.lrec[j];
+    int  i    = r.x;
+    int  A    = r.y;
+    int  item = r.z >> 8;
+    int  dir  = r.z & 0xff;
+    int  B    = cg[A].nbr[dir];
+    if (B < 0) continue; // no neighbour / other rank
+    int idx   = sp.blockdir[((size_t)A * g.nitem + item) * 27 + dir] + r.w;
+    int m     = sp.msgoff[A * 27 + dir] + idx;
+    int ipB   = sp.recvoff[B * 27 + (26 - dir)] + idx;
+    if (m >= sp.lcap) {
+      atomicOr(err, NIXB200_ERR_CAPACITY);
+      continue;
+    }
+    double v[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) v[k] = sp.xu[soa(k, sp.cap, i)];
+    // xtensor_particle.hpp:371-375   x += (x < X1)*L - (x >= X2)*L   (z,y,x stored as v[2],v[1],v[0])
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      double p  = v[2 - a];
+      double L  = g.glen[a];
+      double s1 = (p < g.glo[a]) ? L : 0.0;
+      double s2 = (p >= g.ghi[a]) ? L : 0.0;
+      v[2 - a]  = __dadd_rn(p, __dsub_rn(s1, s2));
+    }
+    const ChunkGeo& c    = cg[B];
+    int             lane = ipB & (LANES - 1);
+    int             key  = -1;
+    if (dir_code(c, v[0], v[1], v[2]) == 13) {
+      key = (B * g.ncell + cell_index(g, c, v[0], v[1], v[2])) * LANES + lane;
+      atomicAdd(&sp.hist[key], 1);
+    } else {
+      atomicAdd(&sp.oob[B * LANES + lane], 1);
+    }
+#pragma unroll
+    for (int k = 0; k < NC; k++) sp.msg[soa(k, sp.lcap, m)] = v[k];
+    sp.msgkey[m] = key;
+    sp.msgord[m] = ipB;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// exclusive scan of the histogram (reduce / scan block sums / apply)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v)
+{
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// exclusive scan of one value per thread over the block; returns the block total in `total`
+__device__ __forceinline__ int block_excl_scan(int v, int& total)
+{
+  __shared__ int s_w[32];
+  const int      lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int            inc = warp_incl_scan(v);
+  if (lane == 31) s_w[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int t = (lane < nw) ? s_w[lane] : 0;
+    t     = warp_incl_scan(t);
+    s_w[lane] = t;
+  }
+  __syncthreads();
+  int base = (w > 0) ? s_w[w - 1] : 0;
+  total    = s_w[nw - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const int32_t* __restrict__ in, size_t n,
+                                                              int32_t* __restrict__ bsum)
+{
+  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  int    s    = 0;
+  if (base + SCAN_ITEMS <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+      int4 v = p[q];
+      s += v.x + v.y + v.z + v.w;
+    }
+  } else {
+    for (int q = 0; q < SCAN_ITEMS; q++)
+      if (base + q < n) s += in[base + q];
+  }
+  int total;
+  block_excl_scan(s, total);
+  if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_bsum(int32_t* bsum, int nblk, int32_t* total_out)
+{
+  __shared__ int s_carry;
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int b0 = 0; b0 < nblk; b0 += blockDim.x) {
+    int i = b0 + threadIdx.x;
+    int v = (i < nblk) ? bsum[i] : 0;
+    int total;
+    int ex    = block_excl_scan(v, total);
+    int carry = s_carry;
+    if (i < nblk) bsum[i] = carry + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) s_carry = carry + total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total_out = s_carry;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const int32_t* __restrict__ in, size_t n,
+                                                             const int32_t* __restrict__ bsum,
+                                                             int32_t* __restrict__ out)
+{
+  size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+  int    v[SCAN_ITEMS];
+  int    s = 0;
+  if (base + SCAN_ITEMS <= n) {
+    const int4* p = reinterpret_cast<const int4*>(in + base);
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+      int4 t       = p[q];
+      v[4 * q + 0] = t.x;
+      v[4 * q + 1] = t.y;
+      v[4 * q + 2] = t.z;
+      v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) v[q] = (base + q < n) ? in[base + q] : 0;
+  }
+#pragma unroll
+  for (int q = 0; q < SCAN_ITEMS; q++) s += v[q];
+  int total;
+  int run = bsum[blockIdx.x] + block_excl_scan(s, total);
+  if (base + SCAN_ITEMS <= n) {
+    int4* o = reinterpret_cast<int4*>(out + base);
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS / 4; q++) {
+      int4 t;
+      t.x = run;
+      run += v[4 * q + 0];
+      t.y = run;
+      run += v[4 * q + 1];
+      t.z = run;
+      run += v[4 * q + 2];
+      t.w = run;
+      run += v[4 * q + 3];
+      o[q] = t;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < SCAN_ITEMS; q++) {
+      if (base + q < n) out[base + q] = run;
+      run += v[q];
+    }
+  }
+}
+
+// new chunk bases = scan value at the first key of every chunk; start[n] = total
+__global__ void k_chunk_bases(Geo g, SpeciesDev sp, const int32_t* __restrict__ total, int* err)
+{
+  const size_t n = (size_t)g.nchunk * g.ncell * LANES;
+  int          c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c == 0) {
+    sp.start[n] = *total;
+    if (*total > sp.cap) atomicOr(err, NIXB200_ERR_CAPACITY);
+  }
+  if (c < g.nchunk) sp.cbase_new[c] = sp.start[(size_t)c * g.ncell * LANES];
+  if (c == g.nchunk) sp.cbase_new[c] = *total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// place: drop each particle's pre-sort index into its bin (any order)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_place(Geo g, SpeciesDev sp)
+{
+  const int ntot   = sp.cbase[g.nchunk];
+  const int perchk = g.ncell * LANES;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
+    int k = sp.key[i];
+    if (k < 0) continue;
+    int ch        = k / perchk;
+    int slot      = sp.start[k] + atomicSub(&sp.hist[k], 1) - 1;
+    sp.ordl[slot] = i - sp.cbase[ch];
+  }
+}
+
+__global__ void k_place_msg(Geo g, SpeciesDev sp)
+{
+  const int nm = min(*sp.nmsg, (int)sp.lcap);
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
+    int k = sp.msgkey[m];
+    if (k < 0) continue;
+    int slot      = sp.start[k] + atomicSub(&sp.hist[k], 1) - 1;
+    sp.ordl[slot] = sp.msgord[m];
+  }
+}
+
+__device__ __forceinline__ int stable_rank(const int32_t* __restrict__ ordl, int lo, int hi, int ord)
+{
+  int r = 0;
+  for (int e = lo; e < hi; e++) r += (ordl[e] < ord) ? 1 : 0;
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter: xv[start[key] + rank] = xu[i]   (xtensor_particle.hpp:303-313)
+// two consecutive particles per thread -> 128-bit coalesced loads of every SoA component
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_scatter(Geo g, SpeciesDev sp)
+{
+  const int ntot   = sp.cbase[g.nchunk];
+  const int perchk = g.ncell * LANES;
+  const int npair  = (ntot + 1) >> 1;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npair; t += gridDim.x * blockDim.x) {
+    const int i0 = 2 * t;
+    int       k0 = -1, k1 = -1;
+    if (i0 + 1 < ntot) {
+      int2 kk = *reinterpret_cast<const int2*>(sp.key + i0);
+      k0      = kk.x;
+      k1      = kk.y;
+    } else {
+      k0 = sp.key[i0];
+    }
+    if (k0 < 0 && k1 < 0) continue;
+    int dst0 = -1, dst1 = -1;
+    if (k0 >= 0) {
+      int lo = sp.start[k0], hi = sp.start[k0 + 1];
+      dst0 = lo + stable_rank(sp.ordl, lo, hi, i0 - sp.cbase[k0 / perchk]);
+    }
+    if (k1 >= 0) {
+      int lo = sp.start[k1], hi = sp.start[k1 + 1];
+      dst1 = lo + stable_rank(sp.ordl, lo, hi, i0 + 1 - sp.cbase[k1 / perchk]);
+    }
+    if (dst0 >= sp.cap) dst0 = -1;
+    if (dst1 >= sp.cap) dst1 = -1;
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+      const double* src = sp.xu + soa(c, sp.cap, i0);
+      double        a, b = 0.0;
+      if (i0 + 1 < ntot) {
+        double2 v = *reinterpret_cast<const double2*>(src);
+        a         = v.x;
+        b         = v.y;
+      } else {
+        a = src[0];
+      }
+      if (dst0 >= 0) sp.xv[soa(c, sp.cap, dst0)] = a;
+      if (dst1 >= 0) sp.xv[soa(c, sp.cap, dst1)] = b;
+    }
+  }
+}
+
+__global__ void k_scatter_msg(Geo g, SpeciesDev sp)
+{
+  const int nm = min(*sp.nmsg, (int)sp.lcap);
+  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
+    int k = sp.msgkey[m];
+    if (k < 0) continue;
+    int lo = sp.start[k], hi = sp.start[k + 1];
+    int dst = lo + stable_rank(sp.ordl, lo, hi, sp.msgord[m]);
+    if (dst >= sp.cap) continue;
+#pragma unroll
+    for (int c = 0; c < NC; c++) sp.xv[soa(c, sp.cap, dst)] = sp.msg[soa(c, sp.lcap, m)];
+  }
+}
+
+inline int grid_for(size_t n, int threads, int max_blocks = 148 * 16)
+{
+  size_t b = (n + threads - 1) / threads;
+  if (b < 1) b = 1;
+  if (b > (size_t)max_blocks) b = max_blocks;
+  return (int)b;
+}
+} // namespace
+
+size_t scan_tmp_bytes(size_t n)
+{
+  size_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+  return (nblk + 2) * sizeof(int32_t);
+}
+
+int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st)
+{
+  (void)err;
+  NIX_CUDA(cudaMemsetAsync(sp.oob, 0, sizeof(int32_t) * g.nchunk * LANES, st));
+  NIX_CUDA(cudaMemsetAsync(sp.nleave, 0, sizeof(int32_t), st));
+  NIX_CUDA(cudaMemsetAsync(sp.nmsg, 0, sizeof(int32_t), st));
+  k_count<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, cg, sp);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+// after push_deposit (which filled key/hist for residents and the leaver records)
+int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st)
+{
+  k_mig_scan<<<g.nchunk, 32, 0, st>>>(g, sp);
+  NIX_LAUNCHED();
+  k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp);
+  NIX_LAUNCHED();
+  k_mig_key<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, err);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+// hist -> start, place, scatter; leaves the sorted particles in sp.xv and the new chunk bases in
+// sp.cbase_new (the caller swaps, xtensor_particle.hpp:317)
+int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
+                cudaStream_t st)
+{
+  (void)cg;
+  const size_t n     = (size_t)g.nchunk * g.ncell * LANES;
+  const int    nblk  = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  int32_t*     bsum  = reinterpret_cast<int32_t*>(scan_tmp);
+  int32_t*     total = bsum + nblk;
+  k_scan_reduce<<<nblk, SCAN_THREADS, 0, st>>>(sp.hist, n, bsum);
+  NIX_LAUNCHED();
+  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nblk, total);
+  NIX_LAUNCHED();
+  k_scan_apply<<<nblk, SCAN_THREADS, 0, st>>>(sp.hist, n, bsum, sp.start);
+  NIX_LAUNCHED();
+  k_chunk_bases<<<(g.nchunk + 1 + 255) / 256, 256, 0, st>>>(g, sp, total, err);
+  NIX_LAUNCHED();
+  k_place<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp);
+  NIX_LAUNCHED();
+  k_place_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp);
+  NIX_LAUNCHED();
+  k_scatter<<<grid_for(sp.cap / 2, 256), 256, 0, st>>>(g, sp);
+  NIX_LAUNCHED();
+  k_scatter_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp);
+  NIX_LAUNCHED();
+  return 0;
+}
+} // namespace nixb200
