@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- particle-updates/s of the per-chunk PIC step (push + deposit + sort + halo + migration).
+
+    python bench.py --gpus N --steps K --warmup W            # the B200 path (libnixb200.so)
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle/_ref)
+
+Workload (BASELINE.json configs[1]): 128^3 cells per GPU, 128 particles per cell (electrons + ions,
+64 each), 2nd-order shape, fp64, periodic thermal plasma, as 8^3 chunks of 16^3 cells (the
+reference's int-addressed chunk serialisation caps one chunk at < 2 GiB).
+One step = clear J, gather + Boris push + move + Esirkepov deposit, J halo, E/B halo, particle
+migration and per-cell count/sort, for every chunk and species.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md section 6 for how every field is obtained.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-updates/s (push+deposit+sort)"
+ALGO_BYTES_PUSH = 116.0  # push+deposit+count reads 56 B, writes 56 B + 4 B per particle
+
+
+def workload(args):
+    small = os.environ.get("NIXB200_BENCH_SMALL", "") == "1" or args.small
+    cd = (2, 2, 2) if small else (8, 8, 8)
+    if args.cdims:
+        cd = tuple(int(v) for v in args.cdims.split(","))
+    return dict(cdims=cd, dims=(16, 16, 16), order=2, ppc=64, ns=2)
+
+
+def make_problem(w, seed=2024, cdims=None):
+    from nix_b200.synth import Problem
+    return Problem(cdims or w["cdims"], w["dims"], w["order"], ppc=w["ppc"], ns=w["ns"], seed=seed,
+                   vth=(0.1, 0.02))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_reference_run(w, steps, warmup, budget_s=None):
+    """Time the reference's own CPU implementation (oracle/_ref when it was built from the reference
+    sources, else the plain-C port) on a bounded sample of the workload with all host threads."""
+    from oracle import nixoracle as no
+    name = no.best_timing_backend()
+    lib = no.load(name)
+    nthreads = os.cpu_count() or 1
+    lib.nixo_set_num_threads(nthreads)
+    nthreads = lib.nixo_get_num_threads()
+    # bounded sample: same chunk shape / ppc / order, fewer chunks (>= 1 chunk per thread and phase)
+    if nthreads <= 8:
+        cd = (2, 2, 2)
+    elif nthreads <= 32:
+        cd = (2, 4, 4)
+    elif nthreads <= 128:
+        cd = (4, 4, 4)
+    else:
+        cd = (4, 4, 8)
+    prob = make_problem(w, cdims=cd)
+    dom = no.Domain(lib, prob.cdims, prob.dims, prob.nb, prob.order, prob.ns, prob.q, prob.m, prob.coord,
+                    prob.ncell() * prob.ppc)
+    for k, c in enumerate(dom.chunks):
+        c.uf[...] = prob.field(k)
+        for s in range(prob.ns):
+            c.set_particles(s, prob.particles(k, s))
+    dom.exchange(no.MODE_FIELD)
+    dom.sort_only()
+    simd = name.startswith("ref")  # the reference's vectorised sorted path (xsimd batches)
+    npart = dom.total_particles()
+    for _ in range(warmup):
+        dom.step(0.5, 1.0, simd)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        dom.step(0.5, 1.0, simd)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    kind = "reference" if name.startswith("ref") else "port"
+    return {
+        "value": npart * done / dt, "unit": "particle-updates/s", "cores": nthreads, "kind": kind,
+        "backend": name, "simd_lanes": lib.nixo_simd_lanes() if simd else 1,
+        "sample": f"{cd[0]}x{cd[1]}x{cd[2]} chunks of 16^3 cells, {w['ppc']} ppc x {w['ns']} species "
+                  f"({npart} particles), order {w['order']}, {done} steps after {warmup} warm-up",
+        "ms_per_step": 1e3 * dt / done, "steps": done,
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return  # the CPU arm runs on rank 0 only
+    w = workload(args)
+    r = cpu_reference_run(w, args.steps, args.warmup)
+    out = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "128^3 cells, 128 ppc (2 species x 64), order 2, fp64, 8^3 chunks of 16^3 "
+                               "(bounded CPU sample: " + r["sample"] + ")"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes")},
+        "e2e": {"value": r["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 path has no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from nix_b200 import core
+
+    w = workload(args)
+    prob = make_problem(w, seed=2024 + rank)
+    stream = torch.cuda.current_stream()
+    dom = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, device=local,
+                      strict_fp=bool(args.strict), capacity_factor=1.15, stream=stream.cuda_stream)
+    nchunk = dom.nchunk
+    cells = int(np.prod(dom.M))
+    # pinned host mirrors of the grid arrays (the host-side field solver's view)
+    uf_host = torch.empty((nchunk, cells, 6), dtype=torch.float64, pin_memory=True)
+    uj_host = torch.empty((nchunk, cells, 4), dtype=torch.float64, pin_memory=True)
+    ufn = uf_host.numpy()
+    for k in range(nchunk):
+        ufn[k] = prob.field(k).reshape(cells, 6)
+    dom.field_upload_async(core.FIELD_UF, uf_host.data_ptr())
+    dom.exchange_field()
+    dom.field_download_async(core.FIELD_UF, uf_host.data_ptr())  # ghosts consistent on the host too
+    dom.synchronize()
+    npc = prob.ncell() * prob.ppc
+    for s in range(prob.ns):
+        flat = np.empty((nchunk * npc, 7), dtype=np.float64)
+        for k in range(nchunk):
+            flat[k * npc:(k + 1) * npc] = prob.particles(k, s)
+        dom.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
+        del flat
+    dom.sort()
+    dom.synchronize()
+    ntot = dom.total_particles()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    dt = 0.5
+    for _ in range(max(args.warmup, 3)):
+        dom.step(dt)
+    barrier()
+    err = dom.check()
+    if err:
+        raise SystemExit(f"bench.py: device error bits {err} during warm-up")
+
+    # ---- timed region: K device-resident steps ----
+    try:
+        gpu_sel = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+    except Exception:
+        gpu_sel = str(local)
+    sampler = ClockSampler(gpu_sel)
+    sampler.start()
+    dom.set_profiling(True)
+    dom.phase_ms()
+    l0 = core.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        dom.step(dt)
+    e1.record(stream)
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = core.launch_count() - l0
+    phases = dom.phase_ms()
+    dom.set_profiling(False)
+    clocks = sampler.stop()
+
+    # ---- end to end: host E/B in, J + particle counts out, every step (host-side field solver) ----
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    for _ in range(args.steps):
+        dom.field_upload_async(core.FIELD_UF, uf_host.data_ptr())
+        dom.step(dt)
+        dom.field_download_async(core.FIELD_UJ, uj_host.data_ptr())
+        dom.get_np(0)  # Chunk::get_total_load-style read back (synchronises)
+    e3.record(stream)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    err = dom.check()
+    if err:
+        raise SystemExit(f"bench.py: device error bits {err} during the timed region")
+    ntot_end = dom.total_particles()
+
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    n = torch.tensor([float(ntot)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(n, op=dist.ReduceOp.SUM)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    nglobal = float(n[0])
+
+    if rank == 0:
+        push_ms, push_calls = phases["push_deposit"]
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+        except OSError:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+        per_launch_ms = push_ms / max(push_calls, 1) / prob.ns  # one launch per species
+        achieved = ALGO_BYTES_PUSH * (ntot / prob.ns) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "push_deposit_traffic.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get("dram_bytes_per_launch")
+            except (OSError, ValueError):
+                traffic = None
+        out = {
+            "metric": METRIC, "value": nglobal * args.steps / (ms * 1e-3), "unit": "particle-updates/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {
+                "workload": "128^3 cells per GPU, 128 ppc (electrons+ions, 64 each), order 2, fp64, periodic "
+                            "thermal plasma, %dx%dx%d chunks of 16^3 per GPU" % prob.cdims,
+                "particles_per_gpu": ntot, "particles_end": ntot_end, "fp_contract": "off" if args.strict else "fma",
+                "l2": "inputs (%.1f GB of particles per GPU) larger than L2" % (ntot * 56 / 1e9),
+                "multi_gpu": "independent periodic box per rank" if world > 1 else "single GPU",
+            },
+            "clocks": clocks,
+            "e2e": {"value": nglobal * args.steps / (ms_e2e * 1e-3), "unit": "particle-updates/s",
+                    "h2d_bytes_per_step": int(uf_host.numel() * 8),
+                    "d2h_bytes_per_step": int(uj_host.numel() * 8 + nchunk * 4 + 4),
+                    "what": "per step: E/B of every chunk from pinned host memory, one full step, J of every "
+                            "chunk + per-chunk particle counts back to the host"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k_push_deposit<2>", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                         "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_PUSH,
+                         "launch_ms": per_launch_ms,
+                         "note": "fp64-pipe/shared-memory bound for order 2 (SURVEY.md 8d), not HBM bound"},
+            "phases_ms_per_step": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in phases.items()},
+        }
+        if world == 1 and not args.no_cpu:
+            r = cpu_reference_run(w, steps=3, warmup=1, budget_s=25.0)
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes")}
+        print(json.dumps(out))
+    dom.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--strict", action="store_true", help="no FMA contraction in the push (bit-exact mode)")
+    ap.add_argument("--small", action="store_true", help="2x2x2 chunks (smoke / profiling)")
+    ap.add_argument("--cdims", default="", help="override chunks per axis, e.g. 4,4,4")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

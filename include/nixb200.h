@@ -82,6 +82,10 @@ int nixb200_domain_check(nixb200_domain* d, int* errbits);
 /* local chunk index k = id - id_begin */
 int nixb200_chunk_field_upload(nixb200_domain* d, int k, int which, const double* host);
 int nixb200_chunk_field_download(nixb200_domain* d, int k, int which, double* host);
+/* all local chunks at once, asynchronous on the domain's stream (host memory should be pinned);
+ * call nixb200_domain_synchronize before reusing / reading the host buffer */
+int nixb200_domain_field_upload_async(nixb200_domain* d, int which, const double* host);
+int nixb200_domain_field_download_async(nixb200_domain* d, int which, double* host);
 /* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each */
 int nixb200_domain_set_particles(nixb200_domain* d, int is, const double* xu_aos,
                                  const int64_t* np_chunk);
@@ -115,6 +119,14 @@ int nixb200_halo_layout(nixb200_domain* d, int mode, int* bufsize27, int* bufadd
 int nixb200_chunk_halo_pack(nixb200_domain* d, int k, int mode, void* host_sendbuf);
 int nixb200_chunk_halo_unpack(nixb200_domain* d, int k, int mode, const void* host_recvbuf,
                               const int* nbvalid27);
+
+/* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
+ * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only).
+ * With profiling on, every phase call is bracketed by CUDA events on the domain's stream;
+ * get_phase_ms synchronises, then returns and resets the accumulated milliseconds and call count. */
+#define NIXB200_NPHASE 5
+int nixb200_domain_set_profiling(nixb200_domain* d, int on);
+int nixb200_domain_get_phase_ms(nixb200_domain* d, int phase, double* ms_sum, int* calls);
 
 /* Chunk::get_total_load (chunk.hpp:189-192): device milliseconds of the last push_deposit */
 int nixb200_domain_get_load(nixb200_domain* d, double* ms);

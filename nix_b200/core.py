@@ -26,8 +26,11 @@ SYMBOLS = [
     "nixb200_domain_clear_current", "nixb200_domain_push_deposit", "nixb200_domain_exchange_current",
     "nixb200_domain_exchange_field", "nixb200_domain_migrate_sort", "nixb200_domain_step",
     "nixb200_halo_layout", "nixb200_chunk_halo_pack", "nixb200_chunk_halo_unpack",
-    "nixb200_domain_get_load", "nixb200_domain_total_particles",
+    "nixb200_domain_get_load", "nixb200_domain_total_particles", "nixb200_domain_field_upload_async",
+    "nixb200_domain_field_download_async", "nixb200_domain_set_profiling", "nixb200_domain_get_phase_ms",
 ]
+
+PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort")
 
 
 class DomainDesc(C.Structure):
@@ -94,6 +97,10 @@ def load_library():
     sig("nixb200_halo_layout", I, P, I, PI, PI)
     sig("nixb200_chunk_halo_pack", I, P, I, I, P)
     sig("nixb200_chunk_halo_unpack", I, P, I, I, P, PI)
+    sig("nixb200_domain_field_upload_async", I, P, I, P)
+    sig("nixb200_domain_field_download_async", I, P, I, P)
+    sig("nixb200_domain_set_profiling", I, P, I)
+    sig("nixb200_domain_get_phase_ms", I, P, I, PD, PI)
     sig("nixb200_domain_get_load", I, P, PD)
     sig("nixb200_domain_total_particles", C.c_int64, P)
     _lib = lib
@@ -280,6 +287,25 @@ class Domain:
             v = np.ascontiguousarray(nbvalid, dtype=np.int32)
             pv = v.ctypes.data_as(C.POINTER(C.c_int))
         self._ck(self.lib.nixb200_chunk_halo_unpack(self.h, k, mode, buf.ctypes.data_as(C.c_void_p), pv))
+
+    def field_upload_async(self, which, host_ptr):
+        """host_ptr: address of a (pinned) host buffer holding all local chunks back to back."""
+        self._ck(self.lib.nixb200_domain_field_upload_async(self.h, which, C.c_void_p(int(host_ptr))))
+
+    def field_download_async(self, which, host_ptr):
+        self._ck(self.lib.nixb200_domain_field_download_async(self.h, which, C.c_void_p(int(host_ptr))))
+
+    def set_profiling(self, on=True):
+        self._ck(self.lib.nixb200_domain_set_profiling(self.h, int(on)))
+
+    def phase_ms(self):
+        """{phase: (ms_sum, calls)} accumulated since the last call (synchronises the stream)."""
+        out = {}
+        for i, name in enumerate(PHASES):
+            ms, n = C.c_double(0), C.c_int(0)
+            self._ck(self.lib.nixb200_domain_get_phase_ms(self.h, i, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
 
     def get_load(self):
         ms = C.c_double(0)

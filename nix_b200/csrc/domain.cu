@@ -41,6 +41,30 @@ struct Domain {
   bool                    timed = false;
   size_t                  cells_per_chunk = 0;
   bool                    particles_set   = false;
+  bool                    profiling       = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[NIXB200_NPHASE];
+  double                  phase_ms[NIXB200_NPHASE]    = {0, 0, 0, 0, 0};
+  int                     phase_calls[NIXB200_NPHASE] = {0, 0, 0, 0, 0};
+};
+
+// RAII bracket: records an event pair around one phase when profiling is on
+struct PhaseTimer {
+  Domain*     d;
+  int         phase;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PhaseTimer(Domain* dd, int ph) : d(dd), phase(ph)
+  {
+    if (!d->profiling) return;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, d->stream);
+  }
+  ~PhaseTimer()
+  {
+    if (!e0) return;
+    cudaEventRecord(e1, d->stream);
+    d->pending[phase].push_back({e0, e1});
+  }
 };
 
 static int required_nb(int order)
@@ -440,6 +464,56 @@ int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* h
   return 0;
 }
 
+int nixb200_domain_field_upload_async(nixb200_domain* dd, int which, const double* host)
+{
+  Domain* d = D(dd);
+  if (!d || !host) return 1;
+  int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  double* dst = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
+  NIX_CUDA(cudaMemcpyAsync(dst, host, sizeof(double) * nc * d->cells_per_chunk * d->geo.nchunk, cudaMemcpyHostToDevice, d->stream));
+  return 0;
+}
+
+int nixb200_domain_field_download_async(nixb200_domain* dd, int which, double* host)
+{
+  Domain* d = D(dd);
+  if (!d || !host) return 1;
+  int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const double* src = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
+  NIX_CUDA(cudaMemcpyAsync(host, src, sizeof(double) * nc * d->cells_per_chunk * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
+  return 0;
+}
+
+int nixb200_domain_set_profiling(nixb200_domain* dd, int on)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  d->profiling = on != 0;
+  return 0;
+}
+
+int nixb200_domain_get_phase_ms(nixb200_domain* dd, int phase, double* ms_sum, int* calls)
+{
+  Domain* d = D(dd);
+  if (!d || phase < 0 || phase >= NIXB200_NPHASE || !ms_sum || !calls) return 1;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  for (auto& pr : d->pending[phase]) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, pr.first, pr.second) == cudaSuccess) {
+      d->phase_ms[phase] += t;
+      d->phase_calls[phase]++;
+    }
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  d->pending[phase].clear();
+  *ms_sum               = d->phase_ms[phase];
+  *calls                = d->phase_calls[phase];
+  d->phase_ms[phase]    = 0;
+  d->phase_calls[phase] = 0;
+  return 0;
+}
+
 int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_aos, const int64_t* np_chunk)
 {
   Domain* d = D(dd);
@@ -553,6 +627,7 @@ int nixb200_domain_sort(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  PhaseTimer pt(d, 4);
   for (auto& s : d->sp) {
     if (launch_count_only(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
     if (do_sort_species(d, s)) return 1;
@@ -572,6 +647,7 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  PhaseTimer pt(d, 0);
   NIX_CUDA(cudaEventRecord(d->ev0, d->stream));
   for (auto& s : d->sp) {
     PushArgs a;
@@ -593,6 +669,7 @@ int nixb200_domain_exchange_current(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  PhaseTimer pt(d, 1);
   return launch_halo_current(d->geo, d->cg_dev, d->uj, d->stream);
 }
 
@@ -600,6 +677,7 @@ int nixb200_domain_exchange_field(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  PhaseTimer pt(d, 2);
   return launch_halo_field(d->geo, d->cg_dev, d->uf, d->stream);
 }
 
@@ -607,6 +685,7 @@ int nixb200_domain_migrate_sort(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  PhaseTimer pt(d, 3);
   for (auto& s : d->sp) {
     if (launch_migrate(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
     if (do_sort_species(d, s)) return 1;
