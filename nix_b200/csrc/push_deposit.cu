@@ -35,21 +35,22 @@ constexpr int THREADS = 128;
 
 template <int O>
 struct Cfg {
-  static constexpr int NW   = O + 2;         // gather stencil width   (interp.hpp)
-  static constexpr int NS   = O + 3;         // deposit mesh width     (esirkepov.hpp:326-328)
-  static constexpr int NCOL = NS * NS;       // (jy,jz) columns
+  static constexpr int NW   = O + 2;          // gather stencil width   (interp.hpp)
+  static constexpr int NS   = O + 3;          // deposit mesh width     (esirkepov.hpp:326-328)
+  static constexpr int NCOL = NS * NS;        // (jy,jz) columns
   static constexpr int G    = THREADS / NCOL; // particle groups: 8 / 5 / 3
-  static constexpr int F    = 12 * NS;       // scratch doubles per particle
-  static constexpr int FS   = F + 2;         // padded stride (even: 16-byte aligned rows)
-  // scratch field offsets
-  static constexpr int X_S1 = 0 * NS, X_CP = 1 * NS, X_S0 = 2 * NS, X_DS = 3 * NS, X_P = 4 * NS,
-                       X_Q = 5 * NS;
-  static constexpr int Y_S0 = 6 * NS, Y_DS = 7 * NS, Y_CP = 8 * NS;
-  static constexpr int Z_S0 = 9 * NS, Z_DS = 10 * NS, Z_CP = 11 * NS;
+  // per-particle scratch, stored field-major ([field][particle], row stride SP) so that the stores of
+  // phase 1 (consecutive particles) and the loads of phase 2 (consecutive fields) are conflict free
+  static constexpr int X_S0 = 0;              // S0x[1..O+1]        (O+1 values; slots 0 and O+2 are 0)
+  static constexpr int X_DS = X_S0 + O + 1;   // DSx[0..NS-1]
+  static constexpr int Y_S0 = X_DS + NS, Y_DS = Y_S0 + NS, Y_CP = Y_DS + NS;
+  static constexpr int Z_S0 = Y_CP + NS, Z_DS = Z_S0 + NS, Z_CP = Z_DS + NS;
+  static constexpr int F    = Z_CP + NS;      // 30 / 38 / 46 doubles per particle
+  static constexpr int SP   = THREADS + 1;    // odd row stride
 };
 
 struct SmemLayout {
-  int    eb_doubles, jt_doubles, stage_doubles, scratch_doubles;
+  int    eb_doubles, stage_doubles, scratch_doubles;
   size_t bytes;
 };
 
@@ -58,14 +59,12 @@ __host__ __device__ inline SmemLayout smem_layout(int seg)
 {
   using C = Cfg<O>;
   SmemLayout L;
-  int        ex   = seg + C::NW - 1;
-  int        tx   = seg + C::NS - 1;
-  L.eb_doubles    = ((C::NW * C::NW * ex * 6) + 15) / 16 * 16; // keep 128-byte multiples
-  L.jt_doubles    = ((C::NS * C::NS * tx * 4) + 15) / 16 * 16;
-  L.stage_doubles = ((C::G * C::NCOL * 4) + 15) / 16 * 16;
-  L.scratch_doubles = THREADS * C::FS;
-  L.bytes = sizeof(double) * ((size_t)L.eb_doubles + L.jt_doubles + L.stage_doubles + L.scratch_doubles) +
-            128 /* alignment slack */ + 256 * sizeof(int) /* ints */;
+  int        ex     = seg + C::NW - 1;
+  L.eb_doubles      = ((C::NW * C::NW * ex * 6) + 15) / 16 * 16; // keep 128-byte multiples
+  L.stage_doubles   = ((2 * C::G * C::NCOL * 4) + 15) / 16 * 16; // double buffered
+  L.scratch_doubles = (C::F * C::SP + 15) / 16 * 16;
+  L.bytes = sizeof(double) * ((size_t)L.eb_doubles + L.stage_doubles + L.scratch_doubles) +
+            256 * sizeof(int) /* ints */;
   return L;
 }
 
@@ -149,19 +148,19 @@ struct Kparams {
 };
 
 template <int O, bool S>
-__global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
-                                                          const Kparams P)
+__global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
+                                                             const Kparams P)
 {
-  using C                = Cfg<O>;
-  constexpr int NW       = C::NW;
-  constexpr int NS       = C::NS;
-  constexpr int NCOL     = C::NCOL;
-  constexpr int G        = C::G;
-  constexpr int FS       = C::FS;
-  const Geo&    g        = P.geo;
-  const int     tid      = threadIdx.x;
-  const int     lane     = tid & 31;
-  const int     warp     = tid >> 5;
+  using C            = Cfg<O>;
+  constexpr int NW   = C::NW;
+  constexpr int NS   = C::NS;
+  constexpr int NCOL = C::NCOL;
+  constexpr int G    = C::G;
+  constexpr int SP   = C::SP;
+  const Geo&    g    = P.geo;
+  const int     tid  = threadIdx.x;
+  const int     lane = tid & 31;
+  const int     warp = tid >> 5;
 
   // ---- decode the work item -------------------------------------------------------------------
   const int item = blockIdx.x % g.nitem;
@@ -169,8 +168,8 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
   const int sg   = item % g.nseg;
   const int ry   = (item / g.nseg) % g.R[1];
   const int rz   = item / (g.nseg * g.R[1]);
-  const int xs   = sg * g.seg;                   // first cell (bin index) of the segment
-  const int ncs  = min(g.seg, g.R[2] - xs);      // cells in this segment
+  const int xs   = sg * g.seg;              // first cell (bin index) of the segment
+  const int ncs  = min(g.seg, g.R[2] - xs); // cells in this segment
   const int row0 = (ch * g.ncell + (rz * g.R[1] + ry) * g.R[2] + xs) * LANES; // key of first bin
 
   const int32_t* __restrict__ start = P.sp.start;
@@ -178,21 +177,19 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
   const int p_end   = start[row0 + ncs * LANES];
   if (p_begin == p_end) return;
 
-  // ---- shared memory carve-up -------------------------------------------------------------------
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // ---- shared memory carve-up (indices into one __shared__ array: keeps LDS/STS addressing) -----
+  extern __shared__ __align__(1024) double smem_d[];
   const SmemLayout L = smem_layout<O>(g.seg);
-  double* s_eb      = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  double* s_jt      = s_eb + L.eb_doubles;
-  double* s_stage   = s_jt + L.jt_doubles;
-  double* s_scr     = s_stage + L.stage_doubles;
-  int*    s_int     = reinterpret_cast<int*>(s_scr + L.scratch_doubles);
-  uint64_t* s_bar   = reinterpret_cast<uint64_t*>(s_int);        // 2 ints
-  int*    s_pidx    = s_int + 2;                                 // [seg+1] <= 66
-  int*    s_dirbase = s_int + 72;                                // [27]
-  int*    s_warpcnt = s_int + 100;                               // [4][27]
+  double*   s_eb      = smem_d;
+  double*   s_stage   = smem_d + L.eb_doubles;
+  double*   s_scr     = s_stage + L.stage_doubles;
+  int*      s_int     = reinterpret_cast<int*>(s_scr + L.scratch_doubles);
+  uint64_t* s_bar     = reinterpret_cast<uint64_t*>(s_int); // 2 ints
+  int*      s_pidx    = s_int + 2;                          // [seg+1] <= 66
+  int*      s_dirbase = s_int + 72;                         // [27]
+  int*      s_warpcnt = s_int + 100;                        // [4][27]
 
   const int EX = g.seg + NW - 1; // E/B tile extent along x
-  const int TX = g.seg + NS - 1; // J tile extent along x
 
   // tile origins (array indices)
   const int Lb  = g.nb;
@@ -207,17 +204,17 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
   for (int t = tid; t <= ncs; t += THREADS) s_pidx[t] = start[row0 + t * LANES];
   for (int t = tid; t < 27; t += THREADS) s_dirbase[t] = 0;
   for (int t = tid; t < 4 * 27; t += THREADS) s_warpcnt[t] = 0;
-  for (int t = tid; t < L.jt_doubles; t += THREADS) s_jt[t] = 0.0;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(s_bar, (uint32_t)(NW * NW * EX * 6 * sizeof(double)));
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
 
-  const ChunkGeo& c    = P.cg[ch];
-  const int       cb   = P.sp.cbase[ch];
-  const size_t    cap  = P.sp.cap;
+  const ChunkGeo& c   = P.cg[ch];
+  const int       cb  = P.sp.cbase[ch];
+  const size_t    cap = P.sp.cap;
   double* __restrict__ xu = P.sp.xu;
+  double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
 
   // phase-2 role
   const bool dep_active = tid < G * NCOL;
@@ -230,26 +227,33 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
   for (int s = 0; s < NS; s++)
 #pragma unroll
     for (int k = 0; k < 4; k++) acc[s][k] = 0.0;
-  int cc = 0; // current cell (relative to xs) of the sliding deposit window
+  int cc  = 0; // current cell (relative to xs) of the sliding deposit window
+  int par = 0; // staging buffer parity
 
   mbar_wait(s_bar, 0);
 
-  // retire slot 0 of the window into the J tile at x = cc, slide
+  // Retire slot 0 of the window: reduce it over the G groups through the staging buffer and add it
+  // to J in global memory (every (z,y,x) of the CTA's footprint is retired exactly once, so this
+  // is the CTA's single flush of that entry), then slide the window by one cell.
   auto retire = [&]() {
+    double* st = s_stage + par * (G * NCOL * 4);
     if (dep_active) {
 #pragma unroll
-      for (int k = 0; k < 4; k++) s_stage[(grp * NCOL + col) * 4 + k] = acc[0][k];
+      for (int k = 0; k < 4; k++) st[(grp * NCOL + col) * 4 + k] = acc[0][k];
     }
     __syncthreads();
     for (int t = tid; t < NCOL * 4; t += THREADS) {
       double sum = 0.0;
 #pragma unroll
-      for (int gg = 0; gg < G; gg++) sum += s_stage[gg * NCOL * 4 + t];
-      int cl = t >> 2, k = t & 3;
-      int yy = cl % NS, zz = cl / NS;
-      s_jt[((zz * NS + yy) * TX + cc) * 4 + k] += sum;
+      for (int gg = 0; gg < G; gg++) sum += st[gg * NCOL * 4 + t];
+      if (sum != 0.0) {
+        int cl = t >> 2, k = t & 3;
+        int gy = jy0 + cl % NS, gz = jz0 + cl / NS, gx = jx0 + cc;
+        if (gx >= 0 && gx < g.M[2] && gy >= 0 && gy < g.M[1] && gz >= 0 && gz < g.M[0])
+          atomicAdd(&ujc[(((size_t)gz * g.M[1] + gy) * g.M[2] + gx) * 4 + k], sum);
+      }
     }
-    __syncthreads();
+    par ^= 1; // the other buffer is free: its readers passed the barrier above
 #pragma unroll
     for (int s = 0; s < NS - 1; s++)
 #pragma unroll
@@ -264,11 +268,11 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
     const int  i     = b0 + tid;
     const bool valid = i < b1;
     int        dir   = 13;
-    double*    scr   = s_scr + (size_t)tid * FS;
+    double*    scr   = s_scr + tid; // field f of this thread's particle: scr[f * SP]
 
     // =============================== phase 1: push ===============================
     if (valid) {
-      double pos[3], u[3]; // (z, y, x) order for pos/u indices 0,1,2 = z,y,x
+      double pos[3], u[3]; // index 0,1,2 = z,y,x
       pos[2] = xu[soa(0, cap, i)];
       pos[1] = xu[soa(1, cap, i)];
       pos[0] = xu[soa(2, cap, i)];
@@ -278,7 +282,6 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
 
       int    ki[3], sh[3];
       double wi[3][NW], wh[3][NW];
-      bool   sorted_ok = true;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         int ii = digitize(pos[a], c.off[a], g.rdel[a]);
@@ -299,8 +302,8 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
         }
         sh[a] = ii;
       }
-      const int txo = sh[2] - xs; // cell offset inside the segment
-      sorted_ok     = (sh[0] == rz) && (sh[1] == ry) && (txo >= 0) && (txo < ncs);
+      const int  txo       = sh[2] - xs; // cell offset inside the segment
+      const bool sorted_ok = (sh[0] == rz) && (sh[1] == ry) && (txo >= 0) && (txo < ncs);
       if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
       const int tx = sorted_ok ? txo : 0;
 
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
           double rx6[6];
 #pragma unroll
           for (int k = 0; k < 6; k++) rx6[k] = 0.0;
-          const double2* pt = reinterpret_cast<const double2*>(s_eb + ((size_t)(jzz * NW + jyy) * EX + tx) * 6);
+          const double2* pt = reinterpret_cast<const double2*>(s_eb + ((jzz * NW + jyy) * EX + tx) * 6);
 #pragma unroll
           for (int jxx = 0; jxx < NW; jxx++) {
             double2 e01 = pt[3 * jxx + 0], e23 = pt[3 * jxx + 1], e45 = pt[3 * jxx + 2];
@@ -385,16 +388,16 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
       int  dcode  = 0;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        i1[a]  = digitize(pn[a], c.off[a], g.rdel[a]);
-        int dd = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
-        dcode  = dcode * 3 + dd;
+        i1[a]   = digitize(pn[a], c.off[a], g.rdel[a]);
+        int dd  = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
+        dcode   = dcode * 3 + dd;
         int sft = (i1[a] - g.is_odd) - ki[a];
         cfl_ok  = cfl_ok && (sft >= -1) && (sft <= 1);
       }
       dir            = dcode;
       const int lnid = (i - cb) & (LANES - 1);
       if (dir == 13) {
-        int key = (ch * g.ncell + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
+        int key     = (ch * g.ncell + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
         P.sp.key[i] = key;
         atomicAdd(&P.sp.hist[key], 1);
       } else {
@@ -404,8 +407,7 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
       if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
 
       // ---- 1-D deposit weights of this particle -> scratch -----------------------------------
-      const bool   dep_ok = cfl_ok && sorted_ok;
-      const double A = 1.0 / 2, B = 1.0 / 3;
+      const bool dep_ok = cfl_ok && sorted_ok;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         double wn[NW];
@@ -414,36 +416,31 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
         int k1  = i1[a] - g.is_odd;
         int sft = k1 - ki[a];
         shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
-        double s0[NS], s1[NS];
+        const int base_s0 = (a == 2) ? C::X_S0 : (a == 1 ? C::Y_S0 : C::Z_S0);
+        const int base_ds = (a == 2) ? C::X_DS : (a == 1 ? C::Y_DS : C::Z_DS);
+        const int base_cp = (a == 1) ? C::Y_CP : C::Z_CP;
+        double    cp      = 0.0;
 #pragma unroll
         for (int j = 0; j < NS; j++) {
           // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
-          s0[j] = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
-          double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;          // sft = -1 : slot j <- wn[j]
-          double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0;  // sft =  0
-          double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0;  // sft = +1
-          s1[j]     = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
+          double s0 = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
+          double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // sft = -1 : slot j <- wn[j]
+          double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // sft =  0
+          double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // sft = +1
+          double s1 = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
           if (!dep_ok) {
-            s0[j] = 0.0;
-            s1[j] = 0.0;
+            s0 = 0.0;
+            s1 = 0.0;
           }
-        }
-        double cp = 0.0;
-        const int base_s0 = (a == 2) ? C::X_S0 : (a == 1 ? C::Y_S0 : C::Z_S0);
-        const int base_ds = (a == 2) ? C::X_DS : (a == 1 ? C::Y_DS : C::Z_DS);
-        const int base_cp = (a == 2) ? C::X_CP : (a == 1 ? C::Y_CP : C::Z_CP);
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          double ds        = s1[j] - s0[j];
-          scr[base_s0 + j] = s0[j];
-          scr[base_ds + j] = ds;
-          scr[base_cp + j] = cp; // sum of DS over slots < j
-          cp += ds;
+          double ds = s1 - s0; // ds3d, esirkepov.hpp:167-174
           if (a == 2) {
-            scr[C::X_S1 + j] = s1[j];
-            scr[C::X_P + j]  = s0[j] + A * ds;
-            scr[C::X_Q + j]  = A * s0[j] + B * ds;
+            if (j >= 1 && j <= O + 1) scr[(base_s0 + j - 1) * SP] = s0;
+          } else {
+            scr[(base_s0 + j) * SP] = s0;
+            scr[(base_cp + j) * SP] = cp; // sum of DS over slots < j
           }
+          scr[(base_ds + j) * SP] = ds;
+          cp += ds;
         }
       }
     }
@@ -480,14 +477,19 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
     }
 
     // =============================== phase 2: deposit ===============================
+    // Per particle and (jy,jz) column, with S0/DS the old weights and the weight differences:
+    //   rho[x] += q S1y S1z (S0x+DSx)[x]                                           esirkepov.hpp:155-164
+    //   Jx[x]  += -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz) sum_{l<x} DSx[l]            :177-195
+    //   Jy[x]  += -q dy/dt sum_{l<jy} DSy[l] ((S0z+DSz/2) S0x[x] + (S0z/2+DSz/3) DSx[x])     :198-216
+    //   Jz[x]  += -q dz/dt sum_{l<jz} DSz[l] ((S0x+DSx/2)[x] S0y + (S0x/2+DSx/3)[x] DSy)     :219-237
     while (true) {
       const int lo = max(s_pidx[cc], b0);
       const int hi = min(s_pidx[cc + 1], b1);
       if (dep_active) {
         for (int p = lo + grp; p < hi; p += G) {
-          const double* sc  = s_scr + (size_t)(p - b0) * FS;
-          const double  s0y = sc[C::Y_S0 + jy], dsy = sc[C::Y_DS + jy], cyp = sc[C::Y_CP + jy];
-          const double  s0z = sc[C::Z_S0 + jz], dsz = sc[C::Z_DS + jz], czp = sc[C::Z_CP + jz];
+          const double* sc  = s_scr + (p - b0);
+          const double  s0y = sc[(C::Y_S0 + jy) * SP], dsy = sc[(C::Y_DS + jy) * SP], cyp = sc[(C::Y_CP + jy) * SP];
+          const double  s0z = sc[(C::Z_S0 + jz) * SP], dsz = sc[(C::Z_DS + jz) * SP], czp = sc[(C::Z_CP + jz) * SP];
           const double  A = 1.0 / 2, B = 1.0 / 3;
           const double  ar = P.q * (s0y + dsy) * (s0z + dsz);
           const double  wx = -((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz) * P.qdxdt[2];
@@ -495,12 +497,23 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
           const double  g0 = fy * (s0z + A * dsz), g1 = fy * (A * s0z + B * dsz);
           const double  fz = -czp * P.qdxdt[0];
           const double  h0 = fz * s0y, h1 = fz * dsy;
+          const double  k0 = h0 + A * h1, k1 = A * h0 + B * h1;
+          double        cpx = 0.0;
 #pragma unroll
           for (int s = 0; s < NS; s++) {
-            acc[s][0] = fma(ar, sc[C::X_S1 + s], acc[s][0]);
-            acc[s][1] = fma(wx, sc[C::X_CP + s], acc[s][1]);
-            acc[s][2] = fma(g0, sc[C::X_S0 + s], fma(g1, sc[C::X_DS + s], acc[s][2]));
-            acc[s][3] = fma(h0, sc[C::X_P + s], fma(h1, sc[C::X_Q + s], acc[s][3]));
+            const double dsx = sc[(C::X_DS + s) * SP];
+            if (s >= 1 && s <= O + 1) {
+              const double s0x = sc[(C::X_S0 + s - 1) * SP];
+              acc[s][0] = fma(ar, s0x + dsx, acc[s][0]);
+              acc[s][2] = fma(g0, s0x, fma(g1, dsx, acc[s][2]));
+              acc[s][3] = fma(k0, s0x, fma(k1, dsx, acc[s][3]));
+            } else {
+              acc[s][0] = fma(ar, dsx, acc[s][0]);
+              acc[s][2] = fma(g1, dsx, acc[s][2]);
+              acc[s][3] = fma(k1, dsx, acc[s][3]);
+            }
+            if (s >= 1) acc[s][1] = fma(wx, cpx, acc[s][1]);
+            cpx += dsx;
           }
         }
       }
@@ -514,23 +527,8 @@ __global__ void __launch_bounds__(THREADS) k_push_deposit(const __grid_constant_
     __syncthreads(); // scratch may be overwritten by the next batch
   }
 
-  // ---- drain the window, then flush the J tile ---------------------------------------------------
+  // ---- drain the window --------------------------------------------------------------------------
   for (int s = 0; s < NS - 1; s++) retire();
-
-  const int    ntile = NS * NS * TX * 4;
-  double*      ujc   = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
-  for (int t = tid; t < ntile; t += THREADS) {
-    double v = s_jt[t];
-    if (v == 0.0) continue;
-    int k  = t & 3;
-    int r  = t >> 2;
-    int xx = r % TX;
-    int yy = (r / TX) % NS;
-    int zz = r / (TX * NS);
-    int gx = jx0 + xx, gy = jy0 + yy, gz = jz0 + zz;
-    if (gx < 0 || gx >= g.M[2] || gy < 0 || gy >= g.M[1] || gz < 0 || gz >= g.M[0]) continue;
-    atomicAdd(&ujc[(((size_t)gz * g.M[1] + gy) * g.M[2] + gx) * 4 + k], v);
-  }
 
   // leavers of this work item per direction (scanned over the items of the chunk by k_mig_scan)
   if (tid < 27) P.sp.blockdir[((size_t)ch * g.nitem + item) * 27 + tid] = s_dirbase[tid];
