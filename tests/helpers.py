@@ -53,3 +53,34 @@ def ref_pcount_before_sort(c, s):
     pc = c.pcount(s).reshape(-1).astype(np.int64)
     cnt = np.diff(np.concatenate([[0], pc]))
     return cnt.reshape(-1, 8).astype(np.int32)
+
+
+def load_golden_domain(lib, g, order):
+    """Build an oracle Domain from a tests/golden/steps_order*.npz fixture (inputs are stored in it)."""
+    cdims, dims, nb = tuple(g["cdims"]), tuple(g["dims"]), int(g["nb"])
+    q, m = g["q"], g["m"]
+    ns = len(q)
+    nchunk = int(np.prod(cdims))
+    npr = max(len(g[f"in_xu_{k}_{s}"]) for k in range(nchunk) for s in range(ns))
+    dom = no.Domain(lib, cdims, dims, nb, order, ns, q, m, g["coord"], npr)
+    for k, c in enumerate(dom.chunks):
+        c.uf[...] = g[f"in_uf_{k}"]
+        for s in range(ns):
+            c.set_particles(s, g[f"in_xu_{k}_{s}"])
+    dom.exchange(no.MODE_FIELD)
+    dom.sort_only()
+    return dom, ns
+
+
+def gpu_domain_from_golden(g, order, strict=True):
+    from nix_b200 import core
+    cdims, dims, nb = tuple(int(v) for v in g["cdims"]), tuple(int(v) for v in g["dims"]), int(g["nb"])
+    q, m = g["q"], g["m"]
+    d = core.Domain(cdims, dims, nb, order, q, m, coord=g["coord"], strict_fp=strict)
+    for k in range(d.nchunk):
+        d.set_field(k, g[f"in_uf_{k}"])
+    d.exchange_field()
+    for s in range(len(q)):
+        d.set_particles(s, [g[f"in_xu_{k}_{s}"] for k in range(d.nchunk)])
+    d.sort()
+    return d

@@ -1,0 +1,102 @@
+"""Pin the plain-C restatement (oracle/nix_oracle.c) against the reference's own templates
+(oracle/_ref/libnixref.so, built from /root/reference by oracle/Makefile) -- bit for bit -- and the
+reference's vectorised (xsimd, sorted) code path against its scalar path.  Skipped where oracle/_ref
+has not been built and cannot be (no reference sources)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from nix_b200.synth import Problem
+from oracle import nixoracle as no
+
+from helpers import bits, oracle_domain
+
+PD = C.POINTER(C.c_double)
+
+
+def test_impl_names(oracle_port, oracle_ref):
+    assert oracle_port.nixo_impl_name().decode() == "port"
+    assert oracle_ref.nixo_impl_name().decode() == "reference"
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_primitives_bit_exact(oracle_port, oracle_ref, order):
+    rng = np.random.default_rng(100 + order)
+    for _ in range(200):
+        x = float(rng.uniform(-3, 9))
+        X = float(np.floor(x) if order % 2 else np.floor(x + 0.5))
+        a, b = np.zeros(order + 1), np.zeros(order + 1)
+        oracle_port.nixo_shape_mc(order, x, X, 1.0, a.ctypes.data_as(PD))
+        oracle_ref.nixo_shape_mc(order, x, X, 1.0, b.ctypes.data_as(PD))
+        assert np.array_equal(bits(a), bits(b))
+        assert oracle_port.nixo_digitize(x, -1.0, 2.0) == oracle_ref.nixo_digitize(x, -1.0, 2.0)
+    for _ in range(100):
+        u = rng.normal(0, 2.0, 3)
+        eb = np.ascontiguousarray(rng.normal(0, 0.5, 6))
+        ua, ub = u.copy(), u.copy()
+        oracle_port.nixo_push_boris(ua.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.5)
+        oracle_ref.nixo_push_boris(ub.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.5)
+        assert np.array_equal(bits(ua), bits(ub))
+        assert oracle_port.nixo_lorentz_factor(*u, 1 / 1.5) == oracle_ref.nixo_lorentz_factor(*u, 1 / 1.5)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("cdims,dims", [((2, 2, 2), (6, 6, 6)), ((1, 1, 1), (8, 8, 8)), ((3, 1, 2), (5, 7, 6))])
+def test_full_steps_bit_exact(oracle_port, oracle_ref, order, cdims, dims):
+    prob = Problem(cdims, dims, order, ppc=5, seed=70 + order, vth=(0.35, 0.08))
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    for step in range(3):
+        a.step(0.5, 1.0)
+        b.step(0.5, 1.0)
+        for ca, cb in zip(a.chunks, b.chunks):
+            assert np.array_equal(bits(ca.uj), bits(cb.uj)), f"step {step}: J"
+            assert np.array_equal(bits(ca.uf), bits(cb.uf))
+            for s in range(prob.ns):
+                assert ca.np(s) == cb.np(s)
+                assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s))), f"step {step}: particles"
+                assert np.array_equal(ca.pindex(s), cb.pindex(s))
+                assert np.array_equal(ca.pcount(s), cb.pcount(s))
+    assert a.total_particles() == b.total_particles() == prob.total_particles()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_reference_simd_path_matches_scalar(oracle_ref, order):
+    """The xsimd sorted path (interp3d_impl_sorted, append_current3d with reduce_add) differs from
+    the scalar path by summation order only."""
+    prob = Problem((2, 2, 1), (6, 6, 6), order, ppc=9, seed=80 + order, vth=(0.3, 0.05))
+    a = oracle_domain(oracle_ref, prob)
+    b = oracle_domain(oracle_ref, prob)
+    a.clear_current()
+    b.clear_current()
+    a.push_deposit(0.5, 1.0, simd=False)
+    b.push_deposit(0.5, 1.0, simd=True)
+    for ca, cb in zip(a.chunks, b.chunks):
+        scale = np.abs(ca.uj).max()
+        assert np.abs(ca.uj - cb.uj).max() < 1e-13 * scale
+        for s in range(prob.ns):
+            pa, pb = ca.particles(s), cb.particles(s)
+            assert np.array_equal(bits(pa[:, 6]), bits(pb[:, 6]))
+            assert np.abs(pa[:, :6] - pb[:, :6]).max() < 1e-13 * np.abs(pa[:, :6]).max()
+
+
+def test_halo_buffers_bit_exact(oracle_port, oracle_ref):
+    """Send-buffer layout and contents (Chunk::set_mpi_buffer chunk.cpp:257-286, Halo pack)."""
+    prob = Problem((2, 2, 2), (4, 5, 6), 2, ppc=3, seed=91, vth=(0.5, 0.2))
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    a.clear_current(); b.clear_current()
+    a.push_deposit(0.5, 1.0); b.push_deposit(0.5, 1.0)
+    for mode in (no.MODE_FIELD, no.MODE_CURRENT):
+        for ca, cb in zip(a.chunks, b.chunks):
+            assert np.array_equal(ca.bufsize(mode), cb.bufsize(mode))
+            assert np.array_equal(ca.bufaddr(mode), cb.bufaddr(mode))
+            ca.halo_pack(mode); cb.halo_pack(mode)
+            assert np.array_equal(ca.sendbuf(mode), cb.sendbuf(mode))
+    for ca, cb in zip(a.chunks, b.chunks):
+        for s in range(prob.ns):
+            ca.count(s, 0, ca.np(s) - 1, True); cb.count(s, 0, cb.np(s) - 1, True)
+        ca.halo_pack(no.MODE_PARTICLE); cb.halo_pack(no.MODE_PARTICLE)
+        assert np.array_equal(ca.bufsize(no.MODE_PARTICLE), cb.bufsize(no.MODE_PARTICLE))
+        assert np.array_equal(ca.sendbuf(no.MODE_PARTICLE), cb.sendbuf(no.MODE_PARTICLE))
