@@ -15,16 +15,22 @@
 //   * TMA (cp.async.bulk.tensor.5d) stages the (O+2)x(O+2)x(SEG+O+1)x6 E/B tile of the row -- ghosts
 //     included -- into shared memory; an mbarrier signals arrival.
 //   * phase 1, thread per particle (batches of 128): coalesced SoA loads, weights, gather from the
-//     smem tile, Boris, move, coalesced stores, bin of the new position (-> key + histogram, or a
-//     leaver record with its ordered rank inside the item), and the 1-D deposit weights of the
-//     particle into a smem scratch.
-//   * phase 2, thread per (jy,jz) column of the (O+3)^3 deposit mesh, G groups splitting the
-//     particles of the current cell: the Esirkepov current of every particle is accumulated in
-//     REGISTERS over all particles of the cell (the GPU analogue of the reference's sorted
-//     `reduce_add` path, primitives.hpp:798-809).  The mesh slides along x with the cell index:
-//     the column that falls out of the window is reduced over the groups through a small staging
-//     buffer and added to the J tile in shared memory (no atomics, fixed order).
-//   * the J tile is flushed to global memory once per CTA with red.global.add.f64.
+//     smem tile over the EXACT support of every component ((O+1)^3 points; the half-grid components
+//     start one node later when the particle sits in the upper half of its cell), Boris, move,
+//     coalesced stores, bin of the new position (-> key + histogram, or a leaver record with its
+//     ordered rank inside the item), and the 1-D deposit weights of the particle into a
+//     particle-major scratch row (128-bit stores, conflict free).
+//   * phase 2 accumulates the Esirkepov current of all particles of one cell in REGISTERS (the GPU
+//     analogue of the reference's sorted `reduce_add` path, primitives.hpp:798-809), thread per
+//     (jy,jz) column of the deposit mesh, particles of the cell split over thread groups:
+//       F path  particles that stay in their cell (the vast majority): their weights touch only the
+//               central (O+1)^3 nodes, so a group is (O+1)^2 threads and the x loop has O+1 slots;
+//               the accumulators slide along x with the cell index and live across batches.
+//       C path  particles that change cell: full (O+3)^3 mesh, (O+3)^2 threads per group, transient
+//               accumulators flushed into a small sliding window in shared memory.
+//     When a cell is finished the x-slot that leaves the window is reduced over the groups through
+//     a staging buffer, merged with the C window and added to J in global memory with
+//     red.global.add.f64 -- once per (z,y,x,component) and CTA, no shared-memory atomics.
 #include "common.cuh"
 
 namespace nixb200
@@ -32,27 +38,34 @@ namespace nixb200
 namespace
 {
 constexpr int THREADS = 128;
+constexpr int NWARP   = THREADS / 32;
+constexpr int MAXSEG  = 48;
 
 template <int O>
 struct Cfg {
-  static constexpr int NW   = O + 2;          // gather stencil width   (interp.hpp)
+  static constexpr int NW   = O + 2;          // gather stencil width of the staged tile (interp.hpp)
+  static constexpr int N1   = O + 1;          // support of one shape function
   static constexpr int NS   = O + 3;          // deposit mesh width     (esirkepov.hpp:326-328)
-  static constexpr int NCOL = NS * NS;        // (jy,jz) columns
-  static constexpr int G    = THREADS / NCOL; // particle groups: 8 / 5 / 3
-  // per-particle scratch, stored field-major ([field][particle], row stride SP) so that the stores of
-  // phase 1 (consecutive particles) and the loads of phase 2 (consecutive fields) are conflict free
-  static constexpr int X_S0 = 0;              // S0x[1..O+1]        (O+1 values; slots 0 and O+2 are 0)
-  static constexpr int X_DS = X_S0 + O + 1;   // DSx[0..NS-1]
-  static constexpr int Y_S0 = X_DS + NS, Y_DS = Y_S0 + NS, Y_CP = Y_DS + NS;
-  static constexpr int Z_S0 = Y_CP + NS, Z_DS = Z_S0 + NS, Z_CP = Z_DS + NS;
-  static constexpr int F    = Z_CP + NS;      // 30 / 38 / 46 doubles per particle
-  static constexpr int SP   = THREADS + 1;    // odd row stride
+  static constexpr int NCOL = NS * NS;        // (jy,jz) columns of the full mesh       (C path)
+  static constexpr int GC   = THREADS / NCOL; // C groups: 8 / 5 / 3
+  static constexpr int NCF  = N1 * N1;        // (jy,jz) columns of the central mesh    (F path)
+  static constexpr int GF   = THREADS / NCF;  // F groups: 32 / 14 / 8
+  // particle-major scratch row (doubles); pairs are 16-byte aligned
+  static constexpr int PY  = 0;               // (S0y[j], DSy[j]) j = 1..N1
+  static constexpr int PZ  = 2 * N1;
+  static constexpr int PX  = 4 * N1;
+  static constexpr int CY  = 6 * N1;          // CPy[j] = sum of DSy over slots < j, j = 1..N1
+  static constexpr int CZ  = 7 * N1;
+  static constexpr int OUT = 8 * N1;          // DSy0 DSyL CPyL DSz0 DSzL CPzL DSx0 DSxL  (L = NS-1)
+  static constexpr int ROW = 8 * N1 + 10;     // == 2 (mod 4): 128-bit stores of 8 lanes hit 32 banks
 };
 
 struct SmemLayout {
-  int    eb_doubles, stage_doubles, scratch_doubles;
+  int    eb_doubles, stf_doubles, win_doubles, scratch_doubles;
   size_t bytes;
 };
+
+constexpr int SMEM_INTS = 1024;
 
 template <int O>
 __host__ __device__ inline SmemLayout smem_layout(int seg)
@@ -61,10 +74,11 @@ __host__ __device__ inline SmemLayout smem_layout(int seg)
   SmemLayout L;
   int        ex     = seg + C::NW - 1;
   L.eb_doubles      = ((C::NW * C::NW * ex * 6) + 15) / 16 * 16; // keep 128-byte multiples
-  L.stage_doubles   = ((2 * C::G * C::NCOL * 4) + 15) / 16 * 16; // double buffered
-  L.scratch_doubles = (C::F * C::SP + 15) / 16 * 16;
-  L.bytes = sizeof(double) * ((size_t)L.eb_doubles + L.stage_doubles + L.scratch_doubles) +
-            256 * sizeof(int) /* ints */;
+  L.stf_doubles     = ((2 * C::GF * C::NCF * 4) + 15) / 16 * 16; // double buffered
+  L.win_doubles     = ((C::NS * C::NCOL * 4) + 15) / 16 * 16;
+  L.scratch_doubles = (C::ROW * THREADS + 15) / 16 * 16;
+  L.bytes = sizeof(double) * ((size_t)L.eb_doubles + L.stf_doubles + L.win_doubles + L.scratch_doubles) +
+            SMEM_INTS * sizeof(int);
   return L;
 }
 
@@ -137,6 +151,31 @@ __device__ __forceinline__ void shape_mc(double x, double X, double rdx, double*
   }
 }
 
+// One field component gathered over its exact support (interp3d_impl_sorted, interp.hpp:95-113:
+// same nesting and summation order; the reference's extra stencil slot carries a zero weight).
+// e points at (bz, by, tx + bx, component); EX = x extent of the staged tile.
+template <int O, bool S>
+__device__ __forceinline__ double gather1(const double* __restrict__ e, int EX, const double* wz,
+                                          const double* wy, const double* wx)
+{
+  constexpr int NW = O + 2;
+  double        rz = 0.0;
+#pragma unroll
+  for (int jz = 0; jz <= O; jz++) {
+    double ry = 0.0;
+#pragma unroll
+    for (int jy = 0; jy <= O; jy++) {
+      double        rx = 0.0;
+      const double* p  = e + (size_t)((jz * NW + jy) * EX) * 6;
+#pragma unroll
+      for (int jx = 0; jx <= O; jx++) rx = mad<S>(p[jx * 6], wx[jx], rx);
+      ry = mad<S>(rx, wy[jy], ry);
+    }
+    rz = mad<S>(ry, wz[jz], rz);
+  }
+  return rz;
+}
+
 struct Kparams {
   Geo             geo;
   const ChunkGeo* cg;
@@ -153,10 +192,13 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
 {
   using C            = Cfg<O>;
   constexpr int NW   = C::NW;
+  constexpr int N1   = C::N1;
   constexpr int NS   = C::NS;
   constexpr int NCOL = C::NCOL;
-  constexpr int G    = C::G;
-  constexpr int SP   = C::SP;
+  constexpr int GC   = C::GC;
+  constexpr int NCF  = C::NCF;
+  constexpr int GF   = C::GF;
+  constexpr int ROW  = C::ROW;
   const Geo&    g    = P.geo;
   const int     tid  = threadIdx.x;
   const int     lane = tid & 31;
@@ -181,13 +223,18 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
   extern __shared__ __align__(1024) double smem_d[];
   const SmemLayout L = smem_layout<O>(g.seg);
   double*   s_eb      = smem_d;
-  double*   s_stage   = smem_d + L.eb_doubles;
-  double*   s_scr     = s_stage + L.stage_doubles;
+  double*   s_stf     = smem_d + L.eb_doubles;
+  double*   s_win     = s_stf + L.stf_doubles;
+  double*   s_scr     = s_win + L.win_doubles;
   int*      s_int     = reinterpret_cast<int*>(s_scr + L.scratch_doubles);
   uint64_t* s_bar     = reinterpret_cast<uint64_t*>(s_int); // 2 ints
-  int*      s_pidx    = s_int + 2;                          // [seg+1] <= 66
-  int*      s_dirbase = s_int + 72;                         // [27]
-  int*      s_warpcnt = s_int + 100;                        // [4][27]
+  int*      s_pidx    = s_int + 2;                          // [seg+1]
+  int*      s_dirbase = s_int + 64;                         // [27]
+  int*      s_warpcnt = s_int + 96;                         // [4][27]
+  int*      s_ccnt    = s_int + 208;                        // [2][MAXSEG] movers per cell, by batch parity
+  int*      s_wcnt    = s_int + 304;                        // [4] movers per warp
+  int*      s_cls     = s_int + 320;                        // [128] 1 = mover (C path)
+  int*      s_clist   = s_int + 448;                        // [4][32] batch slots of the movers, per warp
 
   const int EX = g.seg + NW - 1; // E/B tile extent along x
 
@@ -204,6 +251,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
   for (int t = tid; t <= ncs; t += THREADS) s_pidx[t] = start[row0 + t * LANES];
   for (int t = tid; t < 27; t += THREADS) s_dirbase[t] = 0;
   for (int t = tid; t < 4 * 27; t += THREADS) s_warpcnt[t] = 0;
+  for (int t = tid; t < 2 * MAXSEG; t += THREADS) s_ccnt[t] = 0;
+  for (int t = tid; t < NS * NCOL * 4; t += THREADS) s_win[t] = 0.0;
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(s_bar, (uint32_t)(NW * NW * EX * 6 * sizeof(double)));
@@ -216,50 +265,76 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
   double* __restrict__ xu = P.sp.xu;
   double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
 
-  // phase-2 role
-  const bool dep_active = tid < G * NCOL;
-  const int  grp        = tid / NCOL;
-  const int  col        = tid % NCOL;
-  const int  jy         = col % NS;
-  const int  jz         = col / NS;
-  double     acc[NS][4];
+  // ---- phase-2 roles ---------------------------------------------------------------------------
+  // F: group gf, central column (fy, fz) in 0..O  <->  mesh column (fy+1, fz+1)
+  const bool f_active = tid < GF * NCF;
+  const int  gf       = tid / NCF;
+  const int  colf     = tid % NCF;
+  const int  fy       = colf % N1;
+  const int  fz       = colf / N1;
+  // C: group gc, mesh column (jy, jz) in 0..NS-1
+  const bool c_active = tid < GC * NCOL;
+  const int  gc       = tid / NCOL;
+  const int  col      = tid % NCOL;
+  const int  jy       = col % NS;
+  const int  jz       = col / NS;
+  // scratch offsets of this C column: (S0, DS) pair or lone DS, and CP; -1 = identically zero
+  const int c_py = (jy >= 1 && jy <= N1) ? C::PY + 2 * (jy - 1) : -1;
+  const int c_dy = (jy == 0) ? C::OUT + 0 : C::OUT + 1;
+  const int c_cy = (jy == 0) ? -1 : ((jy <= N1) ? C::CY + jy - 1 : C::OUT + 2);
+  const int c_pz = (jz >= 1 && jz <= N1) ? C::PZ + 2 * (jz - 1) : -1;
+  const int c_dz = (jz == 0) ? C::OUT + 3 : C::OUT + 4;
+  const int c_cz = (jz == 0) ? -1 : ((jz <= N1) ? C::CZ + jz - 1 : C::OUT + 5);
+
+  // F accumulators: slot 0 carries the previous cell's slot 1, slots 1..N1 receive this cell
+  double accf[N1 + 1][4];
 #pragma unroll
-  for (int s = 0; s < NS; s++)
+  for (int s = 0; s <= N1; s++)
 #pragma unroll
-    for (int k = 0; k < 4; k++) acc[s][k] = 0.0;
-  int cc  = 0; // current cell (relative to xs) of the sliding deposit window
-  int par = 0; // staging buffer parity
+    for (int k = 0; k < 4; k++) accf[s][k] = 0.0;
+  int cc   = 0; // current cell (relative to xs) of the sliding deposit window
+  int par  = 0; // staging buffer parity
+  int rot  = 0; // C window rotation: mesh slot s lives at plane (s + rot) % NS
+  int bpar = 0; // batch parity of s_ccnt
 
   mbar_wait(s_bar, 0);
 
-  // Retire slot 0 of the window: reduce it over the G groups through the staging buffer and add it
-  // to J in global memory (every (z,y,x) of the CTA's footprint is retired exactly once, so this
-  // is the CTA's single flush of that entry), then slide the window by one cell.
+  // Retire slot 0 of the window: reduce the F accumulators over the GF groups through the staging
+  // buffer, merge the C window, add to J in global memory (every (z,y,x) of the CTA's footprint is
+  // retired exactly once, so this is the CTA's single flush of that entry), then slide by one cell.
   auto retire = [&]() {
-    double* st = s_stage + par * (G * NCOL * 4);
-    if (dep_active) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) st[(grp * NCOL + col) * 4 + k] = acc[0][k];
+    double* st = s_stf + par * (GF * NCF * 4);
+    if (f_active) {
+      double2* o = reinterpret_cast<double2*>(st + (gf * NCF + colf) * 4);
+      o[0]       = make_double2(accf[0][0], accf[0][1]);
+      o[1]       = make_double2(accf[0][2], accf[0][3]);
     }
     __syncthreads();
+    double* w0 = s_win + (rot % NS) * (NCOL * 4);
     for (int t = tid; t < NCOL * 4; t += THREADS) {
-      double sum = 0.0;
-#pragma unroll
-      for (int gg = 0; gg < G; gg++) sum += st[gg * NCOL * 4 + t];
+      const int cl = t >> 2, k = t & 3;
+      const int yy = cl % NS, zz = cl / NS;
+      double    sum = w0[t];
+      w0[t]         = 0.0;
+      if (yy >= 1 && yy <= N1 && zz >= 1 && zz <= N1) {
+        const double* sp = st + ((zz - 1) * N1 + (yy - 1)) * 4 + k;
+#pragma unroll 4
+        for (int gg = 0; gg < GF; gg++) sum += sp[gg * NCF * 4];
+      }
       if (sum != 0.0) {
-        int cl = t >> 2, k = t & 3;
-        int gy = jy0 + cl % NS, gz = jz0 + cl / NS, gx = jx0 + cc;
+        int gy = jy0 + yy, gz = jz0 + zz, gx = jx0 + cc;
         if (gx >= 0 && gx < g.M[2] && gy >= 0 && gy < g.M[1] && gz >= 0 && gz < g.M[0])
           atomicAdd(&ujc[(((size_t)gz * g.M[1] + gy) * g.M[2] + gx) * 4 + k], sum);
       }
     }
     par ^= 1; // the other buffer is free: its readers passed the barrier above
+    rot = (rot + 1) % NS;
 #pragma unroll
-    for (int s = 0; s < NS - 1; s++)
+    for (int s = 0; s < N1; s++)
 #pragma unroll
-      for (int k = 0; k < 4; k++) acc[s][k] = acc[s + 1][k];
+      for (int k = 0; k < 4; k++) accf[s][k] = accf[s + 1][k];
 #pragma unroll
-    for (int k = 0; k < 4; k++) acc[NS - 1][k] = 0.0;
+    for (int k = 0; k < 4; k++) accf[N1][k] = 0.0;
     cc++;
   };
 
@@ -268,7 +343,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
     const int  i     = b0 + tid;
     const bool valid = i < b1;
     int        dir   = 13;
-    double*    scr   = s_scr + tid; // field f of this thread's particle: scr[f * SP]
+    bool       mover = false;
+    int*       ccnt  = s_ccnt + bpar * MAXSEG;
 
     // =============================== phase 1: push ===============================
     if (valid) {
@@ -280,26 +356,18 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
       u[1]   = xu[soa(4, cap, i)];
       u[0]   = xu[soa(5, cap, i)];
 
-      int    ki[3], sh[3];
-      double wi[3][NW], wh[3][NW];
+      int    ki[3], sh[3], bh[3];
+      double wi[3][N1], wh[3][N1];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         int ii = digitize(pos[a], c.off[a], g.rdel[a]);
         ki[a]  = ii - g.is_odd;
         int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
-#pragma unroll
-        for (int j = 0; j < NW; j++) {
-          wi[a][j] = 0.0;
-          wh[a][j] = 0.0;
-        }
         shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
         shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
-        // interp::shift_weights<O>(hh - ki, wh)  interp.hpp:154-160
-        if (hh - ki[a] > 0) {
-#pragma unroll
-          for (int j = NW - 1; j > 0; j--) wh[a][j] = wh[a][j - 1];
-          wh[a][0] = 0.0;
-        }
+        // interp::shift_weights<O>(hh - ki, wh)  interp.hpp:154-160: the half-grid support starts
+        // one node later; kept as a base offset instead of moving the weights
+        bh[a] = (hh - ki[a] > 0) ? 1 : 0;
         sh[a] = ii;
       }
       const int  txo       = sh[2] - xs; // cell offset inside the segment
@@ -307,45 +375,16 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
       if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
       const int tx = sorted_ok ? txo : 0;
 
-      // ---- gather: 6 components, factorised exactly like interp3d_impl_sorted -----------------
+      // ---- gather: Ex Ey Ez Bx By Bz; half-grid axes: Ex x | Ey y | Ez z | Bx y,z | By x,z | Bz x,y
+      const double* e0 = s_eb + (size_t)tx * 6;
+      auto          at = [&](int bz, int by, int bx, int k) { return e0 + (size_t)((bz * NW + by) * EX + bx) * 6 + k; };
       double rz6[6];
-#pragma unroll
-      for (int k = 0; k < 6; k++) rz6[k] = 0.0;
-#pragma unroll
-      for (int jzz = 0; jzz < NW; jzz++) {
-        double ry6[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) ry6[k] = 0.0;
-#pragma unroll
-        for (int jyy = 0; jyy < NW; jyy++) {
-          double rx6[6];
-#pragma unroll
-          for (int k = 0; k < 6; k++) rx6[k] = 0.0;
-          const double2* pt = reinterpret_cast<const double2*>(s_eb + ((jzz * NW + jyy) * EX + tx) * 6);
-#pragma unroll
-          for (int jxx = 0; jxx < NW; jxx++) {
-            double2 e01 = pt[3 * jxx + 0], e23 = pt[3 * jxx + 1], e45 = pt[3 * jxx + 2];
-            rx6[0] = mad<S>(e01.x, wh[2][jxx], rx6[0]); // Ex: half in x
-            rx6[1] = mad<S>(e01.y, wi[2][jxx], rx6[1]); // Ey
-            rx6[2] = mad<S>(e23.x, wi[2][jxx], rx6[2]); // Ez
-            rx6[3] = mad<S>(e23.y, wi[2][jxx], rx6[3]); // Bx
-            rx6[4] = mad<S>(e45.x, wh[2][jxx], rx6[4]); // By
-            rx6[5] = mad<S>(e45.y, wh[2][jxx], rx6[5]); // Bz
-          }
-          ry6[0] = mad<S>(rx6[0], wi[1][jyy], ry6[0]);
-          ry6[1] = mad<S>(rx6[1], wh[1][jyy], ry6[1]); // Ey: half in y
-          ry6[2] = mad<S>(rx6[2], wi[1][jyy], ry6[2]);
-          ry6[3] = mad<S>(rx6[3], wh[1][jyy], ry6[3]); // Bx
-          ry6[4] = mad<S>(rx6[4], wi[1][jyy], ry6[4]);
-          ry6[5] = mad<S>(rx6[5], wh[1][jyy], ry6[5]); // Bz
-        }
-        rz6[0] = mad<S>(ry6[0], wi[0][jzz], rz6[0]);
-        rz6[1] = mad<S>(ry6[1], wi[0][jzz], rz6[1]);
-        rz6[2] = mad<S>(ry6[2], wh[0][jzz], rz6[2]); // Ez: half in z
-        rz6[3] = mad<S>(ry6[3], wh[0][jzz], rz6[3]); // Bx
-        rz6[4] = mad<S>(ry6[4], wh[0][jzz], rz6[4]); // By
-        rz6[5] = mad<S>(ry6[5], wi[0][jzz], rz6[5]);
-      }
+      rz6[0] = gather1<O, S>(at(0, 0, bh[2], 0), EX, wi[0], wi[1], wh[2]);
+      rz6[1] = gather1<O, S>(at(0, bh[1], 0, 1), EX, wi[0], wh[1], wi[2]);
+      rz6[2] = gather1<O, S>(at(bh[0], 0, 0, 2), EX, wh[0], wi[1], wi[2]);
+      rz6[3] = gather1<O, S>(at(bh[0], bh[1], 0, 3), EX, wh[0], wh[1], wi[2]);
+      rz6[4] = gather1<O, S>(at(bh[0], 0, bh[2], 4), EX, wh[0], wi[1], wh[2]);
+      rz6[5] = gather1<O, S>(at(0, bh[1], bh[2], 5), EX, wi[0], wh[1], wh[2]);
       double ex = mul<S>(rz6[0], P.dt1), ey = mul<S>(rz6[1], P.dt1), ez = mul<S>(rz6[2], P.dt1);
       double bx = mul<S>(rz6[3], P.dt1), by = mul<S>(rz6[4], P.dt1), bz = mul<S>(rz6[5], P.dt1);
 
@@ -386,6 +425,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
       int  i1[3];
       bool cfl_ok = true;
       int  dcode  = 0;
+      bool moved  = false;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         i1[a]   = digitize(pn[a], c.off[a], g.rdel[a]);
@@ -393,6 +433,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
         dcode   = dcode * 3 + dd;
         int sft = (i1[a] - g.is_odd) - ki[a];
         cfl_ok  = cfl_ok && (sft >= -1) && (sft <= 1);
+        moved   = moved || (sft != 0);
       }
       dir            = dcode;
       const int lnid = (i - cb) & (LANES - 1);
@@ -406,23 +447,24 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
       }
       if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
 
-      // ---- 1-D deposit weights of this particle -> scratch -----------------------------------
+      // ---- 1-D deposit weights of this particle -> scratch row --------------------------------
+      // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
+      // ds = ss[1] - ss[0] (ds3d, esirkepov.hpp:167-174); cp[j] = sum of ds over slots < j
       const bool dep_ok = cfl_ok && sorted_ok;
+      mover             = dep_ok && moved;
+      double* row       = s_scr + (size_t)tid * ROW;
+      double  tail[2 * N1 + 8]; // CPy[1..N1] CPz[1..N1] | DSy0 DSyL CPyL DSz0 DSzL CPzL DSx0 DSxL
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        double wn[NW];
-#pragma unroll
-        for (int j = 0; j < NW; j++) wn[j] = 0.0;
-        int k1  = i1[a] - g.is_odd;
-        int sft = k1 - ki[a];
+        double wn[N1];
+        int    k1  = i1[a] - g.is_odd;
+        int    sft = k1 - ki[a];
         shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
-        const int base_s0 = (a == 2) ? C::X_S0 : (a == 1 ? C::Y_S0 : C::Z_S0);
-        const int base_ds = (a == 2) ? C::X_DS : (a == 1 ? C::Y_DS : C::Z_DS);
-        const int base_cp = (a == 1) ? C::Y_CP : C::Z_CP;
-        double    cp      = 0.0;
+        const int base_p = (a == 2) ? C::PX : (a == 1 ? C::PY : C::PZ);
+        double    cp     = 0.0;
+        double    cpv[NS], dsv[NS], s0v[NS];
 #pragma unroll
         for (int j = 0; j < NS; j++) {
-          // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
           double s0 = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
           double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // sft = -1 : slot j <- wn[j]
           double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // sft =  0
@@ -432,17 +474,39 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
             s0 = 0.0;
             s1 = 0.0;
           }
-          double ds = s1 - s0; // ds3d, esirkepov.hpp:167-174
-          if (a == 2) {
-            if (j >= 1 && j <= O + 1) scr[(base_s0 + j - 1) * SP] = s0;
-          } else {
-            scr[(base_s0 + j) * SP] = s0;
-            scr[(base_cp + j) * SP] = cp; // sum of DS over slots < j
-          }
-          scr[(base_ds + j) * SP] = ds;
-          cp += ds;
+          s0v[j] = s0;
+          dsv[j] = s1 - s0;
+          cpv[j] = cp;
+          cp += dsv[j];
+        }
+#pragma unroll
+        for (int j = 1; j <= N1; j++)
+          *reinterpret_cast<double2*>(row + base_p + 2 * (j - 1)) = make_double2(s0v[j], dsv[j]);
+        if (a != 2) {
+          const int tc = (a == 1) ? 0 : N1;
+          const int to = 2 * N1 + ((a == 1) ? 0 : 3);
+#pragma unroll
+          for (int j = 1; j <= N1; j++) tail[tc + j - 1] = cpv[j];
+          tail[to + 0] = dsv[0];
+          tail[to + 1] = dsv[NS - 1];
+          tail[to + 2] = cpv[NS - 1];
+        } else {
+          tail[2 * N1 + 6] = dsv[0];
+          tail[2 * N1 + 7] = dsv[NS - 1];
         }
       }
+#pragma unroll
+      for (int j = 0; j < N1 + 4; j++)
+        *reinterpret_cast<double2*>(row + C::CY + 2 * j) = make_double2(tail[2 * j], tail[2 * j + 1]);
+      s_cls[tid] = mover ? 1 : 0;
+      if (mover) atomicAdd(&ccnt[tx], 1);
+    }
+
+    // ---- movers of this batch, in particle order (per-warp lists) ------------------------------
+    {
+      const unsigned mm = __ballot_sync(0xffffffffu, mover);
+      if (mover) s_clist[warp * 32 + __popc(mm & ((1u << lane) - 1))] = tid;
+      if (lane == 0) s_wcnt[warp] = __popc(mm);
     }
 
     // ---- ordered rank of the leavers inside this work item (segmented counting scan) ----------
@@ -475,6 +539,8 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
       }
       // (next use of s_warpcnt / s_dirbase is behind the barriers of phase 2)
     }
+    // the other parity's mover counts are free now (last read before the barrier above)
+    for (int t = tid; t < MAXSEG; t += THREADS) s_ccnt[(bpar ^ 1) * MAXSEG + t] = 0;
 
     // =============================== phase 2: deposit ===============================
     // Per particle and (jy,jz) column, with S0/DS the old weights and the weight differences:
@@ -482,41 +548,130 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
     //   Jx[x]  += -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz) sum_{l<x} DSx[l]            :177-195
     //   Jy[x]  += -q dy/dt sum_{l<jy} DSy[l] ((S0z+DSz/2) S0x[x] + (S0z/2+DSz/3) DSx[x])     :198-216
     //   Jz[x]  += -q dz/dt sum_{l<jz} DSz[l] ((S0x+DSx/2)[x] S0y + (S0x/2+DSx/3)[x] DSy)     :219-237
+    const int nmov_w[NWARP] = {s_wcnt[0], s_wcnt[1], s_wcnt[2], s_wcnt[3]};
+    int       cbase_e       = 0; // movers of this batch in cells before cc
+    const double A = 1.0 / 2, B = 1.0 / 3;
     while (true) {
-      const int lo = max(s_pidx[cc], b0);
-      const int hi = min(s_pidx[cc + 1], b1);
-      if (dep_active) {
-        for (int p = lo + grp; p < hi; p += G) {
-          const double* sc  = s_scr + (p - b0);
-          const double  s0y = sc[(C::Y_S0 + jy) * SP], dsy = sc[(C::Y_DS + jy) * SP], cyp = sc[(C::Y_CP + jy) * SP];
-          const double  s0z = sc[(C::Z_S0 + jz) * SP], dsz = sc[(C::Z_DS + jz) * SP], czp = sc[(C::Z_CP + jz) * SP];
-          const double  A = 1.0 / 2, B = 1.0 / 3;
+      const int lo = max(s_pidx[cc], b0) - b0;
+      const int hi = min(s_pidx[cc + 1], b1) - b0;
+
+      // ---------- F path: particles that stay in their cell ----------
+      if (f_active) {
+        for (int p = lo + gf; p < hi; p += GF) {
+          if (s_cls[p]) continue;
+          const double* sc  = s_scr + (size_t)p * ROW;
+          const double2 yv  = *reinterpret_cast<const double2*>(sc + C::PY + 2 * fy);
+          const double2 zv  = *reinterpret_cast<const double2*>(sc + C::PZ + 2 * fz);
+          const double  cyp = sc[C::CY + fy], czp = sc[C::CZ + fz];
+          const double  s0y = yv.x, dsy = yv.y, s0z = zv.x, dsz = zv.y;
           const double  ar = P.q * (s0y + dsy) * (s0z + dsz);
           const double  wx = -((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz) * P.qdxdt[2];
-          const double  fy = -cyp * P.qdxdt[1];
-          const double  g0 = fy * (s0z + A * dsz), g1 = fy * (A * s0z + B * dsz);
-          const double  fz = -czp * P.qdxdt[0];
-          const double  h0 = fz * s0y, h1 = fz * dsy;
+          const double  fyv = -cyp * P.qdxdt[1];
+          const double  g0 = fyv * (s0z + A * dsz), g1 = fyv * (A * s0z + B * dsz);
+          const double  fzv = -czp * P.qdxdt[0];
+          const double  h0 = fzv * s0y, h1 = fzv * dsy;
           const double  k0 = h0 + A * h1, k1 = A * h0 + B * h1;
           double        cpx = 0.0;
 #pragma unroll
-          for (int s = 0; s < NS; s++) {
-            const double dsx = sc[(C::X_DS + s) * SP];
-            if (s >= 1 && s <= O + 1) {
-              const double s0x = sc[(C::X_S0 + s - 1) * SP];
-              acc[s][0] = fma(ar, s0x + dsx, acc[s][0]);
-              acc[s][2] = fma(g0, s0x, fma(g1, dsx, acc[s][2]));
-              acc[s][3] = fma(k0, s0x, fma(k1, dsx, acc[s][3]));
-            } else {
-              acc[s][0] = fma(ar, dsx, acc[s][0]);
-              acc[s][2] = fma(g1, dsx, acc[s][2]);
-              acc[s][3] = fma(k1, dsx, acc[s][3]);
-            }
-            if (s >= 1) acc[s][1] = fma(wx, cpx, acc[s][1]);
+          for (int s = 0; s < N1; s++) {
+            const double2 xv  = *reinterpret_cast<const double2*>(sc + C::PX + 2 * s);
+            const double  s0x = xv.x, dsx = xv.y;
+            accf[s + 1][0]    = fma(ar, s0x + dsx, accf[s + 1][0]);
+            if (s >= 1) accf[s + 1][1] = fma(wx, cpx, accf[s + 1][1]);
+            accf[s + 1][2] = fma(g0, s0x, fma(g1, dsx, accf[s + 1][2]));
+            accf[s + 1][3] = fma(k0, s0x, fma(k1, dsx, accf[s + 1][3]));
             cpx += dsx;
           }
         }
       }
+
+      // ---------- C path: particles that change cell (block-uniform control flow) ----------
+      const int nmc = s_ccnt[bpar * MAXSEG + cc];
+      if (nmc > 0) {
+        double accc[NS][4];
+#pragma unroll
+        for (int s = 0; s < NS; s++)
+#pragma unroll
+          for (int k = 0; k < 4; k++) accc[s][k] = 0.0;
+        if (c_active) {
+          for (int e = cbase_e + gc; e < cbase_e + nmc; e += GC) {
+            // e-th mover of the batch -> (warp list, index)
+            int w = 0, r = e;
+#pragma unroll
+            for (int q = 0; q < NWARP - 1; q++)
+              if (w == q && r >= nmov_w[q]) {
+                r -= nmov_w[q];
+                w = q + 1;
+              }
+            const int     p   = s_clist[w * 32 + r];
+            const double* sc  = s_scr + (size_t)p * ROW;
+            double        s0y = 0.0, dsy, s0z = 0.0, dsz;
+            if (c_py >= 0) {
+              const double2 v = *reinterpret_cast<const double2*>(sc + c_py);
+              s0y             = v.x;
+              dsy             = v.y;
+            } else {
+              dsy = sc[c_dy];
+            }
+            if (c_pz >= 0) {
+              const double2 v = *reinterpret_cast<const double2*>(sc + c_pz);
+              s0z             = v.x;
+              dsz             = v.y;
+            } else {
+              dsz = sc[c_dz];
+            }
+            const double cyp = (c_cy >= 0) ? sc[c_cy] : 0.0;
+            const double czp = (c_cz >= 0) ? sc[c_cz] : 0.0;
+            const double ar = P.q * (s0y + dsy) * (s0z + dsz);
+            const double wx = -((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz) * P.qdxdt[2];
+            const double fyv = -cyp * P.qdxdt[1];
+            const double g0 = fyv * (s0z + A * dsz), g1 = fyv * (A * s0z + B * dsz);
+            const double fzv = -czp * P.qdxdt[0];
+            const double h0 = fzv * s0y, h1 = fzv * dsy;
+            const double k0 = h0 + A * h1, k1 = A * h0 + B * h1;
+            double       cpx = 0.0;
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+              if (s >= 1 && s <= N1) {
+                const double2 xv  = *reinterpret_cast<const double2*>(sc + C::PX + 2 * (s - 1));
+                const double  s0x = xv.x, dsx = xv.y;
+                accc[s][0]        = fma(ar, s0x + dsx, accc[s][0]);
+                accc[s][1]        = fma(wx, cpx, accc[s][1]);
+                accc[s][2]        = fma(g0, s0x, fma(g1, dsx, accc[s][2]));
+                accc[s][3]        = fma(k0, s0x, fma(k1, dsx, accc[s][3]));
+                cpx += dsx;
+              } else {
+                const double dsx = sc[C::OUT + 6 + (s == 0 ? 0 : 1)];
+                accc[s][0]       = fma(ar, dsx, accc[s][0]);
+                if (s >= 1) accc[s][1] = fma(wx, cpx, accc[s][1]);
+                accc[s][2] = fma(g1, dsx, accc[s][2]);
+                accc[s][3] = fma(k1, dsx, accc[s][3]);
+                cpx += dsx;
+              }
+            }
+          }
+        }
+        // flush the groups that had work into the window, one group per round (no atomics)
+        const int nround = min(nmc, GC);
+        for (int r = 0; r < nround; r++) {
+          __syncthreads();
+          if (c_active && gc == r) {
+#pragma unroll
+            for (int s = 0; s < NS; s++) {
+              double2* w = reinterpret_cast<double2*>(s_win + ((s + rot) % NS) * (NCOL * 4) + col * 4);
+              double2  a = w[0], b = w[1];
+              a.x += accc[s][0];
+              a.y += accc[s][1];
+              b.x += accc[s][2];
+              b.y += accc[s][3];
+              w[0] = a;
+              w[1] = b;
+            }
+          }
+        }
+        cbase_e += nmc;
+      }
+
       if (cc < ncs && s_pidx[cc + 1] <= b1) {
         retire(); // cell finished: slide the window (block-uniform)
         if (cc >= ncs) break;
@@ -524,6 +679,7 @@ __global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_consta
         break;
       }
     }
+    bpar ^= 1;
     __syncthreads(); // scratch may be overwritten by the next batch
   }
 
@@ -547,6 +703,10 @@ int launch_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st)
   P.q    = a.sp.q;
   for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
   P.err = a.err;
+  if (a.geo.seg + 1 > MAXSEG) {
+    set_error("push segment longer than MAXSEG");
+    return 1;
+  }
   size_t smem = smem_layout<O>(a.geo.seg).bytes;
   static bool attr_set = false;
   if (!attr_set) {
