@@ -34,21 +34,26 @@ def needs_build():
     return any(os.path.getmtime(p) > t for p in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
+def build(force=False, verbose=False, defines=(), out=None):
+    """defines / out: experiment builds (e.g. -DNIX_PUSH_MINB=3 into libnixb200_x.so, selected at run
+    time with NIXB200_LIB); the default build takes neither."""
+    if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-o", LIB] + sources()
+    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or LIB] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libnixb200.so")
-    with open(os.path.join(HERE, "ptxas_report.txt"), "w") as f:
-        f.write(res.stderr)
-    return LIB
+    if out is None:
+        with open(os.path.join(HERE, "ptxas_report.txt"), "w") as f:
+            f.write(res.stderr)
+    return out or LIB
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose=True)
-    print(LIB)
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith("--out=")]
+    out = os.path.join(HERE, outs[0]) if outs else None
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, defines=defs, out=out))

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libnixb200.so")
+LIB_PATH = os.environ.get("NIXB200_LIB") or os.path.join(HERE, "libnixb200.so")
 
 MODE_FIELD, MODE_CURRENT, MODE_PARTICLE = 0, 1, 2
 FIELD_UF, FIELD_UJ = 0, 1

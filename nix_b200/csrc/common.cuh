@@ -27,9 +27,15 @@ struct Geo {
   int    nb, order, is_odd, half;
   int    ncell;   // R[0]*R[1]*R[2]  flat indices in use
   int    nchunk;  // local chunks
-  int    seg;     // cells per push work item along x
-  int    nseg;    // segments per row
-  int    nitem;   // work items per chunk = nc[0]*nc[1]*nseg
+  // push work item = a (tile[0] x tile[1] x tile[2]) box of bins of one chunk, one CTA each
+  int    tile[3];  // bins per tile (z,y,x)
+  int    ntl[3];   // tiles per axis = ceil(nc/tile)
+  int    ntile;    // tiles per chunk
+  // leaver bookkeeping: a particle that leaves the chunk in direction d can only come from the
+  // outermost `slabt` bin layers on the sides where d points outwards (it moves < 1 bin per step),
+  // so the per-(bin, direction) leaver counts live in 26 slabs instead of a full [ncell][27] array
+  int    slabt;       // slab thickness in bins: 1 for even orders, 2 for odd (bins straddle cells)
+  int    slaboff[28]; // first entry of the slab of direction d; slaboff[27] = entries per chunk
   double del[3], rdel[3];
   double glo[3], ghi[3], glen[3]; // global box (set_boundary_periodic, xtensor_particle.hpp:359-369)
   double cc, rc;
@@ -58,13 +64,13 @@ struct SpeciesDev {
   int32_t* cbase; // [nchunk+1]   first particle of each chunk in xu
   int32_t* cbase_new;
   // migration
-  int32_t* blockdir; // [nchunk][nitem][27] leavers per push work item and direction
+  int32_t* slabcnt;  // [nchunk][slaboff[27]] leavers per (slab bin, direction); scanned in place
   int32_t* sendcnt;  // [nchunk][27]
   int32_t* msgoff;   // [nchunk][27]  first message slot of (chunk, dir)
   int32_t* recvoff;  // [nchunk][27]  pre-sort local index of the first particle received in slot e
   int32_t* nleave;   // [1] number of leaver records
   int32_t* nmsg;     // [1] total message particles
-  int4*    lrec;     // [lcap] leaver records {i, chunk, item<<8|dir, rank in item}
+  int4*    lrec;     // [lcap] leaver records {i, chunk, slab entry, (rank in bin)<<5 | dir}
   double*  msg;      // [7][lcap] message payload (wrapped positions), SoA
   int32_t* msgkey;   // [lcap]
   int32_t* msgord;   // [lcap]
@@ -125,6 +131,23 @@ __device__ __forceinline__ int digitize(double x, double xmin, double rdx)
   return (int)floor(__dmul_rn(__dsub_rn(x, xmin), rdx));
 }
 
+// entry of bin (b[0],b[1],b[2]) in the slab of direction d = 9*ez+3*ey+ex (0/1/2 = -/centre/+);
+// -1 when the bin is not inside that slab.  Entries of one slab follow the flat bin order, i.e.
+// the particle order of the cell-sorted container.
+__host__ __device__ inline int slab_entry(const Geo& g, int d, const int* b)
+{
+  int e[3] = {d / 9, (d / 3) % 3, d % 3};
+  int pos = 0;
+  for (int a = 0; a < 3; a++) {
+    int lo = (e[a] == 2) ? g.nc[a] - g.slabt : 0;
+    int n  = (e[a] == 1) ? g.nc[a] : g.slabt;
+    int r  = b[a] - lo;
+    if (r < 0 || r >= n) return -1;
+    pos = pos * n + r;
+  }
+  return g.slaboff[d] + pos;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-side error plumbing
 // ---------------------------------------------------------------------------------------------
@@ -162,6 +185,8 @@ struct PushArgs {
 
 int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st);
 size_t push_smem_bytes(const Geo& g);
+void   push_tile_box(int order, int& tz, int& ty, int& tx);
+int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits
 
 int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
 int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);

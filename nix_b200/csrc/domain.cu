@@ -90,7 +90,9 @@ static int make_tensor_map(Domain* d)
   cuuint64_t  dims[5] = {6, (cuuint64_t)g.M[2], (cuuint64_t)g.M[1], (cuuint64_t)g.M[0], (cuuint64_t)g.nchunk};
   cuuint64_t  strides[4] = {48, (cuuint64_t)g.M[2] * 48, (cuuint64_t)g.M[1] * g.M[2] * 48,
                             (cuuint64_t)g.M[0] * g.M[1] * g.M[2] * 48};
-  cuuint32_t  box[5]  = {6, (cuuint32_t)(g.seg + NW - 1), (cuuint32_t)NW, (cuuint32_t)NW, 1};
+  int bz, by, bx;
+  push_tile_box(g.order, bz, by, bx); // compile-time box of the push kernel (>= g.tile)
+  cuuint32_t  box[5]  = {6, (cuuint32_t)(bx + NW - 1), (cuuint32_t)(by + NW - 1), (cuuint32_t)(bz + NW - 1), 1};
   cuuint32_t  estr[5] = {1, 1, 1, 1, 1};
   CUresult    r = ((encode_fn)fn)(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, d->uf, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -105,7 +107,7 @@ static int make_tensor_map(Domain* d)
 static int free_species(SpeciesDev& s)
 {
   void* ptrs[] = {s.xu,      s.xv,     s.key,    s.ordl,  s.hist,   s.start, s.oob,    s.cbase, s.cbase_new,
-                  s.blockdir, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey,
+                  s.slabcnt, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey,
                   s.msgord};
   for (void* p : ptrs)
     if (p) cudaFree(p);
@@ -122,7 +124,7 @@ static int alloc_species_fixed(Domain* d, SpeciesDev& s)
   NIX_CUDA(cudaMalloc(&s.oob, sizeof(int32_t) * g.nchunk * LANES));
   NIX_CUDA(cudaMalloc(&s.cbase, sizeof(int32_t) * (g.nchunk + 1)));
   NIX_CUDA(cudaMalloc(&s.cbase_new, sizeof(int32_t) * (g.nchunk + 1)));
-  NIX_CUDA(cudaMalloc(&s.blockdir, sizeof(int32_t) * (size_t)g.nchunk * g.nitem * 27));
+  NIX_CUDA(cudaMalloc(&s.slabcnt, sizeof(int32_t) * (size_t)g.nchunk * g.slaboff[27]));
   NIX_CUDA(cudaMalloc(&s.sendcnt, sizeof(int32_t) * g.nchunk * 27));
   NIX_CUDA(cudaMalloc(&s.msgoff, sizeof(int32_t) * g.nchunk * 27));
   NIX_CUDA(cudaMalloc(&s.recvoff, sizeof(int32_t) * g.nchunk * 27));
@@ -133,7 +135,7 @@ static int alloc_species_fixed(Domain* d, SpeciesDev& s)
   NIX_CUDA(cudaMemset(s.oob, 0, sizeof(int32_t) * g.nchunk * LANES));
   NIX_CUDA(cudaMemset(s.cbase, 0, sizeof(int32_t) * (g.nchunk + 1)));
   NIX_CUDA(cudaMemset(s.cbase_new, 0, sizeof(int32_t) * (g.nchunk + 1)));
-  NIX_CUDA(cudaMemset(s.blockdir, 0, sizeof(int32_t) * (size_t)g.nchunk * g.nitem * 27));
+  NIX_CUDA(cudaMemset(s.slabcnt, 0, sizeof(int32_t) * (size_t)g.nchunk * g.slaboff[27]));
   NIX_CUDA(cudaMemset(s.sendcnt, 0, sizeof(int32_t) * g.nchunk * 27));
   NIX_CUDA(cudaMemset(s.nleave, 0, sizeof(int32_t)));
   NIX_CUDA(cudaMemset(s.nmsg, 0, sizeof(int32_t)));
@@ -293,21 +295,27 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
   g.cc    = desc->cc;
   g.rc    = 1 / desc->cc;
   g.ncell = g.R[0] * g.R[1] * g.R[2];
-  {
-    int r  = g.R[2];
-    int ns = (r + 39) / 40;
-    g.seg  = (r + ns - 1) / ns;
-    g.nseg = (r + g.seg - 1) / g.seg;
+  if (choose_push_tile(g)) {
+    delete d;
+    set_error("no push tile fits shared memory");
+    return 1;
   }
-  g.nitem = g.R[0] * g.R[1] * g.nseg;
+  g.slabt = 2;
+  {
+    int off = 0;
+    for (int s = 0; s < 27; s++) {
+      g.slaboff[s] = off;
+      if (s == 13) continue;
+      int e[3] = {s / 9, (s / 3) % 3, s % 3};
+      int n    = 1;
+      for (int a = 0; a < 3; a++) n *= (e[a] == 1) ? g.nc[a] : g.slabt;
+      off += n;
+    }
+    g.slaboff[27] = off;
+  }
   if ((double)g.nchunk * g.ncell * LANES >= 2147483000.0) {
     delete d;
     set_error("key space (nchunk*ncell*8) exceeds int32");
-    return 1;
-  }
-  if (push_smem_bytes(g) > 200 * 1024) {
-    delete d;
-    set_error("push tile does not fit shared memory");
     return 1;
   }
 

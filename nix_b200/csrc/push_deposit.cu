@@ -10,28 +10,28 @@
 //   XtensorParticle::count      xtensor_particle.hpp:324-357   (of the NEW positions)
 //   XtensorHaloParticle3D::pre_pack classification  xtensor_halo3d.hpp:288-302
 //
-// Work item = one x-segment of one (z,y) row of cells of one chunk; its particles are contiguous
-// because the container is cell-sorted.  One CTA of 128 threads per item:
-//   * TMA (cp.async.bulk.tensor.5d) stages the (O+2)x(O+2)x(SEG+O+1)x6 E/B tile of the row -- ghosts
-//     included -- into shared memory; an mbarrier signals arrival.
-//   * phase 1, thread per particle (batches of 128): coalesced SoA loads, weights, gather from the
-//     smem tile over the EXACT support of every component ((O+1)^3 points; the half-grid components
-//     start one node later when the particle sits in the upper half of its cell), Boris, move,
-//     coalesced stores, bin of the new position (-> key + histogram, or a leaver record with its
-//     ordered rank inside the item), and the 1-D deposit weights of the particle into a
-//     particle-major scratch row (128-bit stores, conflict free).
-//   * phase 2 accumulates the Esirkepov current of all particles of one cell in REGISTERS (the GPU
-//     analogue of the reference's sorted `reduce_add` path, primitives.hpp:798-809), thread per
-//     (jy,jz) column of the deposit mesh, particles of the cell split over thread groups:
-//       F path  particles that stay in their cell (the vast majority): their weights touch only the
-//               central (O+1)^3 nodes, so a group is (O+1)^2 threads and the x loop has O+1 slots;
-//               the accumulators slide along x with the cell index and live across batches.
-//       C path  particles that change cell: full (O+3)^3 mesh, (O+3)^2 threads per group, transient
-//               accumulators flushed into a small sliding window in shared memory.
-//     When a cell is finished the x-slot that leaves the window is reduced over the groups through
-//     a staging buffer, merged with the C window and added to J in global memory with
-//     red.global.add.f64 -- once per (z,y,x,component) and CTA, no shared-memory atomics.
+// Work item = one (tz x ty x tx) tile of bins of one chunk, one CTA of 4 warps:
+//   * TMA (cp.async.bulk.tensor.5d) stages the E/B tile of the CTA -- ghosts included -- into shared
+//     memory; an mbarrier signals arrival.  A J tile of the CTA's deposit footprint lives in shared
+//     memory next to it and is flushed to global memory ONCE per CTA with red.global.add.f64.
+//   * a WARP owns one bin (cell) at a time; its particles are contiguous because the container is
+//     cell-sorted, so the 32 lanes read 32 consecutive particles (coalesced SoA loads / stores).
+//     Lane = particle: weights, gather from the E/B tile over the EXACT (O+1)^3 support of every
+//     component, Boris, move, store, bin of the new position (-> key + histogram, or a leaver record
+//     with its ordered rank inside the bin).
+//   * deposit: every lane keeps the Esirkepov current of ITS particles on the central (O+1)^3 nodes
+//     of the bin in REGISTERS (81 values for order 2; structural zeros are not stored), accumulated
+//     over all particles of the bin.  When the bin is done the lanes are summed with a butterfly
+//     transpose-reduction on warp shuffles (every lane ends up owning one node value per z-plane)
+//     and added to the J tile.  This is the GPU analogue of the reference's sorted `reduce_add`
+//     path (primitives.hpp:798-809): one scatter per bin instead of one per particle.
+//   * particles that change bin ("movers", a few per cent) additionally touch nodes outside the
+//     central mesh.  Their 1-D weights go to a small per-warp record list; lanes = face nodes then
+//     add the extra values to the J tile (9 nodes per single-axis mover; the rare multi-axis mover
+//     walks its whole (O+3)^3 mesh).
 #include "common.cuh"
+
+#include <algorithm>
 
 namespace nixb200
 {
@@ -39,46 +39,56 @@ namespace
 {
 constexpr int THREADS = 128;
 constexpr int NWARP   = THREADS / 32;
-constexpr int MAXSEG  = 48;
+constexpr int MAXMOV  = 8; // mover records per warp
+constexpr unsigned FULL = 0xffffffffu;
+#ifndef NIX_GATHER_UNROLL
+#define NIX_GATHER_UNROLL 1 // 1: six copies of the gather body (no weight selects, larger code)
+#endif
+#ifndef NIX_PUSH_MINB
+#define NIX_PUSH_MINB 3
+#endif
 
 template <int O>
 struct Cfg {
-  static constexpr int NW   = O + 2;          // gather stencil width of the staged tile (interp.hpp)
-  static constexpr int N1   = O + 1;          // support of one shape function
-  static constexpr int NS   = O + 3;          // deposit mesh width     (esirkepov.hpp:326-328)
-  static constexpr int NCOL = NS * NS;        // (jy,jz) columns of the full mesh       (C path)
-  static constexpr int GC   = THREADS / NCOL; // C groups: 8 / 5 / 3
-  static constexpr int NCF  = N1 * N1;        // (jy,jz) columns of the central mesh    (F path)
-  static constexpr int GF   = THREADS / NCF;  // F groups: 32 / 14 / 8
-  // particle-major scratch row (doubles); pairs are 16-byte aligned
-  static constexpr int PY  = 0;               // (S0y[j], DSy[j]) j = 1..N1
-  static constexpr int PZ  = 2 * N1;
-  static constexpr int PX  = 4 * N1;
-  static constexpr int CY  = 6 * N1;          // CPy[j] = sum of DSy over slots < j, j = 1..N1
-  static constexpr int CZ  = 7 * N1;
-  static constexpr int OUT = 8 * N1;          // DSy0 DSyL CPyL DSz0 DSzL CPzL DSx0 DSxL  (L = NS-1)
-  static constexpr int ROW = 8 * N1 + 10;     // == 2 (mod 4): 128-bit stores of 8 lanes hit 32 banks
+  static constexpr int NW = O + 2; // stencil width the staged E/B tile is padded by (interp.hpp)
+  static constexpr int N1 = O + 1; // support of one shape function
+  static constexpr int NS = O + 3; // deposit mesh width     (esirkepov.hpp:326-328)
+  // values per z-plane of the central mesh kept in registers: rho, Jx (x slots 2..), Jy (y slots 2..),
+  // Jz (planes 2..); the skipped entries are structural zeros for particles that stay in their bin
+  static constexpr int P_RHO = 0;
+  static constexpr int P_JX  = N1 * N1;
+  static constexpr int P_JY  = P_JX + N1 * (N1 - 1);
+  static constexpr int P_JZ  = P_JY + (N1 - 1) * N1;
+  static constexpr int PV    = P_JZ + N1 * N1;         // 12 / 30 / 56
+  // mover record (doubles): per axis (z,y,x): S0[NS] DS[NS] CP[NS]; then 2 doubles of ints
+  static constexpr int REC = 9 * NS + 2;
+  // bins per CTA (compile-time, so that every shared-memory offset of the gather is an immediate);
+  // smaller chunks simply use part of the box
+  static constexpr int TZ = 4, TY = 4, TX = 9;
+  static constexpr int EZ = TZ + NW - 1, EY = TY + NW - 1, EX = TX + NW - 1; // staged E/B tile
+  static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
+  static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
+  static constexpr int J_DOUBLES   = (JZ * JY * JX * 4 + 15) / 16 * 16;
+  static constexpr int REC_DOUBLES = (4 * 8 * REC + 15) / 16 * 16;
 };
 
 struct SmemLayout {
-  int    eb_doubles, stf_doubles, win_doubles, scratch_doubles;
+  int    eb_doubles, j_doubles, rec_doubles;
   size_t bytes;
 };
-
-constexpr int SMEM_INTS = 1024;
+constexpr int SMEM_INTS = 640;
+static_assert(256 + 4 * 4 * (9 + 1) <= 416 && 416 + sizeof(ChunkGeo) / 4 <= SMEM_INTS, "s_cs / s_cg must fit");
 
 template <int O>
-__host__ __device__ inline SmemLayout smem_layout(int seg)
+__host__ __device__ inline SmemLayout smem_layout()
 {
   using C = Cfg<O>;
+  static_assert(NWARP == 4 && MAXMOV == 8, "REC_DOUBLES assumes 4 warps x 8 records");
   SmemLayout L;
-  int        ex     = seg + C::NW - 1;
-  L.eb_doubles      = ((C::NW * C::NW * ex * 6) + 15) / 16 * 16; // keep 128-byte multiples
-  L.stf_doubles     = ((2 * C::GF * C::NCF * 4) + 15) / 16 * 16; // double buffered
-  L.win_doubles     = ((C::NS * C::NCOL * 4) + 15) / 16 * 16;
-  L.scratch_doubles = (C::ROW * THREADS + 15) / 16 * 16;
-  L.bytes = sizeof(double) * ((size_t)L.eb_doubles + L.stf_doubles + L.win_doubles + L.scratch_doubles) +
-            SMEM_INTS * sizeof(int);
+  L.eb_doubles  = C::EB_DOUBLES;
+  L.j_doubles   = C::J_DOUBLES;
+  L.rec_doubles = C::REC_DOUBLES;
+  L.bytes       = sizeof(double) * ((size_t)L.eb_doubles + L.j_doubles + L.rec_doubles) + SMEM_INTS * sizeof(int);
   return L;
 }
 
@@ -153,12 +163,12 @@ __device__ __forceinline__ void shape_mc(double x, double X, double rdx, double*
 
 // One field component gathered over its exact support (interp3d_impl_sorted, interp.hpp:95-113:
 // same nesting and summation order; the reference's extra stencil slot carries a zero weight).
-// e points at (bz, by, tx + bx, component); EX = x extent of the staged tile.
+// e points at the first support node of the component; sy / sz = row / plane strides in doubles.
 template <int O, bool S>
-__device__ __forceinline__ double gather1(const double* __restrict__ e, int EX, const double* wz,
-                                          const double* wy, const double* wx)
+__device__ __forceinline__ double gather1(const double* __restrict__ e, const double* wz, const double* wy,
+                                          const double* wx)
 {
-  constexpr int NW = O + 2;
+  constexpr int sy = Cfg<O>::EX * 6, sz = Cfg<O>::EY * Cfg<O>::EX * 6;
   double        rz = 0.0;
 #pragma unroll
   for (int jz = 0; jz <= O; jz++) {
@@ -166,7 +176,7 @@ __device__ __forceinline__ double gather1(const double* __restrict__ e, int EX, 
 #pragma unroll
     for (int jy = 0; jy <= O; jy++) {
       double        rx = 0.0;
-      const double* p  = e + (size_t)((jz * NW + jy) * EX) * 6;
+      const double* p  = e + jz * sz + jy * sy;
 #pragma unroll
       for (int jx = 0; jx <= O; jx++) rx = mad<S>(p[jx * 6], wx[jx], rx);
       ry = mad<S>(rx, wy[jy], ry);
@@ -186,508 +196,625 @@ struct Kparams {
   int*            err;
 };
 
+// 1-D deposit weights of one particle on the central slots 1..N1 of the (O+3) mesh, per axis (z,y,x):
+// S0 = old weights, DS = new - old, CP[j] = sum of DS over slots < j (esirkepov.hpp:167-174)
+template <int O>
+struct Wts {
+  double s0[3][O + 1], ds[3][O + 1], cp[3][O + 1];
+};
+
+// Esirkepov current of one particle on z-plane jz of the central mesh, added into acc[PV]:
+//   rho[x] += q S1y S1z S1x[x]                                                   esirkepov.hpp:155-164
+//   Jx[x]  += -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz) CPx[x]                        :177-195
+//   Jy[x]  += -q dy/dt CPy ((S0z+DSz/2) S0x[x] + (S0z/2+DSz/3) DSx[x])                     :198-216
+//   Jz[x]  += -q dz/dt CPz ((S0x+DSx/2)[x] S0y + (S0x/2+DSx/3)[x] DSy)                     :219-237
+template <int O>
+__device__ __forceinline__ void plane_accumulate(const double s0z, const double dsz, const double cpz,
+                                                 const bool with_jz, const Wts<O>& w, const double q,
+                                                 const double* qd, double* acc)
+{
+  using C          = Cfg<O>;
+  constexpr int N1 = C::N1;
+  const double  A = 1.0 / 2, B = 1.0 / 3;
+  const double  qs1z = q * (s0z + dsz);
+  const double  azy = -qd[1] * (s0z + A * dsz), bzy = -qd[1] * (A * s0z + B * dsz);
+  const double  fz  = -qd[0] * cpz;
+#pragma unroll
+  for (int jy = 0; jy < N1; jy++) {
+    const double s0y = w.s0[1][jy], dsy = w.ds[1][jy];
+    const double ar  = qs1z * (s0y + dsy);
+    const double wx  = -qd[2] * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
+#pragma unroll
+    for (int jx = 0; jx < N1; jx++) {
+      const double s0x = w.s0[2][jx], dsx = w.ds[2][jx];
+      acc[C::P_RHO + jy * N1 + jx] = fma(ar, s0x + dsx, acc[C::P_RHO + jy * N1 + jx]);
+      if (jx >= 1) acc[C::P_JX + jy * (N1 - 1) + jx - 1] = fma(wx, w.cp[2][jx], acc[C::P_JX + jy * (N1 - 1) + jx - 1]);
+      if (jy >= 1) {
+        const double wy = azy * s0x + bzy * dsx;
+        acc[C::P_JY + (jy - 1) * N1 + jx] = fma(wy, w.cp[1][jy], acc[C::P_JY + (jy - 1) * N1 + jx]);
+      }
+    }
+  }
+  if (with_jz) { // plane 0 carries no Jz of the register set (structural zero / mover extra)
+#pragma unroll
+    for (int jy = 0; jy < N1; jy++) {
+      const double s0y = w.s0[1][jy], dsy = w.ds[1][jy];
+#pragma unroll
+      for (int jx = 0; jx < N1; jx++) {
+        const double s0x = w.s0[2][jx], dsx = w.ds[2][jx];
+        const double wz  = (s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy;
+        acc[C::P_JZ + jy * N1 + jx] = fma(fz, wz, acc[C::P_JZ + jy * N1 + jx]);
+      }
+    }
+  }
+}
+
+// butterfly transpose-reduction of v[0..PV) over the 32 lanes; afterwards lane l holds, at local
+// slot j, the warp-wide sum of original entry  j + sum over set bits of l of the half sizes
+template <int N>
+struct Halves {
+  static constexpr int h = (N + 1) / 2;
+};
+
+template <int N, int OFF>
+__device__ __forceinline__ void bfly_step(double* v, int lane)
+{
+  constexpr int h     = (N + 1) / 2;
+  const bool    upper = (lane & OFF) != 0;
+#pragma unroll
+  for (int j = 0; j < h; j++) {
+    const double lo   = v[j];
+    const double hi   = (j + h < N) ? v[j + h] : 0.0;
+    const double send = upper ? lo : hi;
+    const double keep = upper ? hi : lo;
+    v[j]              = keep + __shfl_xor_sync(FULL, send, OFF);
+  }
+}
+
+template <int PV>
+__device__ __forceinline__ void bfly_reduce(double* v, int lane, int& base)
+{
+  constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
+  bfly_step<PV, 16>(v, lane);
+  bfly_step<n1, 8>(v, lane);
+  bfly_step<n2, 4>(v, lane);
+  bfly_step<n3, 2>(v, lane);
+  bfly_step<n4, 1>(v, lane);
+  base = ((lane & 16) ? n1 : 0) + ((lane & 8) ? n2 : 0) + ((lane & 4) ? n3 : 0) + ((lane & 2) ? n4 : 0) +
+         ((lane & 1) ? (n4 + 1) / 2 : 0);
+}
+template <int PV>
+struct BflyOut {
+  static constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
+  static constexpr int nf = (n4 + 1) / 2; // values left per lane
+};
+
+// Add the extra values (outside the register-resident set) of the recorded movers of one warp to the
+// J tile.  Called once per bin (or when the record list is full): kept out of line so that the hot
+// per-particle loop stays small enough for the instruction cache.
+template <int O>
+__device__ __noinline__ void flush_movers(double* s_j, const double* myrec, int* myml, int nrec, double q,
+                                          double qdz, double qdy, double qdx)
+{
+  using C          = Cfg<O>;
+  constexpr int N1 = C::N1, NS = C::NS, JY = C::JY, JX = C::JX;
+  const int     lane = threadIdx.x & 31;
+  __syncwarp();
+  // single-axis movers: lanes = (record, face node (u,v)), N1*N1 nodes each
+  int nsingle = 0;
+  for (int m = 0; m < nrec; m++) {
+    const int* ri = reinterpret_cast<const int*>(myrec + m * C::REC + 9 * NS);
+    if (ri[1] >= 0) {
+      if (lane == 0) myml[nsingle] = m;
+      nsingle++;
+    }
+  }
+  __syncwarp();
+  const double A = 1.0 / 2, B = 1.0 / 3;
+  auto         node = [&](const double* r, int jz, int jy, int jx, double& rho, double& wx, double& wy, double& wz) {
+    const double s0z = r[0 * NS + jz], dsz = r[1 * NS + jz];
+    const double s0y = r[3 * NS + jy], dsy = r[4 * NS + jy];
+    const double s0x = r[6 * NS + jx], dsx = r[7 * NS + jx];
+    rho = q * (s0z + dsz) * (s0y + dsy) * (s0x + dsx);
+    wx  = -qdx * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
+    wy  = -qdy * ((s0z + A * dsz) * s0x + (A * s0z + B * dsz) * dsx);
+    wz  = -qdz * ((s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy);
+  };
+  for (int it0 = 0; it0 < nsingle * N1 * N1; it0 += 32) {
+    const int gi = it0 + lane;
+    if (gi < nsingle * N1 * N1) {
+      const int     m  = myml[gi / (N1 * N1)];
+      const int     uv = gi % (N1 * N1);
+      const double* r  = myrec + m * C::REC;
+      const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
+      const int     cbase = ri[0], ax = ri[1] >> 1, o = (ri[1] & 1) ? NS - 1 : 0;
+      // mesh slots z,y,x: the moving axis sits on its outer slot, the two in-plane axes (ascending
+      // axis order) run over the central slots
+      const int u = uv / N1 + 1, v = uv % N1 + 1;
+      const int jz = (ax == 0) ? o : u;
+      const int jy = (ax == 1) ? o : ((ax == 0) ? u : v);
+      const int jx = (ax == 2) ? o : v;
+      double    rho, wx, wy, wz;
+      node(r, jz, jy, jx, rho, wx, wy, wz);
+      double*      dst = s_j + cbase + ((jz * JY + jy) * JX + jx) * 4;
+      const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+      if (rho != 0.0) atomicAdd(dst + 0, rho);
+      if (vx != 0.0) atomicAdd(dst + 1, vx);
+      if (vy != 0.0) atomicAdd(dst + 2, vy);
+      if (vz != 0.0) atomicAdd(dst + 3, vz);
+      if (o == 0) {
+        // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
+        const int    st = (ax == 0) ? JY * JX * 4 : ((ax == 1) ? JX * 4 : 4);
+        const double w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
+        if (w1 != 0.0) atomicAdd(dst + st + (3 - ax), w1);
+      }
+    }
+  }
+  // multi-axis movers: the whole (O+3)^3 mesh minus what the register path already holds
+  for (int m = 0; m < nrec; m++) {
+    const double* r  = myrec + m * C::REC;
+    const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
+    if (ri[1] >= 0) continue;
+    const int cbase = ri[0];
+    for (int n = lane; n < NS * NS * NS; n += 32) {
+      const int  jz = n / (NS * NS), jy = (n / NS) % NS, jx = n % NS;
+      const bool central = jz >= 1 && jz <= N1 && jy >= 1 && jy <= N1 && jx >= 1 && jx <= N1;
+      double     rho, wx, wy, wz;
+      node(r, jz, jy, jx, rho, wx, wy, wz);
+      double*      dst = s_j + cbase + ((jz * JY + jy) * JX + jx) * 4;
+      const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+      if (!central && rho != 0.0) atomicAdd(dst + 0, rho);
+      if (!(central && jx >= 2) && vx != 0.0) atomicAdd(dst + 1, vx);
+      if (!(central && jy >= 2) && vy != 0.0) atomicAdd(dst + 2, vy);
+      if (!(central && jz >= 2) && vz != 0.0) atomicAdd(dst + 3, vz);
+    }
+  }
+  __syncwarp();
+}
+
 template <int O, bool S>
-__global__ void __launch_bounds__(THREADS, 3) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
+__global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
                                                              const Kparams P)
 {
-  using C            = Cfg<O>;
-  constexpr int NW   = C::NW;
-  constexpr int N1   = C::N1;
-  constexpr int NS   = C::NS;
-  constexpr int NCOL = C::NCOL;
-  constexpr int GC   = C::GC;
-  constexpr int NCF  = C::NCF;
-  constexpr int GF   = C::GF;
-  constexpr int ROW  = C::ROW;
+  using C          = Cfg<O>;
+  constexpr int NW = C::NW;
+  constexpr int N1 = C::N1;
+  constexpr int NS = C::NS;
+  constexpr int PV = C::PV;
   const Geo&    g    = P.geo;
   const int     tid  = threadIdx.x;
   const int     lane = tid & 31;
   const int     warp = tid >> 5;
 
   // ---- decode the work item -------------------------------------------------------------------
-  const int item = blockIdx.x % g.nitem;
-  const int ch   = blockIdx.x / g.nitem;
-  const int sg   = item % g.nseg;
-  const int ry   = (item / g.nseg) % g.R[1];
-  const int rz   = item / (g.nseg * g.R[1]);
-  const int xs   = sg * g.seg;              // first cell (bin index) of the segment
-  const int ncs  = min(g.seg, g.R[2] - xs); // cells in this segment
-  const int row0 = (ch * g.ncell + (rz * g.R[1] + ry) * g.R[2] + xs) * LANES; // key of first bin
+  const int tl = blockIdx.x % g.ntile;
+  const int ch = blockIdx.x / g.ntile;
+  int       b0[3], nbn[3];
+  {
+    int t[3] = {tl / (g.ntl[1] * g.ntl[2]), (tl / g.ntl[2]) % g.ntl[1], tl % g.ntl[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      b0[a]  = t[a] * g.tile[a];
+      nbn[a] = min(g.tile[a], g.nc[a] - b0[a]);
+    }
+  }
+  constexpr int EY = C::EY, EX = C::EX;
+  constexpr int JZ = C::JZ, JY = C::JY, JX = C::JX;
+  constexpr int esy = EX * 6, esz = EY * EX * 6;
+
+  extern __shared__ __align__(1024) double smem_d[];
+  const SmemLayout L = smem_layout<O>();
+  double*   s_eb   = smem_d;
+  double*   s_j    = smem_d + L.eb_doubles;
+  double*   s_rec  = s_j + L.j_doubles;
+  int*      s_int  = reinterpret_cast<int*>(s_rec + L.rec_doubles);
+  uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int); // 2 ints
+  int*      s_any  = s_int + 2;                          // [1]
+  int*      s_tbl  = s_int + 8;                          // [PV] J-tile offset of every plane value
+  int*      s_dcnt = s_int + 72;                         // [NWARP][32] leavers of the current bin per direction
+  int*      s_mlst = s_int + 72 + NWARP * 32;            // [NWARP][MAXMOV] single-axis mover records
+  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + 416); // 8-byte aligned
+  int*      s_cs   = s_int + 256;                        // [TZ*TY][TX+1] first particle of every bin of the tile
 
   const int32_t* __restrict__ start = P.sp.start;
-  const int p_begin = start[row0];
-  const int p_end   = start[row0 + ncs * LANES];
-  if (p_begin == p_end) return;
+  const int cellkey0 = ch * g.ncell;
 
-  // ---- shared memory carve-up (indices into one __shared__ array: keeps LDS/STS addressing) -----
-  extern __shared__ __align__(1024) double smem_d[];
-  const SmemLayout L = smem_layout<O>(g.seg);
-  double*   s_eb      = smem_d;
-  double*   s_stf     = smem_d + L.eb_doubles;
-  double*   s_win     = s_stf + L.stf_doubles;
-  double*   s_scr     = s_win + L.win_doubles;
-  int*      s_int     = reinterpret_cast<int*>(s_scr + L.scratch_doubles);
-  uint64_t* s_bar     = reinterpret_cast<uint64_t*>(s_int); // 2 ints
-  int*      s_pidx    = s_int + 2;                          // [seg+1]
-  int*      s_dirbase = s_int + 64;                         // [27]
-  int*      s_warpcnt = s_int + 96;                         // [4][27]
-  int*      s_ccnt    = s_int + 208;                        // [2][MAXSEG] movers per cell, by batch parity
-  int*      s_wcnt    = s_int + 304;                        // [4] movers per warp
-  int*      s_cls     = s_int + 320;                        // [128] 1 = mover (C path)
-  int*      s_clist   = s_int + 448;                        // [4][32] batch slots of the movers, per warp
-
-  const int EX = g.seg + NW - 1; // E/B tile extent along x
+  // ---- particle ranges of the tile's bins -> shared memory; empty tile? (e.g. the rounding-guard
+  //      bin layer of even orders) ------------------------------------------------------------------
+  constexpr int CSW = C::TX + 1; // row width of s_cs
+  if (tid == 0) *s_any = 0;
+  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += THREADS)
+    reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
+  for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += THREADS) {
+    const int r = t / CSW, x = t % CSW;
+    if (x <= nbn[2]) {
+      const int rz = b0[0] + r / nbn[1], ry = b0[1] + r % nbn[1];
+      s_cs[t] = start[(cellkey0 + (rz * g.R[1] + ry) * g.R[2] + b0[2] + x) * LANES];
+    }
+  }
+  __syncthreads();
+  if (tid < nbn[0] * nbn[1] && s_cs[tid * CSW + nbn[2]] != s_cs[tid * CSW]) atomicOr(s_any, 1);
+  __syncthreads();
+  if (*s_any == 0) return;
 
   // tile origins (array indices)
   const int Lb  = g.nb;
-  const int ez0 = rz - g.is_odd - g.half + Lb, ey0 = ry - g.is_odd - g.half + Lb,
-            ex0 = xs - g.is_odd - g.half + Lb;
+  const int ez0 = b0[0] - g.is_odd - g.half + Lb, ey0 = b0[1] - g.is_odd - g.half + Lb,
+            ex0 = b0[2] - g.is_odd - g.half + Lb;
   const int jz0 = ez0 - 1, jy0 = ey0 - 1, jx0 = ex0 - 1;
 
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int t = tid; t <= ncs; t += THREADS) s_pidx[t] = start[row0 + t * LANES];
-  for (int t = tid; t < 27; t += THREADS) s_dirbase[t] = 0;
-  for (int t = tid; t < 4 * 27; t += THREADS) s_warpcnt[t] = 0;
-  for (int t = tid; t < 2 * MAXSEG; t += THREADS) s_ccnt[t] = 0;
-  for (int t = tid; t < NS * NCOL * 4; t += THREADS) s_win[t] = 0.0;
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(s_bar, (uint32_t)(NW * NW * EX * 6 * sizeof(double)));
+    mbar_expect_tx(s_bar, (uint32_t)(C::EZ * EY * EX * 6 * sizeof(double)));
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
+  for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) s_j[t] = 0.0;
+  for (int v = tid; v < PV; v += THREADS) {
+    // plane value v -> (component, jy, jx) in mesh slots (central index + 1)
+    int comp, jy, jx;
+    if (v < C::P_JX) {
+      comp = 0, jy = v / N1, jx = v % N1;
+    } else if (v < C::P_JY) {
+      int r = v - C::P_JX;
+      comp = 1, jy = r / (N1 - 1), jx = r % (N1 - 1) + 1;
+    } else if (v < C::P_JZ) {
+      int r = v - C::P_JY;
+      comp = 2, jy = r / N1 + 1, jx = r % N1;
+    } else {
+      int r = v - C::P_JZ;
+      comp = 3, jy = r / N1, jx = r % N1;
+    }
+    s_tbl[v] = ((jy + 1) * JX + (jx + 1)) * 4 + comp;
+  }
+  __syncthreads();
 
-  const ChunkGeo& c   = P.cg[ch];
+  const ChunkGeo& c   = *s_cg; // staged in shared memory: read again and again by every iteration
   const int       cb  = P.sp.cbase[ch];
   const size_t    cap = P.sp.cap;
   double* __restrict__ xu = P.sp.xu;
-  double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
-
-  // ---- phase-2 roles ---------------------------------------------------------------------------
-  // F: group gf, central column (fy, fz) in 0..O  <->  mesh column (fy+1, fz+1)
-  const bool f_active = tid < GF * NCF;
-  const int  gf       = tid / NCF;
-  const int  colf     = tid % NCF;
-  const int  fy       = colf % N1;
-  const int  fz       = colf / N1;
-  // C: group gc, mesh column (jy, jz) in 0..NS-1
-  const bool c_active = tid < GC * NCOL;
-  const int  gc       = tid / NCOL;
-  const int  col      = tid % NCOL;
-  const int  jy       = col % NS;
-  const int  jz       = col / NS;
-  // scratch offsets of this C column: (S0, DS) pair or lone DS, and CP; -1 = identically zero
-  const int c_py = (jy >= 1 && jy <= N1) ? C::PY + 2 * (jy - 1) : -1;
-  const int c_dy = (jy == 0) ? C::OUT + 0 : C::OUT + 1;
-  const int c_cy = (jy == 0) ? -1 : ((jy <= N1) ? C::CY + jy - 1 : C::OUT + 2);
-  const int c_pz = (jz >= 1 && jz <= N1) ? C::PZ + 2 * (jz - 1) : -1;
-  const int c_dz = (jz == 0) ? C::OUT + 3 : C::OUT + 4;
-  const int c_cz = (jz == 0) ? -1 : ((jz <= N1) ? C::CZ + jz - 1 : C::OUT + 5);
-
-  // F accumulators: slot 0 carries the previous cell's slot 1, slots 1..N1 receive this cell
-  double accf[N1 + 1][4];
-#pragma unroll
-  for (int s = 0; s <= N1; s++)
-#pragma unroll
-    for (int k = 0; k < 4; k++) accf[s][k] = 0.0;
-  int cc   = 0; // current cell (relative to xs) of the sliding deposit window
-  int par  = 0; // staging buffer parity
-  int rot  = 0; // C window rotation: mesh slot s lives at plane (s + rot) % NS
-  int bpar = 0; // batch parity of s_ccnt
+  double* myrec = s_rec + (size_t)warp * MAXMOV * C::REC;
+  int*    mydc  = s_dcnt + warp * 32;
+  int*    myml  = s_mlst + warp * MAXMOV;
 
   mbar_wait(s_bar, 0);
 
-  // Retire slot 0 of the window: reduce the F accumulators over the GF groups through the staging
-  // buffer, merge the C window, add to J in global memory (every (z,y,x) of the CTA's footprint is
-  // retired exactly once, so this is the CTA's single flush of that entry), then slide by one cell.
-  auto retire = [&]() {
-    double* st = s_stf + par * (GF * NCF * 4);
-    if (f_active) {
-      double2* o = reinterpret_cast<double2*>(st + (gf * NCF + colf) * 4);
-      o[0]       = make_double2(accf[0][0], accf[0][1]);
-      o[1]       = make_double2(accf[0][2], accf[0][3]);
+  // add the reduced plane values of a bin to the J tile
+  auto flush_plane = [&](double* v, int jz, int cellbase) {
+    int base;
+    bfly_reduce<PV>(v, lane, base);
+#pragma unroll
+    for (int j = 0; j < BflyOut<PV>::nf; j++) {
+      const int idx = base + j;
+      if (idx < PV && v[j] != 0.0) atomicAdd(s_j + cellbase + (jz + 1) * JY * JX * 4 + s_tbl[idx], v[j]);
     }
-    __syncthreads();
-    double* w0 = s_win + (rot % NS) * (NCOL * 4);
-    for (int t = tid; t < NCOL * 4; t += THREADS) {
-      const int cl = t >> 2, k = t & 3;
-      const int yy = cl % NS, zz = cl / NS;
-      double    sum = w0[t];
-      w0[t]         = 0.0;
-      if (yy >= 1 && yy <= N1 && zz >= 1 && zz <= N1) {
-        const double* sp = st + ((zz - 1) * N1 + (yy - 1)) * 4 + k;
-#pragma unroll 4
-        for (int gg = 0; gg < GF; gg++) sum += sp[gg * NCF * 4];
-      }
-      if (sum != 0.0) {
-        int gy = jy0 + yy, gz = jz0 + zz, gx = jx0 + cc;
-        if (gx >= 0 && gx < g.M[2] && gy >= 0 && gy < g.M[1] && gz >= 0 && gz < g.M[0])
-          atomicAdd(&ujc[(((size_t)gz * g.M[1] + gy) * g.M[2] + gx) * 4 + k], sum);
-      }
-    }
-    par ^= 1; // the other buffer is free: its readers passed the barrier above
-    rot = (rot + 1) % NS;
-#pragma unroll
-    for (int s = 0; s < N1; s++)
-#pragma unroll
-      for (int k = 0; k < 4; k++) accf[s][k] = accf[s + 1][k];
-#pragma unroll
-    for (int k = 0; k < 4; k++) accf[N1][k] = 0.0;
-    cc++;
   };
 
-  for (int b0 = p_begin; b0 < p_end; b0 += THREADS) {
-    const int  b1    = min(b0 + THREADS, p_end);
-    const int  i     = b0 + tid;
-    const bool valid = i < b1;
-    int        dir   = 13;
-    bool       mover = false;
-    int*       ccnt  = s_ccnt + bpar * MAXSEG;
-
-    // =============================== phase 1: push ===============================
-    if (valid) {
-      double pos[3], u[3]; // index 0,1,2 = z,y,x
-      pos[2] = xu[soa(0, cap, i)];
-      pos[1] = xu[soa(1, cap, i)];
-      pos[0] = xu[soa(2, cap, i)];
-      u[2]   = xu[soa(3, cap, i)];
-      u[1]   = xu[soa(4, cap, i)];
-      u[0]   = xu[soa(5, cap, i)];
-
-      int    ki[3], sh[3], bh[3];
-      double wi[3][N1], wh[3][N1];
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        int ii = digitize(pos[a], c.off[a], g.rdel[a]);
-        ki[a]  = ii - g.is_odd;
-        int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
-        shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
-        shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
-        // interp::shift_weights<O>(hh - ki, wh)  interp.hpp:154-160: the half-grid support starts
-        // one node later; kept as a base offset instead of moving the weights
-        bh[a] = (hh - ki[a] > 0) ? 1 : 0;
-        sh[a] = ii;
+  // ---- bins of the tile, round robin over the warps; one iteration = up to 32 particles of one
+  //      bin.  The loop is flat and software-pipelined: the particle data of the NEXT iteration is
+  //      requested before the current one is processed (few resident warps, long DRAM latency).
+  const int ncell_t = nbn[0] * nbn[1] * nbn[2];
+  // state of an iteration: bin cl = r * nbn[2] + lx (r = row lz * nbn[1] + ly), particles [i0, pe)
+  auto advance = [&](int& cl, int& r, int& lx, int& i0, int& pe) -> bool {
+    i0 += 32;
+    while (i0 >= pe) { // next non-empty bin of this warp
+      cl += NWARP;
+      lx += NWARP;
+      while (lx >= nbn[2]) {
+        lx -= nbn[2];
+        r++;
       }
-      const int  txo       = sh[2] - xs; // cell offset inside the segment
-      const bool sorted_ok = (sh[0] == rz) && (sh[1] == ry) && (txo >= 0) && (txo < ncs);
-      if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
-      const int tx = sorted_ok ? txo : 0;
-
-      // ---- gather: Ex Ey Ez Bx By Bz; half-grid axes: Ex x | Ey y | Ez z | Bx y,z | By x,z | Bz x,y
-      const double* e0 = s_eb + (size_t)tx * 6;
-      auto          at = [&](int bz, int by, int bx, int k) { return e0 + (size_t)((bz * NW + by) * EX + bx) * 6 + k; };
-      double rz6[6];
-      rz6[0] = gather1<O, S>(at(0, 0, bh[2], 0), EX, wi[0], wi[1], wh[2]);
-      rz6[1] = gather1<O, S>(at(0, bh[1], 0, 1), EX, wi[0], wh[1], wi[2]);
-      rz6[2] = gather1<O, S>(at(bh[0], 0, 0, 2), EX, wh[0], wi[1], wi[2]);
-      rz6[3] = gather1<O, S>(at(bh[0], bh[1], 0, 3), EX, wh[0], wh[1], wi[2]);
-      rz6[4] = gather1<O, S>(at(bh[0], 0, bh[2], 4), EX, wh[0], wi[1], wh[2]);
-      rz6[5] = gather1<O, S>(at(0, bh[1], bh[2], 5), EX, wi[0], wh[1], wh[2]);
-      double ex = mul<S>(rz6[0], P.dt1), ey = mul<S>(rz6[1], P.dt1), ez = mul<S>(rz6[2], P.dt1);
-      double bx = mul<S>(rz6[3], P.dt1), by = mul<S>(rz6[4], P.dt1), bz = mul<S>(rz6[5], P.dt1);
-
-      // ---- push_boris (primitives.hpp:165-189) ----------------------------------------------
-      double ux = u[2], uy = u[1], uz = u[0];
-      ux = add<S>(ux, ex);
-      uy = add<S>(uy, ey);
-      uz = add<S>(uz, ez);
-      double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
-      bx = mul<S>(bx, gm);
-      by = mul<S>(by, gm);
-      bz = mul<S>(bz, gm);
-      double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bx, bx)), mul<S>(by, by)), mul<S>(bz, bz)));
-      double vx = add<S>(ux, sub<S>(mul<S>(uy, bz), mul<S>(uz, by)));
-      double vy = add<S>(uy, sub<S>(mul<S>(uz, bx), mul<S>(ux, bz)));
-      double vz = add<S>(uz, sub<S>(mul<S>(ux, by), mul<S>(uy, bx)));
-      ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bz), mul<S>(vz, by)), bb), ex));
-      uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bx), mul<S>(vx, bz)), bb), ey));
-      uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, by), mul<S>(vy, bx)), bb), ez));
-
-      // ---- position update (lorentz_factor, primitives.hpp:158-161) ------------------------
-      double uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
-      double gam = sqrt_<S>(add<S>(1.0, mul<S>(mul<S>(uu, g.rc), g.rc)));
-      double dtg = div_<S>(P.delt, gam);
-      double pn[3];
-      pn[2] = add<S>(pos[2], mul<S>(ux, dtg));
-      pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
-      pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
-
-      xu[soa(0, cap, i)] = pn[2];
-      xu[soa(1, cap, i)] = pn[1];
-      xu[soa(2, cap, i)] = pn[0];
-      xu[soa(3, cap, i)] = ux;
-      xu[soa(4, cap, i)] = uy;
-      xu[soa(5, cap, i)] = uz;
-
-      // ---- bin of the new position: count / classify ------------------------------------------
-      int  i1[3];
-      bool cfl_ok = true;
-      int  dcode  = 0;
-      bool moved  = false;
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        i1[a]   = digitize(pn[a], c.off[a], g.rdel[a]);
-        int dd  = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
-        dcode   = dcode * 3 + dd;
-        int sft = (i1[a] - g.is_odd) - ki[a];
-        cfl_ok  = cfl_ok && (sft >= -1) && (sft <= 1);
-        moved   = moved || (sft != 0);
-      }
-      dir            = dcode;
-      const int lnid = (i - cb) & (LANES - 1);
-      if (dir == 13) {
-        int key     = (ch * g.ncell + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
-        P.sp.key[i] = key;
-        atomicAdd(&P.sp.hist[key], 1);
-      } else {
-        P.sp.key[i] = -1;
-        atomicAdd(&P.sp.oob[ch * LANES + lnid], 1);
-      }
-      if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
-
-      // ---- 1-D deposit weights of this particle -> scratch row --------------------------------
-      // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
-      // ds = ss[1] - ss[0] (ds3d, esirkepov.hpp:167-174); cp[j] = sum of ds over slots < j
-      const bool dep_ok = cfl_ok && sorted_ok;
-      mover             = dep_ok && moved;
-      double* row       = s_scr + (size_t)tid * ROW;
-      double  tail[2 * N1 + 8]; // CPy[1..N1] CPz[1..N1] | DSy0 DSyL CPyL DSz0 DSzL CPzL DSx0 DSxL
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        double wn[N1];
-        int    k1  = i1[a] - g.is_odd;
-        int    sft = k1 - ki[a];
-        shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
-        const int base_p = (a == 2) ? C::PX : (a == 1 ? C::PY : C::PZ);
-        double    cp     = 0.0;
-        double    cpv[NS], dsv[NS], s0v[NS];
-#pragma unroll
-        for (int j = 0; j < NS; j++) {
-          double s0 = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
-          double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // sft = -1 : slot j <- wn[j]
-          double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // sft =  0
-          double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // sft = +1
-          double s1 = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
-          if (!dep_ok) {
-            s0 = 0.0;
-            s1 = 0.0;
-          }
-          s0v[j] = s0;
-          dsv[j] = s1 - s0;
-          cpv[j] = cp;
-          cp += dsv[j];
-        }
-#pragma unroll
-        for (int j = 1; j <= N1; j++)
-          *reinterpret_cast<double2*>(row + base_p + 2 * (j - 1)) = make_double2(s0v[j], dsv[j]);
-        if (a != 2) {
-          const int tc = (a == 1) ? 0 : N1;
-          const int to = 2 * N1 + ((a == 1) ? 0 : 3);
-#pragma unroll
-          for (int j = 1; j <= N1; j++) tail[tc + j - 1] = cpv[j];
-          tail[to + 0] = dsv[0];
-          tail[to + 1] = dsv[NS - 1];
-          tail[to + 2] = cpv[NS - 1];
-        } else {
-          tail[2 * N1 + 6] = dsv[0];
-          tail[2 * N1 + 7] = dsv[NS - 1];
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < N1 + 4; j++)
-        *reinterpret_cast<double2*>(row + C::CY + 2 * j) = make_double2(tail[2 * j], tail[2 * j + 1]);
-      s_cls[tid] = mover ? 1 : 0;
-      if (mover) atomicAdd(&ccnt[tx], 1);
+      if (cl >= ncell_t) return false;
+      i0 = s_cs[r * CSW + lx];
+      pe = s_cs[r * CSW + lx + 1];
     }
+    return true;
+  };
+  auto fetch = [&](double* d, int i) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) d[k] = xu[soa(k, cap, i)];
+  };
 
-    // ---- movers of this batch, in particle order (per-warp lists) ------------------------------
+  int    ncl = warp - NWARP, nr = -1, nlx = warp - NWARP + nbn[2], ni0 = 0, npe = 0;
+  bool   have = advance(ncl, nr, nlx, ni0, npe);
+  double nxt[6] = {0, 0, 0, 0, 0, 0};
+  if (have && ni0 + lane < npe) fetch(nxt, ni0 + lane);
+
+  int  prev_cl = -1, nrec = 0;
+  int  bz = 0, by = 0, bx = 0, cellbase = 0;
+  bool had_leav = false; // warp-uniform
+  const double* ecell = s_eb;
+  double acc[PV];
+
+  while (have) {
+    const int cl = ncl, cr = nr, clx = nlx, i0 = ni0, pe = npe;
+    double    cur[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cur[k] = nxt[k];
+    have = advance(ncl, nr, nlx, ni0, npe);
+    if (have && ni0 + lane < npe) fetch(nxt, ni0 + lane);
+
+    if (cl != prev_cl) { // first iteration of a bin
+      const int lx = clx, lz = (nbn[1] == C::TY) ? cr / C::TY : cr / nbn[1], ly = cr - lz * nbn[1];
+      bz = b0[0] + lz, by = b0[1] + ly, bx = b0[2] + lx;
+      cellbase = ((lz * JY + ly) * JX + lx) * 4; // J-tile offset of mesh slot (0,0,0)
+      ecell    = s_eb + (size_t)((lz * EY + ly) * EX + lx) * 6;
+      had_leav = false;
+      prev_cl  = cl;
+      __syncwarp();
+      if (lane < 27) mydc[lane] = 0;
+      __syncwarp();
+    }
     {
-      const unsigned mm = __ballot_sync(0xffffffffu, mover);
-      if (mover) s_clist[warp * 32 + __popc(mm & ((1u << lane) - 1))] = tid;
-      if (lane == 0) s_wcnt[warp] = __popc(mm);
-    }
+      const int  i     = i0 + lane;
+      const bool valid = i < pe;
+      int        dir   = 13;
+      bool       dep_ok = false, mover = false;
+      int        mcode = -1; // single-axis mover: axis*2 + (1 if high side); -1: multi-axis
+      Wts<O>     w;
+      double     out0[3], outL[3], cpL[3]; // DS[0], DS[NS-1], CP[NS-1] per axis (movers only)
 
-    // ---- ordered rank of the leavers inside this work item (segmented counting scan) ----------
-    const bool leaver = valid && dir != 13;
-    const int  any    = __syncthreads_or(leaver ? 1 : 0); // also: scratch of the batch is complete
-    if (any) {
-      unsigned lm     = __ballot_sync(0xffffffffu, leaver);
-      int      rank_w = 0;
-      if (leaver) {
-        unsigned grpm = __match_any_sync(lm, dir);
-        rank_w        = __popc(grpm & ((1u << lane) - 1));
-        if (rank_w == 0) s_warpcnt[warp * 27 + dir] = __popc(grpm);
-      }
-      __syncthreads();
-      if (leaver) {
-        int r = s_dirbase[dir] + rank_w;
-        for (int w = 0; w < warp; w++) r += s_warpcnt[w * 27 + dir];
-        int slot = atomicAdd(P.sp.nleave, 1);
-        if (slot < P.sp.lcap) P.sp.lrec[slot] = make_int4(i, ch, (item << 8) | dir, r);
-        else atomicOr(P.err, NIXB200_ERR_CAPACITY);
-      }
-      __syncthreads();
-      if (tid < 27) {
-        int s = 0;
-        for (int w = 0; w < THREADS / 32; w++) {
-          s += s_warpcnt[w * 27 + tid];
-          s_warpcnt[w * 27 + tid] = 0;
-        }
-        s_dirbase[tid] += s;
-      }
-      // (next use of s_warpcnt / s_dirbase is behind the barriers of phase 2)
-    }
-    // the other parity's mover counts are free now (last read before the barrier above)
-    for (int t = tid; t < MAXSEG; t += THREADS) s_ccnt[(bpar ^ 1) * MAXSEG + t] = 0;
+      // =============================== push ===============================
+      if (valid) {
+        const double pos[3] = {cur[2], cur[1], cur[0]}; // index 0,1,2 = z,y,x
+        const double u[3]   = {cur[5], cur[4], cur[3]};
 
-    // =============================== phase 2: deposit ===============================
-    // Per particle and (jy,jz) column, with S0/DS the old weights and the weight differences:
-    //   rho[x] += q S1y S1z (S0x+DSx)[x]                                           esirkepov.hpp:155-164
-    //   Jx[x]  += -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz) sum_{l<x} DSx[l]            :177-195
-    //   Jy[x]  += -q dy/dt sum_{l<jy} DSy[l] ((S0z+DSz/2) S0x[x] + (S0z/2+DSz/3) DSx[x])     :198-216
-    //   Jz[x]  += -q dz/dt sum_{l<jz} DSz[l] ((S0x+DSx/2)[x] S0y + (S0x/2+DSx/3)[x] DSy)     :219-237
-    const int nmov_w[NWARP] = {s_wcnt[0], s_wcnt[1], s_wcnt[2], s_wcnt[3]};
-    int       cbase_e       = 0; // movers of this batch in cells before cc
-    const double A = 1.0 / 2, B = 1.0 / 3;
-    while (true) {
-      const int lo = max(s_pidx[cc], b0) - b0;
-      const int hi = min(s_pidx[cc + 1], b1) - b0;
-
-      // ---------- F path: particles that stay in their cell ----------
-      if (f_active) {
-        for (int p = lo + gf; p < hi; p += GF) {
-          if (s_cls[p]) continue;
-          const double* sc  = s_scr + (size_t)p * ROW;
-          const double2 yv  = *reinterpret_cast<const double2*>(sc + C::PY + 2 * fy);
-          const double2 zv  = *reinterpret_cast<const double2*>(sc + C::PZ + 2 * fz);
-          const double  cyp = sc[C::CY + fy], czp = sc[C::CZ + fz];
-          const double  s0y = yv.x, dsy = yv.y, s0z = zv.x, dsz = zv.y;
-          const double  ar = P.q * (s0y + dsy) * (s0z + dsz);
-          const double  wx = -((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz) * P.qdxdt[2];
-          const double  fyv = -cyp * P.qdxdt[1];
-          const double  g0 = fyv * (s0z + A * dsz), g1 = fyv * (A * s0z + B * dsz);
-          const double  fzv = -czp * P.qdxdt[0];
-          const double  h0 = fzv * s0y, h1 = fzv * dsy;
-          const double  k0 = h0 + A * h1, k1 = A * h0 + B * h1;
-          double        cpx = 0.0;
+        int    ki[3], bh[3];
+        double wi[3][N1], wh[3][N1];
+        bool   sorted_ok = true;
 #pragma unroll
-          for (int s = 0; s < N1; s++) {
-            const double2 xv  = *reinterpret_cast<const double2*>(sc + C::PX + 2 * s);
-            const double  s0x = xv.x, dsx = xv.y;
-            accf[s + 1][0]    = fma(ar, s0x + dsx, accf[s + 1][0]);
-            if (s >= 1) accf[s + 1][1] = fma(wx, cpx, accf[s + 1][1]);
-            accf[s + 1][2] = fma(g0, s0x, fma(g1, dsx, accf[s + 1][2]));
-            accf[s + 1][3] = fma(k0, s0x, fma(k1, dsx, accf[s + 1][3]));
-            cpx += dsx;
+        for (int a = 0; a < 3; a++) {
+          int ii = digitize(pos[a], c.off[a], g.rdel[a]);
+          ki[a]  = ii - g.is_odd;
+          int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
+          shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
+          shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
+          // interp::shift_weights<O>(hh - ki, wh)  interp.hpp:154-160: the half-grid support starts
+          // one node later; kept as a base offset instead of moving the weights
+          bh[a]     = (hh - ki[a] > 0) ? 1 : 0;
+          sorted_ok = sorted_ok && (ii == ((a == 0) ? bz : ((a == 1) ? by : bx)));
+        }
+        if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
+
+        // ---- gather: Ex Ey Ez Bx By Bz; half-grid axes: Ex x | Ey y | Ez z | Bx y,z | By x,z | Bz x,y
+        // one loop body for the six components (code size: the loop must stay instruction-cache
+        // resident); the results shift through f6 so that no register array is indexed dynamically
+        double f6[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) f6[k] = 0.0;
+#if NIX_GATHER_UNROLL
+#pragma unroll
+#else
+#pragma unroll 1
+#endif
+        for (int k = 0; k < 6; k++) {
+          const bool hz = (0x1C >> k) & 1, hy = (0x2A >> k) & 1, hx = (0x31 >> k) & 1;
+          double     wz[N1], wy[N1], wx[N1];
+#pragma unroll
+          for (int j = 0; j < N1; j++) {
+            wz[j] = hz ? wh[0][j] : wi[0][j];
+            wy[j] = hy ? wh[1][j] : wi[1][j];
+            wx[j] = hx ? wh[2][j] : wi[2][j];
+          }
+          const double* e = ecell + (hz ? bh[0] : 0) * esz + (hy ? bh[1] : 0) * esy + (hx ? bh[2] : 0) * 6 + k;
+          const double  f = gather1<O, S>(e, wz, wy, wx);
+#pragma unroll
+          for (int q = 0; q < 5; q++) f6[q] = f6[q + 1];
+          f6[5] = f;
+        }
+        double ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
+        double bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
+
+        // ---- push_boris (primitives.hpp:165-189) ----------------------------------------------
+        double ux = u[2], uy = u[1], uz = u[0];
+        ux = add<S>(ux, ex);
+        uy = add<S>(uy, ey);
+        uz = add<S>(uz, ez);
+        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+        bxx = mul<S>(bxx, gm);
+        byy = mul<S>(byy, gm);
+        bzz = mul<S>(bzz, gm);
+        double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+        ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
+        uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
+        uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
+
+        // ---- position update (lorentz_factor, primitives.hpp:158-161) ------------------------
+        double uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
+        double gam = sqrt_<S>(add<S>(1.0, mul<S>(mul<S>(uu, g.rc), g.rc)));
+        double dtg = div_<S>(P.delt, gam);
+        double pn[3];
+        pn[2] = add<S>(pos[2], mul<S>(ux, dtg));
+        pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
+        pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
+
+        xu[soa(0, cap, i)] = pn[2];
+        xu[soa(1, cap, i)] = pn[1];
+        xu[soa(2, cap, i)] = pn[0];
+        xu[soa(3, cap, i)] = ux;
+        xu[soa(4, cap, i)] = uy;
+        xu[soa(5, cap, i)] = uz;
+
+        // ---- bin of the new position: count / classify ------------------------------------------
+        int  i1[3], sft[3];
+        bool cfl_ok = true;
+        int  dcode  = 0, nmove = 0;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          i1[a]  = digitize(pn[a], c.off[a], g.rdel[a]);
+          int dd = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
+          dcode  = dcode * 3 + dd;
+          sft[a] = (i1[a] - g.is_odd) - ki[a];
+          cfl_ok = cfl_ok && (sft[a] >= -1) && (sft[a] <= 1);
+          if (sft[a] != 0) {
+            nmove++;
+            mcode = a * 2 + (sft[a] > 0 ? 1 : 0);
           }
         }
-      }
+        dir            = dcode;
+        const int lnid = (i - cb) & (LANES - 1);
+        if (dir == 13) {
+          int key     = (cellkey0 + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
+          P.sp.key[i] = key;
+          atomicAdd(&P.sp.hist[key], 1);
+        } else {
+          P.sp.key[i] = -1;
+          atomicAdd(&P.sp.oob[ch * LANES + lnid], 1);
+        }
+        if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
+        dep_ok = cfl_ok && sorted_ok;
+        mover  = dep_ok && nmove > 0;
+        if (nmove > 1) mcode = -1;
 
-      // ---------- C path: particles that change cell (block-uniform control flow) ----------
-      const int nmc = s_ccnt[bpar * MAXSEG + cc];
-      if (nmc > 0) {
-        double accc[NS][4];
+        // ---- 1-D deposit weights -------------------------------------------------------------------
+        // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
 #pragma unroll
-        for (int s = 0; s < NS; s++)
+        for (int a = 0; a < 3; a++) {
+          double wn[N1];
+          int    k1 = i1[a] - g.is_odd;
+          shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
+          double cp = 0.0;
 #pragma unroll
-          for (int k = 0; k < 4; k++) accc[s][k] = 0.0;
-        if (c_active) {
-          for (int e = cbase_e + gc; e < cbase_e + nmc; e += GC) {
-            // e-th mover of the batch -> (warp list, index)
-            int w = 0, r = e;
-#pragma unroll
-            for (int q = 0; q < NWARP - 1; q++)
-              if (w == q && r >= nmov_w[q]) {
-                r -= nmov_w[q];
-                w = q + 1;
-              }
-            const int     p   = s_clist[w * 32 + r];
-            const double* sc  = s_scr + (size_t)p * ROW;
-            double        s0y = 0.0, dsy, s0z = 0.0, dsz;
-            if (c_py >= 0) {
-              const double2 v = *reinterpret_cast<const double2*>(sc + c_py);
-              s0y             = v.x;
-              dsy             = v.y;
-            } else {
-              dsy = sc[c_dy];
+          for (int j = 0; j < NS; j++) {
+            double s0 = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
+            double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // sft = -1 : slot j <- wn[j]
+            double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // sft =  0
+            double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // sft = +1
+            double s1 = (sft[a] == 0) ? v0 : ((sft[a] < 0) ? vm : vp);
+            if (!dep_ok) {
+              s0 = 0.0;
+              s1 = 0.0;
             }
-            if (c_pz >= 0) {
-              const double2 v = *reinterpret_cast<const double2*>(sc + c_pz);
-              s0z             = v.x;
-              dsz             = v.y;
-            } else {
-              dsz = sc[c_dz];
+            const double ds = s1 - s0; // ds3d, esirkepov.hpp:167-174
+            if (j >= 1 && j <= N1) {
+              w.s0[a][j - 1] = s0;
+              w.ds[a][j - 1] = ds;
+              w.cp[a][j - 1] = cp;
             }
-            const double cyp = (c_cy >= 0) ? sc[c_cy] : 0.0;
-            const double czp = (c_cz >= 0) ? sc[c_cz] : 0.0;
-            const double ar = P.q * (s0y + dsy) * (s0z + dsz);
-            const double wx = -((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz) * P.qdxdt[2];
-            const double fyv = -cyp * P.qdxdt[1];
-            const double g0 = fyv * (s0z + A * dsz), g1 = fyv * (A * s0z + B * dsz);
-            const double fzv = -czp * P.qdxdt[0];
-            const double h0 = fzv * s0y, h1 = fzv * dsy;
-            const double k0 = h0 + A * h1, k1 = A * h0 + B * h1;
-            double       cpx = 0.0;
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-              if (s >= 1 && s <= N1) {
-                const double2 xv  = *reinterpret_cast<const double2*>(sc + C::PX + 2 * (s - 1));
-                const double  s0x = xv.x, dsx = xv.y;
-                accc[s][0]        = fma(ar, s0x + dsx, accc[s][0]);
-                accc[s][1]        = fma(wx, cpx, accc[s][1]);
-                accc[s][2]        = fma(g0, s0x, fma(g1, dsx, accc[s][2]));
-                accc[s][3]        = fma(k0, s0x, fma(k1, dsx, accc[s][3]));
-                cpx += dsx;
-              } else {
-                const double dsx = sc[C::OUT + 6 + (s == 0 ? 0 : 1)];
-                accc[s][0]       = fma(ar, dsx, accc[s][0]);
-                if (s >= 1) accc[s][1] = fma(wx, cpx, accc[s][1]);
-                accc[s][2] = fma(g1, dsx, accc[s][2]);
-                accc[s][3] = fma(k1, dsx, accc[s][3]);
-                cpx += dsx;
-              }
+            if (j == 0) out0[a] = ds;
+            if (j == NS - 1) {
+              outL[a] = ds;
+              cpL[a]  = cp;
             }
+            cp += ds;
           }
         }
-        // flush the groups that had work into the window, one group per round (no atomics)
-        const int nround = min(nmc, GC);
-        for (int r = 0; r < nround; r++) {
-          __syncthreads();
-          if (c_active && gc == r) {
-#pragma unroll
-            for (int s = 0; s < NS; s++) {
-              double2* w = reinterpret_cast<double2*>(s_win + ((s + rot) % NS) * (NCOL * 4) + col * 4);
-              double2  a = w[0], b = w[1];
-              a.x += accc[s][0];
-              a.y += accc[s][1];
-              b.x += accc[s][2];
-              b.y += accc[s][3];
-              w[0] = a;
-              w[1] = b;
-            }
-          }
-        }
-        cbase_e += nmc;
-      }
-
-      if (cc < ncs && s_pidx[cc + 1] <= b1) {
-        retire(); // cell finished: slide the window (block-uniform)
-        if (cc >= ncs) break;
       } else {
-        break;
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int j = 0; j < N1; j++) w.s0[a][j] = w.ds[a][j] = w.cp[a][j] = 0.0;
+      }
+
+      // ---- leavers: ordered rank inside this bin per direction (warp shuffles) -----------------------
+      const bool     leaver = valid && dir != 13;
+      const unsigned lm     = __ballot_sync(FULL, leaver);
+      if (lm) {
+        had_leav = true;
+        if (leaver) {
+          const unsigned grpm = __match_any_sync(lm, dir);
+          const int      rk   = __popc(grpm & ((1u << lane) - 1));
+          const int      r    = mydc[dir] + rk;
+          const int      bb3[3] = {bz, by, bx};
+          const int      se   = slab_entry(g, dir, bb3);
+          if (se < 0) atomicOr(P.err, NIXB200_ERR_CFL);
+          int slot = atomicAdd(P.sp.nleave, 1);
+          if (slot < P.sp.lcap && se >= 0) P.sp.lrec[slot] = make_int4(i, ch, se, (r << 5) | dir);
+          else atomicOr(P.err, NIXB200_ERR_CAPACITY);
+          __syncwarp(lm);
+          if (rk == 0) mydc[dir] += __popc(grpm);
+        }
+        __syncwarp();
+      }
+
+      // =============================== deposit ===============================
+      // one loop body for all z-planes; the z weights rotate through slot 0 (back in place after N1
+      // turns).  Every plane is summed over the lanes and added to the J tile right away.
+#pragma unroll 1
+      for (int z = 0; z < N1; z++) {
+#pragma unroll
+        for (int v = 0; v < PV; v++) acc[v] = 0.0;
+        plane_accumulate<O>(w.s0[0][0], w.ds[0][0], w.cp[0][0], z >= 1, w, P.q, P.qdxdt, acc);
+        flush_plane(acc, z, cellbase);
+        const double t0 = w.s0[0][0], t1 = w.ds[0][0], t2 = w.cp[0][0];
+#pragma unroll
+        for (int j = 0; j < N1 - 1; j++) {
+          w.s0[0][j] = w.s0[0][j + 1];
+          w.ds[0][j] = w.ds[0][j + 1];
+          w.cp[0][j] = w.cp[0][j + 1];
+        }
+        w.s0[0][N1 - 1] = t0;
+        w.ds[0][N1 - 1] = t1;
+        w.cp[0][N1 - 1] = t2;
+      }
+
+      // ---- movers: record the full 1-D weights; flush the record list when it is full -----------
+      unsigned mm = __ballot_sync(FULL, mover);
+      while (mm) {
+        const int room = MAXMOV - nrec;
+        const int rk   = __popc(mm & ((1u << lane) - 1));
+        const bool take = mover && ((mm >> lane) & 1u) && rk < room;
+        if (take) {
+          double* r = myrec + (nrec + rk) * C::REC;
+#pragma unroll
+          for (int a = 0; a < 3; a++) {
+            r[(3 * a + 0) * NS + 0] = 0.0;
+            r[(3 * a + 1) * NS + 0] = out0[a];
+            r[(3 * a + 2) * NS + 0] = 0.0;
+#pragma unroll
+            for (int j = 0; j < N1; j++) {
+              r[(3 * a + 0) * NS + 1 + j] = w.s0[a][j];
+              r[(3 * a + 1) * NS + 1 + j] = w.ds[a][j];
+              r[(3 * a + 2) * NS + 1 + j] = w.cp[a][j];
+            }
+            r[(3 * a + 0) * NS + NS - 1] = 0.0;
+            r[(3 * a + 1) * NS + NS - 1] = outL[a];
+            r[(3 * a + 2) * NS + NS - 1] = cpL[a];
+          }
+          int* ri = reinterpret_cast<int*>(r + 9 * NS);
+          ri[0]   = cellbase;
+          ri[1]   = mcode;
+        }
+        const unsigned taken = __ballot_sync(FULL, take);
+        nrec += __popc(taken);
+        mm &= ~taken;
+        if (nrec == MAXMOV) { // records carry their bin, so the list is only flushed when it is full
+          flush_movers<O>(s_j, myrec, myml, nrec, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
+          nrec = 0;
+        }
       }
     }
-    bpar ^= 1;
-    __syncthreads(); // scratch may be overwritten by the next batch
+
+    // last iteration of a bin: its leavers per direction -> slab counts (scanned by k_mig_scan)
+    if (had_leav && (!have || ncl != cl)) {
+      __syncwarp();
+      if (lane < 27 && lane != 13 && mydc[lane] > 0) {
+        const int bb3[3] = {bz, by, bx};
+        const int se     = slab_entry(g, lane, bb3);
+        if (se >= 0) P.sp.slabcnt[(size_t)ch * g.slaboff[27] + se] = mydc[lane];
+      }
+    }
   }
+  if (nrec) flush_movers<O>(s_j, myrec, myml, nrec, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
 
-  // ---- drain the window --------------------------------------------------------------------------
-  for (int s = 0; s < NS - 1; s++) retire();
-
-  // leavers of this work item per direction (scanned over the items of the chunk by k_mig_scan)
-  if (tid < 27) P.sp.blockdir[((size_t)ch * g.nitem + item) * 27 + tid] = s_dirbase[tid];
+  // ---- flush the J tile: the CTA's single scatter to global memory --------------------------------
+  __syncthreads();
+  double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
+  for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) {
+    const double v = s_j[t];
+    if (v != 0.0) {
+      const int k = t & 3, n = t >> 2;
+      const int gx = jx0 + n % JX, gy = jy0 + (n / JX) % JY, gz = jz0 + n / (JX * JY);
+      if (gx >= 0 && gx < g.M[2] && gy >= 0 && gy < g.M[1] && gz >= 0 && gz < g.M[0])
+        atomicAdd(&ujc[(((size_t)gz * g.M[1] + gy) * g.M[2] + gx) * 4 + k], v);
+    }
+  }
 }
 
 template <int O, bool S>
@@ -703,17 +830,13 @@ int launch_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st)
   P.q    = a.sp.q;
   for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
   P.err = a.err;
-  if (a.geo.seg + 1 > MAXSEG) {
-    set_error("push segment longer than MAXSEG");
-    return 1;
-  }
-  size_t smem = smem_layout<O>(a.geo.seg).bytes;
+  size_t smem = smem_layout<O>().bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    NIX_CUDA(cudaFuncSetAttribute(k_push_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    NIX_CUDA(cudaFuncSetAttribute(k_push_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
-  int nblocks = a.geo.nchunk * a.geo.nitem;
+  int nblocks = a.geo.nchunk * a.geo.ntile;
   k_push_deposit<O, S><<<nblocks, THREADS, smem, st>>>(*tmap, P);
   NIX_LAUNCHED();
   return 0;
@@ -723,16 +846,42 @@ int launch_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st)
 size_t push_smem_bytes(const Geo& g)
 {
   switch (g.order) {
-  case 1: return smem_layout<1>(g.seg).bytes;
-  case 2: return smem_layout<2>(g.seg).bytes;
-  default: return smem_layout<3>(g.seg).bytes;
+  case 1: return smem_layout<1>().bytes;
+  case 2: return smem_layout<2>().bytes;
+  default: return smem_layout<3>().bytes;
   }
+}
+
+void push_tile_box(int order, int& tz, int& ty, int& tx)
+{
+  (void)order;
+  tz = Cfg<2>::TZ;
+  ty = Cfg<2>::TY;
+  tx = Cfg<2>::TX;
+}
+
+// The bins-per-CTA box is a compile-time constant of the kernel (Cfg<O>::TZ/TY/TX); small chunks use
+// a part of it, long rows are cut into several tiles.
+int choose_push_tile(Geo& g)
+{
+  const int box[3] = {Cfg<2>::TZ, Cfg<2>::TY, Cfg<2>::TX};
+  static_assert(Cfg<1>::TZ == Cfg<2>::TZ && Cfg<3>::TZ == Cfg<2>::TZ && Cfg<1>::TY == Cfg<2>::TY &&
+                    Cfg<3>::TY == Cfg<2>::TY && Cfg<1>::TX == Cfg<2>::TX && Cfg<3>::TX == Cfg<2>::TX,
+                "one tile box for all orders");
+  g.ntile = 1;
+  for (int a = 0; a < 3; a++) {
+    int n     = (g.nc[a] + box[a] - 1) / box[a];      // tiles along this axis
+    g.tile[a] = (g.nc[a] + n - 1) / n;                // balanced, <= box
+    g.ntl[a]  = (g.nc[a] + g.tile[a] - 1) / g.tile[a];
+    g.ntile *= g.ntl[a];
+  }
+  return 0;
 }
 
 int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st)
 {
   // leaver bookkeeping of this step
-  NIX_CUDA(cudaMemsetAsync(a.sp.blockdir, 0, sizeof(int32_t) * (size_t)a.geo.nchunk * a.geo.nitem * 27, st));
+  NIX_CUDA(cudaMemsetAsync(a.sp.slabcnt, 0, sizeof(int32_t) * (size_t)a.geo.nchunk * a.geo.slaboff[27], st));
   NIX_CUDA(cudaMemsetAsync(a.sp.oob, 0, sizeof(int32_t) * a.geo.nchunk * LANES, st));
   NIX_CUDA(cudaMemsetAsync(a.sp.nleave, 0, sizeof(int32_t), st));
   switch (a.geo.order) {

@@ -80,20 +80,41 @@ __global__ void k_count(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
 // ---------------------------------------------------------------------------------------------
 // migration bookkeeping
 // ---------------------------------------------------------------------------------------------
-// exclusive scan of the per-work-item leaver counts inside each chunk (items are in particle order)
-__global__ void k_mig_scan(Geo g, SpeciesDev sp)
+// exclusive scan of the per-bin leaver counts inside the slab of each (chunk, direction); slab
+// entries follow the flat bin order = particle order.  One block per (chunk, direction).
+__global__ void __launch_bounds__(128) k_mig_scan(Geo g, SpeciesDev sp)
 {
-  int ch  = blockIdx.x;
-  int dir = threadIdx.x;
-  if (dir >= 27) return;
-  int32_t* bd      = sp.blockdir + (size_t)ch * g.nitem * 27;
-  int      running = 0;
-  for (int it = 0; it < g.nitem; it++) {
-    int v            = bd[it * 27 + dir];
-    bd[it * 27 + dir] = running;
-    running += v;
+  __shared__ int s_part[128];
+  const int ch  = blockIdx.x / 27;
+  const int dir = blockIdx.x % 27;
+  if (dir == 13) {
+    if (threadIdx.x == 0) sp.sendcnt[ch * 27 + dir] = 0;
+    return;
   }
-  sp.sendcnt[ch * 27 + dir] = (dir == 13) ? 0 : running;
+  int32_t*  sc  = sp.slabcnt + (size_t)ch * g.slaboff[27] + g.slaboff[dir];
+  const int n   = g.slaboff[dir + 1] - g.slaboff[dir];
+  const int per = (n + blockDim.x - 1) / blockDim.x;
+  const int b = threadIdx.x * per, e = min(n, b + per);
+  int       sum = 0;
+  for (int f = b; f < e; f++) sum += sc[f];
+  s_part[threadIdx.x] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int t = 0; t < blockDim.x; t++) {
+      int v     = s_part[t];
+      s_part[t] = run;
+      run += v;
+    }
+    sp.sendcnt[ch * 27 + dir] = run;
+  }
+  __syncthreads();
+  int run = s_part[threadIdx.x];
+  for (int f = b; f < e; f++) {
+    int v = sc[f];
+    sc[f] = run;
+    run += v;
+  }
 }
 
 // message slots per (chunk, dir) and the append offsets of every receive slot
@@ -148,11 +169,10 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
     int4 r    = sp.lrec[j];
     int  i    = r.x;
     int  A    = r.y;
-    int  item = r.z >> 8;
-    int  dir  = r.z & 0xff;
+    int  dir  = r.w & 31;
     int  B    = cg[A].nbr[dir];
     if (B < 0) continue; // no neighbour / other rank
-    int idx   = sp.blockdir[((size_t)A * g.nitem + item) * 27 + dir] + r.w;
+    int idx   = sp.slabcnt[(size_t)A * g.slaboff[27] + r.z] + (r.w >> 5);
     int m     = sp.msgoff[A * 27 + dir] + idx;
     int ipB   = sp.recvoff[B * 27 + (26 - dir)] + idx;
     if (m >= sp.lcap) {
@@ -448,7 +468,7 @@ int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err
 // after push_deposit (which filled key/hist for residents and the leaver records)
 int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st)
 {
-  k_mig_scan<<<g.nchunk, 32, 0, st>>>(g, sp);
+  k_mig_scan<<<g.nchunk * 27, 128, 0, st>>>(g, sp);
   NIX_LAUNCHED();
   k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp);
   NIX_LAUNCHED();
