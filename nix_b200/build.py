@@ -26,29 +26,54 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+def _deps():
+    return glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "nixb200.h")]
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(HERE, "..", "include", "nixb200.h")]
-    return any(os.path.getmtime(p) > t for p in deps)
+    return any(os.path.getmtime(p) > t for p in sources() + _deps())
 
 
 def build(force=False, verbose=False, defines=(), out=None):
-    """defines / out: experiment builds (e.g. -DNIX_PUSH_MINB=3 into libnixb200_x.so, selected at run
-    time with NIXB200_LIB); the default build takes neither."""
+    """Incremental: every .cu is compiled to build/<name>.o (in parallel, only when it or a header
+    changed), then linked.  defines / out: experiment builds (e.g. -DNIX_PUSH_MINB=3 into
+    libnixb200_x.so, selected at run time with NIXB200_LIB); the default build takes neither."""
     if out is None and not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-D" + d for d in defines] + ["-o", out or LIB] + sources()
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose or res.returncode != 0:
-        sys.stderr.write(res.stdout + res.stderr)
-    if res.returncode != 0:
+    tag = "_".join(sorted(defines)).replace("=", "-") if defines else "default"
+    objdir = os.path.join(HERE, "build", tag)
+    os.makedirs(objdir, exist_ok=True)
+    hdr_t = max(os.path.getmtime(p) for p in _deps())
+    cflags = [f for f in NVCC_FLAGS if f != "-shared"] + ["-D" + d for d in defines]
+    procs, objs = [], []
+    for src in sources():
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
+                and os.path.getmtime(obj) > hdr_t):
+            continue
+        procs.append((src, subprocess.Popen([nvcc] + cflags + ["-c", "-o", obj, src], stdout=subprocess.PIPE,
+                                            stderr=subprocess.PIPE, text=True)))
+    report, failed = [], False
+    for src, p in procs:
+        so, se = p.communicate()
+        report.append(so + se)
+        if verbose or p.returncode != 0:
+            sys.stderr.write(so + se)
+        failed = failed or p.returncode != 0
+    if failed:
         raise RuntimeError("nvcc failed building libnixb200.so")
-    if out is None:
-        with open(os.path.join(HERE, "ptxas_report.txt"), "w") as f:
-            f.write(res.stderr)
+    res = subprocess.run([nvcc, "-shared", "-o", out or LIB] + objs, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed linking libnixb200.so")
+    if out is None and report:
+        with open(os.path.join(HERE, "ptxas_report.txt"), "a" if len(procs) < len(objs) else "w") as f:
+            f.write("".join(report))
     return out or LIB
 
 

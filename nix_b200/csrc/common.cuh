@@ -57,7 +57,7 @@ struct SpeciesDev {
   double*  xu;    // [7][cap]
   double*  xv;    // [7][cap]
   int32_t* key;   // [cap]   (chunk*ncell + cell)*8 + lane, -1 = dropped / leaver
-  int32_t* ordl;  // [cap]   per-bin list of pre-sort local indices (for the stable rank)
+  int32_t* ordl;  // [cap]   per-bin member list: position in xu, or 0x80000000|message slot (stable rank)
   int32_t* hist;  // [nchunk*ncell*8]      counts -> consumed as cursors by place
   int32_t* start; // [nchunk*ncell*8 + 1]  exclusive scan of hist (global particle index)
   int32_t* oob;   // [nchunk][8]  row Ng of the reference's pcount
@@ -66,14 +66,13 @@ struct SpeciesDev {
   // migration
   int32_t* slabcnt;  // [nchunk][slaboff[27]] leavers per (slab bin, direction); scanned in place
   int32_t* sendcnt;  // [nchunk][27]
-  int32_t* msgoff;   // [nchunk][27]  first message slot of (chunk, dir)
+  int32_t* msgoff;   // [nchunk][27]  first message slot of RECEIVE slot e of a chunk (destination-major)
   int32_t* recvoff;  // [nchunk][27]  pre-sort local index of the first particle received in slot e
   int32_t* nleave;   // [1] number of leaver records
   int32_t* nmsg;     // [1] total message particles
   int4*    lrec;     // [lcap] leaver records {i, chunk, slab entry, (rank in bin)<<5 | dir}
   double*  msg;      // [7][lcap] message payload (wrapped positions), SoA
   int32_t* msgkey;   // [lcap]
-  int32_t* msgord;   // [lcap]
   double   q, m;
   int64_t  cap, lcap;
 };

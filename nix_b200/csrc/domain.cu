@@ -107,8 +107,7 @@ static int make_tensor_map(Domain* d)
 static int free_species(SpeciesDev& s)
 {
   void* ptrs[] = {s.xu,      s.xv,     s.key,    s.ordl,  s.hist,   s.start, s.oob,    s.cbase, s.cbase_new,
-                  s.slabcnt, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey,
-                  s.msgord};
+                  s.slabcnt, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   std::memset(&s, 0, sizeof(s));
@@ -144,7 +143,7 @@ static int alloc_species_fixed(Domain* d, SpeciesDev& s)
 
 static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
 {
-  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.msgord};
+  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey};
   for (void* p : old)
     if (p) cudaFree(p);
   double f = d->desc.capacity_factor > 0 ? d->desc.capacity_factor : 1.25;
@@ -166,7 +165,6 @@ static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
   NIX_CUDA(cudaMalloc(&s.lrec, sizeof(int4) * lcap));
   NIX_CUDA(cudaMalloc(&s.msg, sizeof(double) * NC * lcap));
   NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
-  NIX_CUDA(cudaMalloc(&s.msgord, sizeof(int32_t) * lcap));
   NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
   return 0;

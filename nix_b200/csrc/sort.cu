@@ -12,8 +12,11 @@
 //     key = (chunk*ncell + cell)*8 + lane,
 // the histogram over it is the reference's pcount, its exclusive scan gives pindex and the new
 // chunk bases, and stability is obtained without any ordered atomics: `place` drops each
-// particle's pre-sort index `ord` into its bin in arbitrary order, `scatter` then ranks a particle
-// by counting the smaller `ord`s in its (tiny) bin.  All integer work -> bit-exact.
+// particle's pre-sort position `ord` into the slot range of its bin in arbitrary order; `gather`
+// then runs over the DESTINATION slots: slot j holds some member of its bin, ranks it by counting
+// the smaller `ord`s of the (tiny) bin and moves the particle to start[key] + rank.  A warp thus
+// writes a permutation of its own 32 consecutive slots (full sectors, no write amplification) and
+// reads the pre-sort neighbourhood of the same cells.  All integer work -> bit-exact.
 #include "common.cuh"
 
 namespace nixb200
@@ -117,20 +120,23 @@ __global__ void __launch_bounds__(128) k_mig_scan(Geo g, SpeciesDev sp)
   }
 }
 
-// message slots per (chunk, dir) and the append offsets of every receive slot
-// (pre_unpack/unpack order: slots in (iz,iy,ix) order, xtensor_halo3d.hpp:440-461,507-524)
+// message slots and append offsets of every receive slot (pre_unpack/unpack order: slots in
+// (iz,iy,ix) order, xtensor_halo3d.hpp:440-461,507-524).  The message buffer is DESTINATION-major:
+// the particles chunk B receives sit in the order B appends them, so that the order of message
+// slots inside a chunk equals the order of the pre-sort indices (what the stable rank needs).
 __global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
 {
   __shared__ int s_part[1024];
-  const int      n   = g.nchunk * 27;
   const int      tid = threadIdx.x;
-  const int      per = (n + blockDim.x - 1) / blockDim.x;
-  const int      b = tid * per, e = min(n, b + per);
-  int            sum = 0;
-  for (int f = b; f < e; f++) {
-    int ch = f / 27, dir = f % 27;
-    sum += (cg[ch].nbr[dir] >= 0) ? sp.sendcnt[f] : 0;
-  }
+  const int      per = (g.nchunk + blockDim.x - 1) / blockDim.x;
+  const int      b = tid * per, e = min(g.nchunk, b + per);
+  auto recv_cnt = [&](int ch, int s) {
+    int nb = cg[ch].nbr[s];
+    return (s != 13 && nb >= 0) ? sp.sendcnt[nb * 27 + (26 - s)] : 0;
+  };
+  int sum = 0;
+  for (int ch = b; ch < e; ch++)
+    for (int s = 0; s < 27; s++) sum += recv_cnt(ch, s);
   s_part[tid] = sum;
   __syncthreads();
   if (tid == 0) {
@@ -144,17 +150,13 @@ __global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev
   }
   __syncthreads();
   int run = s_part[tid];
-  for (int f = b; f < e; f++) {
-    int ch = f / 27, dir = f % 27;
-    sp.msgoff[f] = run;
-    run += (cg[ch].nbr[dir] >= 0) ? sp.sendcnt[f] : 0;
-  }
-  for (int ch = tid; ch < g.nchunk; ch += blockDim.x) {
+  for (int ch = b; ch < e; ch++) {
     int running = sp.cbase[ch + 1] - sp.cbase[ch];
     for (int s = 0; s < 27; s++) {
-      int nb                  = cg[ch].nbr[s];
-      int cnt                 = (s != 13 && nb >= 0) ? sp.sendcnt[nb * 27 + (26 - s)] : 0;
-      sp.recvoff[ch * 27 + s] = running;
+      int cnt                 = recv_cnt(ch, s);
+      sp.msgoff[ch * 27 + s]  = run;     // first message slot of receive slot s of chunk ch
+      sp.recvoff[ch * 27 + s] = running; // pre-sort local index of its first particle
+      run += cnt;
       running += cnt;
     }
   }
@@ -173,7 +175,7 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
     int  B    = cg[A].nbr[dir];
     if (B < 0) continue; // no neighbour / other rank
     int idx   = sp.slabcnt[(size_t)A * g.slaboff[27] + r.z] + (r.w >> 5);
-    int m     = sp.msgoff[A * 27 + dir] + idx;
+    int m     = sp.msgoff[B * 27 + (26 - dir)] + idx;
     int ipB   = sp.recvoff[B * 27 + (26 - dir)] + idx;
     if (m >= sp.lcap) {
       atomicOr(err, NIXB200_ERR_CAPACITY);
@@ -203,7 +205,6 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
 #pragma unroll
     for (int k = 0; k < NC; k++) sp.msg[soa(k, sp.lcap, m)] = v[k];
     sp.msgkey[m] = key;
-    sp.msgord[m] = ipB;
   }
 }
 
@@ -348,14 +349,12 @@ __global__ void k_chunk_bases(Geo g, SpeciesDev sp, const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 __global__ void k_place(Geo g, SpeciesDev sp)
 {
-  const int ntot   = sp.cbase[g.nchunk];
-  const int perchk = g.ncell * LANES;
+  const int ntot = sp.cbase[g.nchunk];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
     int k = sp.key[i];
     if (k < 0) continue;
-    int ch        = k / perchk;
     int slot      = sp.start[k] + atomicSub(&sp.hist[k], 1) - 1;
-    sp.ordl[slot] = i - sp.cbase[ch];
+    sp.ordl[slot] = i; // residents: position in xu (same order as the pre-sort index inside a chunk)
   }
 }
 
@@ -366,76 +365,38 @@ __global__ void k_place_msg(Geo g, SpeciesDev sp)
     int k = sp.msgkey[m];
     if (k < 0) continue;
     int slot      = sp.start[k] + atomicSub(&sp.hist[k], 1) - 1;
-    sp.ordl[slot] = sp.msgord[m];
+    sp.ordl[slot] = (int)(0x80000000u | (unsigned)m); // received: behind every resident, in append order
   }
 }
 
-__device__ __forceinline__ int stable_rank(const int32_t* __restrict__ ordl, int lo, int hi, int ord)
-{
-  int r = 0;
-  for (int e = lo; e < hi; e++) r += (ordl[e] < ord) ? 1 : 0;
-  return r;
-}
-
 // ---------------------------------------------------------------------------------------------
-// scatter: xv[start[key] + rank] = xu[i]   (xtensor_particle.hpp:303-313)
-// two consecutive particles per thread -> 128-bit coalesced loads of every SoA component
+// gather: for every destination slot j of the sorted array: the member v = ordl[j] of the bin that
+// owns j goes to start[key] + (number of members with a smaller pre-sort position)
+// (xtensor_particle.hpp:303-313).  Unsigned compare: received particles (top bit set) follow the
+// residents.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_scatter(Geo g, SpeciesDev sp)
+__global__ void __launch_bounds__(256) k_gather(Geo g, SpeciesDev sp)
 {
-  const int ntot   = sp.cbase[g.nchunk];
-  const int perchk = g.ncell * LANES;
-  const int npair  = (ntot + 1) >> 1;
-  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < npair; t += gridDim.x * blockDim.x) {
-    const int i0 = 2 * t;
-    int       k0 = -1, k1 = -1;
-    if (i0 + 1 < ntot) {
-      int2 kk = *reinterpret_cast<const int2*>(sp.key + i0);
-      k0      = kk.x;
-      k1      = kk.y;
-    } else {
-      k0 = sp.key[i0];
-    }
-    if (k0 < 0 && k1 < 0) continue;
-    int dst0 = -1, dst1 = -1;
-    if (k0 >= 0) {
-      int lo = sp.start[k0], hi = sp.start[k0 + 1];
-      dst0 = lo + stable_rank(sp.ordl, lo, hi, i0 - sp.cbase[k0 / perchk]);
-    }
-    if (k1 >= 0) {
-      int lo = sp.start[k1], hi = sp.start[k1 + 1];
-      dst1 = lo + stable_rank(sp.ordl, lo, hi, i0 + 1 - sp.cbase[k1 / perchk]);
-    }
-    if (dst0 >= sp.cap) dst0 = -1;
-    if (dst1 >= sp.cap) dst1 = -1;
+  const size_t nkey = (size_t)g.nchunk * g.ncell * LANES;
+  const int    ntot = min(sp.start[nkey], (int)sp.cap);
+  const int32_t* __restrict__ ordl = sp.ordl;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ntot; j += gridDim.x * blockDim.x) {
+    const int      v   = ordl[j];
+    const bool     res = v >= 0;
+    const int      m   = v & 0x7fffffff;
+    const int      k   = res ? sp.key[m] : sp.msgkey[m];
+    const int      lo = sp.start[k], hi = sp.start[k + 1];
+    const unsigned uv = (unsigned)v;
+    int            r  = 0;
+    for (int e = lo; e < hi; e++) r += ((unsigned)ordl[e] < uv) ? 1 : 0;
+    const int     dst = lo + r;
+    const double* src = res ? sp.xu : sp.msg;
+    const size_t  scp = res ? (size_t)sp.cap : (size_t)sp.lcap;
+    double        val[NC];
 #pragma unroll
-    for (int c = 0; c < NC; c++) {
-      const double* src = sp.xu + soa(c, sp.cap, i0);
-      double        a, b = 0.0;
-      if (i0 + 1 < ntot) {
-        double2 v = *reinterpret_cast<const double2*>(src);
-        a         = v.x;
-        b         = v.y;
-      } else {
-        a = src[0];
-      }
-      if (dst0 >= 0) sp.xv[soa(c, sp.cap, dst0)] = a;
-      if (dst1 >= 0) sp.xv[soa(c, sp.cap, dst1)] = b;
-    }
-  }
-}
-
-__global__ void k_scatter_msg(Geo g, SpeciesDev sp)
-{
-  const int nm = min(*sp.nmsg, (int)sp.lcap);
-  for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
-    int k = sp.msgkey[m];
-    if (k < 0) continue;
-    int lo = sp.start[k], hi = sp.start[k + 1];
-    int dst = lo + stable_rank(sp.ordl, lo, hi, sp.msgord[m]);
-    if (dst >= sp.cap) continue;
+    for (int c = 0; c < NC; c++) val[c] = src[soa(c, scp, m)];
 #pragma unroll
-    for (int c = 0; c < NC; c++) sp.xv[soa(c, sp.cap, dst)] = sp.msg[soa(c, sp.lcap, m)];
+    for (int c = 0; c < NC; c++) sp.xv[soa(c, sp.cap, dst)] = val[c];
   }
 }
 
@@ -499,9 +460,7 @@ int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void
   NIX_LAUNCHED();
   k_place_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp);
   NIX_LAUNCHED();
-  k_scatter<<<grid_for(sp.cap / 2, 256), 256, 0, st>>>(g, sp);
-  NIX_LAUNCHED();
-  k_scatter_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp);
+  k_gather<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp);
   NIX_LAUNCHED();
   return 0;
 }
