@@ -120,6 +120,38 @@ int nixb200_chunk_halo_pack(nixb200_domain* d, int k, int mode, void* host_sendb
 int nixb200_chunk_halo_unpack(nixb200_domain* d, int k, int mode, const void* host_recvbuf,
                               const int* nbvalid27);
 
+/* ---- several ranks (one GPU each): chunks partitioned along the space-filling-curve order ----
+ * The host keeps ChunkMap / Balancer and hands over the rank boundaries (ChunkMap::get_rank,
+ * chunkmap.cpp:156-164; Balancer::assign_initial, balancer.cpp:101-124).  Neighbours on other ranks
+ * are then served by ONE message per (peer rank, mode) over NCCL send/recv instead of the
+ * reference's 26 MPI messages per chunk and mode (Chunk::begin_bc_exchange / end_bc_exchange,
+ * chunk.hpp:507-586; probe_bc_exchange, chunk.cpp:310-395); nixb200_domain_exchange_* /
+ * _migrate_sort / _step include the cross-rank part once set_ranks + comm_init have been called.
+ *
+ * The plan (which slab goes to which rank, in the order both sides derive independently: sorted by
+ * sender chunk id, then direction) is pure host logic and needs no device. */
+typedef struct nixb200_plan nixb200_plan;
+int nixb200_plan_create(const int* cdims /*[3]*/, const int* dims /*[3]*/, int nb, const int* coord,
+                        int nrank, const int* boundary /*[nrank+1]*/, int rank, nixb200_plan** out);
+int nixb200_plan_destroy(nixb200_plan* p);
+int nixb200_plan_npeer(const nixb200_plan* p);
+int nixb200_plan_peer(const nixb200_plan* p, int q, int* peer_rank, int* nsend, int* nrecv);
+/* send3 [nsend][3] = (my chunk id, direction, cells); recv3 [nrecv][3] = (my chunk id, receive
+ * slot, cells); entry j of my send list to rank r pairs with entry j of r's receive list from me */
+int nixb200_plan_entries(const nixb200_plan* p, int q, int* send3, int* recv3);
+
+/* boundary[rank], boundary[rank+1] must equal the domain's id_begin, id_end */
+int nixb200_domain_set_ranks(nixb200_domain* d, int nrank, const int* boundary, int rank);
+/* NCCL bootstrap: rank 0 calls comm_unique_id, the host broadcasts the 128 bytes (MPI_Bcast in a nix
+ * application), every rank calls comm_init -- or hands over a communicator it already owns */
+int nixb200_comm_unique_id(void* id128);
+int nixb200_domain_comm_init(nixb200_domain* d, const void* id128);
+int nixb200_domain_set_comm(nixb200_domain* d, void* nccl_comm);
+/* per step: ghost cells sent to other ranks per halo exchange; particles sent / received by the
+ * last migrate */
+int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int64_t* particles_sent,
+                                int64_t* particles_received);
+
 /* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
  * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only).
  * With profiling on, every phase call is bracketed by CUDA events on the domain's stream;

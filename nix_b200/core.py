@@ -28,6 +28,9 @@ SYMBOLS = [
     "nixb200_halo_layout", "nixb200_chunk_halo_pack", "nixb200_chunk_halo_unpack",
     "nixb200_domain_get_load", "nixb200_domain_total_particles", "nixb200_domain_field_upload_async",
     "nixb200_domain_field_download_async", "nixb200_domain_set_profiling", "nixb200_domain_get_phase_ms",
+    "nixb200_plan_create", "nixb200_plan_destroy", "nixb200_plan_npeer", "nixb200_plan_peer",
+    "nixb200_plan_entries", "nixb200_domain_set_ranks", "nixb200_comm_unique_id", "nixb200_domain_comm_init",
+    "nixb200_domain_set_comm", "nixb200_domain_peer_traffic",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort")
@@ -103,6 +106,16 @@ def load_library():
     sig("nixb200_domain_get_phase_ms", I, P, I, PD, PI)
     sig("nixb200_domain_get_load", I, P, PD)
     sig("nixb200_domain_total_particles", C.c_int64, P)
+    sig("nixb200_plan_create", I, PI, PI, I, PI, I, PI, I, C.POINTER(P))
+    sig("nixb200_plan_destroy", I, P)
+    sig("nixb200_plan_npeer", I, P)
+    sig("nixb200_plan_peer", I, P, I, PI, PI, PI)
+    sig("nixb200_plan_entries", I, P, I, PI, PI)
+    sig("nixb200_domain_set_ranks", I, P, I, PI, I)
+    sig("nixb200_comm_unique_id", I, P)
+    sig("nixb200_domain_comm_init", I, P, P)
+    sig("nixb200_domain_set_comm", I, P, P)
+    sig("nixb200_domain_peer_traffic", I, P, PL, PL, PL)
     _lib = lib
     return lib
 
@@ -115,6 +128,42 @@ def lexicographic_coords(cdims):
     """id -> (cz,cy,cx) in plain z-major order (a valid, if not locality-preserving, chunk order)."""
     cz, cy, cx = cdims
     return np.array([(z, y, x) for z in range(cz) for y in range(cy) for x in range(cx)], dtype=np.int32)
+
+
+class Plan:
+    """Which slabs of which local chunk cross to which rank (host logic only, no device needed).
+
+    peers[q] = dict(rank, send=[(chunk id, direction, cells)], recv=[(chunk id, receive slot, cells)]);
+    entry j of my send list to rank r pairs with entry j of r's receive list from me."""
+
+    def __init__(self, cdims, dims, nb, coord, boundary, rank):
+        lib = load_library()
+        cd = np.ascontiguousarray(cdims, dtype=np.int32)
+        dm = np.ascontiguousarray(dims, dtype=np.int32)
+        co = np.ascontiguousarray(coord, dtype=np.int32)
+        bd = np.ascontiguousarray(boundary, dtype=np.int32)
+        PI = C.POINTER(C.c_int)
+        h = C.c_void_p()
+        rc = lib.nixb200_plan_create(cd.ctypes.data_as(PI), dm.ctypes.data_as(PI), int(nb), co.ctypes.data_as(PI),
+                                     len(bd) - 1, bd.ctypes.data_as(PI), int(rank), C.byref(h))
+        if rc != 0:
+            raise NixB200Error(lib.nixb200_last_error().decode())
+        self.peers = []
+        for q in range(lib.nixb200_plan_npeer(h)):
+            r, ns, nr = C.c_int(), C.c_int(), C.c_int()
+            lib.nixb200_plan_peer(h, q, C.byref(r), C.byref(ns), C.byref(nr))
+            snd = np.zeros((ns.value, 3), dtype=np.int32)
+            rcv = np.zeros((nr.value, 3), dtype=np.int32)
+            lib.nixb200_plan_entries(h, q, snd.ctypes.data_as(PI), rcv.ctypes.data_as(PI))
+            self.peers.append(dict(rank=r.value, send=[tuple(int(v) for v in e) for e in snd],
+                                   recv=[tuple(int(v) for v in e) for e in rcv]))
+        lib.nixb200_plan_destroy(h)
+
+
+def uniform_boundary(nchunk, nrank):
+    """Rank boundaries for equal loads: what Balancer::assign_initial (balancer.cpp:101-124) returns
+    for a uniform load vector (unittest/test_balancer.cpp:41-44: boundary[i] == i * nchunk / nrank)."""
+    return np.array([(nchunk * r) // nrank for r in range(nrank + 1)], dtype=np.int32)
 
 
 class Domain:
@@ -154,6 +203,32 @@ class Domain:
             C.byref(self.h)))
         if stream is not None:
             self.set_stream(stream)
+
+    # ---- several ranks ----
+    def set_ranks(self, boundary, rank):
+        """Chunks partitioned over ranks along the id order; boundary[rank:rank+2] must be my id range."""
+        bd = np.ascontiguousarray(boundary, dtype=np.int32)
+        self._ck(self.lib.nixb200_domain_set_ranks(self.h, len(bd) - 1, bd.ctypes.data_as(C.POINTER(C.c_int)),
+                                                   int(rank)))
+
+    def comm_init_torch(self, group=None):
+        """NCCL bootstrap through an initialised torch.distributed group: rank 0 draws the unique id,
+        the group broadcasts its 128 bytes, every rank joins the library's own communicator."""
+        import torch
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if dist.get_rank(group) == 0:
+            self._ck(self.lib.nixb200_comm_unique_id(C.cast(buf, C.c_void_p)))
+        dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+        t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0, group=group)
+        raw = bytes(t.cpu().tolist())
+        self._ck(self.lib.nixb200_domain_comm_init(self.h, C.c_char_p(raw)))
+
+    def peer_traffic(self):
+        a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.nixb200_domain_peer_traffic(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(halo_cells_sent=a.value, particles_sent=b.value, particles_received=c.value)
 
     def _ck(self, rc):
         if rc != 0:

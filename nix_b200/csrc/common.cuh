@@ -73,8 +73,28 @@ struct SpeciesDev {
   int4*    lrec;     // [lcap] leaver records {i, chunk, slab entry, (rank in bin)<<5 | dir}
   double*  msg;      // [7][lcap] message payload (wrapped positions), SoA
   int32_t* msgkey;   // [lcap]
+  // neighbours on other ranks (peer.cu); null / unused for a single-rank domain
+  double*  paysend;  // [lcap][7] AoS payload of the leavers bound for other ranks, peer-major
+  double*  payrecv;  // [lcap][7] AoS payload received from other ranks, peer-major
+  int32_t* ptab;     // per-step tables: spoff[nsend+1] | rpoff[nrecv+1] | rcnt[nrecv]
   double   q, m;
   int64_t  cap, lcap;
+};
+
+// one slab crossing a rank boundary: local chunk k, direction / receive slot dir, first cell of the
+// slab inside the (peer-major) halo buffer, cells in the slab, and the position of its particle
+// count inside the count message of its peer: cidx + species * cstride
+struct PeerEntry {
+  int k, dir, celloff, cells, cidx, cstride;
+};
+
+// tables of the cross-rank exchange, passed to kernels by value; all null for a single-rank domain
+struct PeerTabs {
+  const PeerEntry* send_ent;     // [nsend] sorted by (peer, sender chunk id, direction)
+  const PeerEntry* recv_ent;     // [nrecv] same order as the sender's list
+  const int32_t*   send_slot;    // [nchunk][27] -> send entry, -1
+  const int32_t*   recv_slot;    // [nchunk][27] -> recv entry, -1
+  int              nsend, nrecv;
 };
 
 inline __host__ __device__ size_t soa(int comp, size_t cap, size_t i)
@@ -188,13 +208,23 @@ void   push_tile_box(int order, int& tz, int& ty, int& tx);
 int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits
 
 int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
-int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
+int launch_mig_scan(const Geo& g, SpeciesDev& sp, cudaStream_t st);
+int launch_peer_counts(const Geo& g, const SpeciesDev& sp, const PeerTabs& pt, int is, int32_t* cnt_send,
+                       cudaStream_t st);
+int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int* err,
+                     cudaStream_t st);
+int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int nrecv_particles,
+                    int* err, cudaStream_t st);
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
                 cudaStream_t st);
 size_t scan_tmp_bytes(size_t n);
 
-int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, cudaStream_t st);
-int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, cudaStream_t st);
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, const PeerTabs& pt, const double* recvbuf,
+                      cudaStream_t st);
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, const PeerTabs& pt, const double* recvbuf,
+                        cudaStream_t st);
+int launch_peer_pack(const Geo& g, int mode, const double* data, const PeerTabs& pt, double* sendbuf,
+                     cudaStream_t st);
 int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* buf, cudaStream_t st);
 int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
                        const int* nbvalid_dev, cudaStream_t st);

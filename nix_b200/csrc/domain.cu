@@ -6,7 +6,7 @@
 //                                                                  exactly the reference's arrays
 //   per species: SoA particles of ALL chunks concatenated in chunk order (xu / xv double buffer),
 //                the global (chunk, cell, lane) histogram and its scan (= pcount / pindex).
-#include "common.cuh"
+#include "domain.hpp"
 
 #include <algorithm>
 #include <cstring>
@@ -21,51 +21,6 @@ void set_error(const std::string& msg)
 {
   g_error = msg;
 }
-
-struct Domain {
-  nixb200_domain_desc     desc;
-  Geo                     geo;
-  std::vector<ChunkGeo>   cg_host;
-  ChunkGeo*               cg_dev = nullptr;
-  double*                 uf     = nullptr;
-  double*                 uj     = nullptr;
-  std::vector<SpeciesDev> sp;
-  cudaStream_t            stream = nullptr;
-  CUtensorMap             tmap;
-  void*                   scan_tmp = nullptr;
-  int*                    err_dev  = nullptr;
-  int*                    nbvalid_dev = nullptr;
-  double*                 halo_buf    = nullptr; // device staging for the per-chunk buffer API
-  size_t                  halo_buf_bytes = 0;
-  cudaEvent_t             ev0 = nullptr, ev1 = nullptr;
-  bool                    timed = false;
-  size_t                  cells_per_chunk = 0;
-  bool                    particles_set   = false;
-  bool                    profiling       = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[NIXB200_NPHASE];
-  double                  phase_ms[NIXB200_NPHASE]    = {0, 0, 0, 0, 0};
-  int                     phase_calls[NIXB200_NPHASE] = {0, 0, 0, 0, 0};
-};
-
-// RAII bracket: records an event pair around one phase when profiling is on
-struct PhaseTimer {
-  Domain*     d;
-  int         phase;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  PhaseTimer(Domain* dd, int ph) : d(dd), phase(ph)
-  {
-    if (!d->profiling) return;
-    cudaEventCreate(&e0);
-    cudaEventCreate(&e1);
-    cudaEventRecord(e0, d->stream);
-  }
-  ~PhaseTimer()
-  {
-    if (!e0) return;
-    cudaEventRecord(e1, d->stream);
-    d->pending[phase].push_back({e0, e1});
-  }
-};
 
 static int required_nb(int order)
 {
@@ -107,7 +62,7 @@ static int make_tensor_map(Domain* d)
 static int free_species(SpeciesDev& s)
 {
   void* ptrs[] = {s.xu,      s.xv,     s.key,    s.ordl,  s.hist,   s.start, s.oob,    s.cbase, s.cbase_new,
-                  s.slabcnt, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey};
+                  s.slabcnt, s.sendcnt, s.msgoff, s.recvoff, s.nleave, s.nmsg, s.lrec,   s.msg,   s.msgkey, s.paysend, s.payrecv, s.ptab};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   std::memset(&s, 0, sizeof(s));
@@ -143,9 +98,10 @@ static int alloc_species_fixed(Domain* d, SpeciesDev& s)
 
 static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
 {
-  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey};
+  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.paysend, s.payrecv};
   for (void* p : old)
     if (p) cudaFree(p);
+  s.paysend = s.payrecv = nullptr;
   double f = d->desc.capacity_factor > 0 ? d->desc.capacity_factor : 1.25;
   if (f < 1.0) f = 1.0;
   int64_t cap = (int64_t)((double)ntot * f) + 1024;
@@ -167,6 +123,7 @@ static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
   NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
   NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
+  if (d->peer && peer_alloc_species(d, s)) return 1;
   return 0;
 }
 
@@ -196,7 +153,7 @@ static int check_species(Domain* d, int is)
   return 0;
 }
 
-static int do_sort_species(Domain* d, SpeciesDev& s)
+int do_sort_species(Domain* d, SpeciesDev& s)
 {
   if (launch_sort(d->geo, d->cg_dev, s, d->err_dev, d->scan_tmp, d->stream)) return 1;
   std::swap(s.xu, s.xv);           // XtensorParticle::swap, xtensor_particle.hpp:120-123
@@ -331,6 +288,7 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
     }
     grid2id[(c[0] * cd[1] + c[1]) * cd[2] + c[2]] = id;
   }
+  d->coord_all.assign(coord, coord + 3 * ncid);
   d->cg_host.resize(g.nchunk);
   for (int k = 0; k < g.nchunk; k++) {
     const int* c  = &coord[3 * (desc->id_begin + k)];
@@ -405,6 +363,7 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   Domain* d = D(dd);
   if (!d) return 0;
   cudaDeviceSynchronize();
+  peer_destroy(d);
   for (auto& s : d->sp) free_species(s);
   if (d->cg_dev) cudaFree(d->cg_dev);
   if (d->uf) cudaFree(d->uf);
@@ -676,7 +635,8 @@ int nixb200_domain_exchange_current(nixb200_domain* dd)
   Domain* d = D(dd);
   if (!d) return 1;
   PhaseTimer pt(d, 1);
-  return launch_halo_current(d->geo, d->cg_dev, d->uj, d->stream);
+  if (peer_exchange_halo(d, NIXB200_MODE_CURRENT)) return 1;
+  return launch_halo_current(d->geo, d->cg_dev, d->uj, peer_tabs(d), peer_recvbuf(d), d->stream);
 }
 
 int nixb200_domain_exchange_field(nixb200_domain* dd)
@@ -684,7 +644,8 @@ int nixb200_domain_exchange_field(nixb200_domain* dd)
   Domain* d = D(dd);
   if (!d) return 1;
   PhaseTimer pt(d, 2);
-  return launch_halo_field(d->geo, d->cg_dev, d->uf, d->stream);
+  if (peer_exchange_halo(d, NIXB200_MODE_FIELD)) return 1;
+  return launch_halo_field(d->geo, d->cg_dev, d->uf, peer_tabs(d), peer_recvbuf(d), d->stream);
 }
 
 int nixb200_domain_migrate_sort(nixb200_domain* dd)
@@ -692,8 +653,11 @@ int nixb200_domain_migrate_sort(nixb200_domain* dd)
   Domain* d = D(dd);
   if (!d) return 1;
   PhaseTimer pt(d, 3);
+  if (d->peer) return peer_migrate(d);
+  const PeerTabs none = peer_tabs(d);
   for (auto& s : d->sp) {
-    if (launch_migrate(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
+    if (launch_mig_scan(d->geo, s, d->stream)) return 1;
+    if (launch_mig_route(d->geo, d->cg_dev, s, none, d->err_dev, d->stream)) return 1;
     if (do_sort_species(d, s)) return 1;
   }
   return 0;

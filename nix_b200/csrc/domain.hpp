@@ -1,0 +1,69 @@
+// domain.hpp -- host-side state of one rank's device-resident chunk set (shared by domain.cu, peer.cu)
+#pragma once
+
+#include "common.cuh"
+
+#include <memory>
+
+namespace nixb200
+{
+struct Plan;   // peer.cu: which slabs cross to which rank
+struct PeerCtx; // peer.cu: device tables, buffers and the NCCL communicator of the cross-rank exchange
+
+struct Domain {
+  nixb200_domain_desc     desc;
+  Geo                     geo;
+  std::vector<ChunkGeo>   cg_host;
+  ChunkGeo*               cg_dev = nullptr;
+  double*                 uf     = nullptr;
+  double*                 uj     = nullptr;
+  std::vector<SpeciesDev> sp;
+  cudaStream_t            stream = nullptr;
+  CUtensorMap             tmap;
+  void*                   scan_tmp = nullptr;
+  int*                    err_dev  = nullptr;
+  int*                    nbvalid_dev = nullptr;
+  double*                 halo_buf    = nullptr; // device staging for the per-chunk buffer API
+  size_t                  halo_buf_bytes = 0;
+  cudaEvent_t             ev0 = nullptr, ev1 = nullptr;
+  bool                    timed = false;
+  size_t                  cells_per_chunk = 0;
+  bool                    particles_set   = false;
+  bool                    profiling       = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[NIXB200_NPHASE];
+  std::vector<int>        coord_all; // id -> (cz,cy,cx) of every chunk of the box
+  PeerCtx*                peer = nullptr; // non-null after nixb200_domain_set_ranks with neighbours on other ranks
+  double                  phase_ms[NIXB200_NPHASE]    = {0, 0, 0, 0, 0};
+  int                     phase_calls[NIXB200_NPHASE] = {0, 0, 0, 0, 0};
+};
+
+// RAII bracket: records an event pair around one phase when profiling is on
+struct PhaseTimer {
+  Domain*     d;
+  int         phase;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  PhaseTimer(Domain* dd, int ph) : d(dd), phase(ph)
+  {
+    if (!d->profiling) return;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, d->stream);
+  }
+  ~PhaseTimer()
+  {
+    if (!e0) return;
+    cudaEventRecord(e1, d->stream);
+    d->pending[phase].push_back({e0, e1});
+  }
+};
+
+
+// peer.cu
+PeerTabs peer_tabs(const Domain* d);
+void     peer_destroy(Domain* d);
+int      peer_alloc_species(Domain* d, SpeciesDev& s);
+int      peer_exchange_halo(Domain* d, int mode);       // pack -> NCCL send/recv (no-op without peers)
+const double* peer_recvbuf(const Domain* d);
+int      peer_migrate(Domain* d);                       // the whole migrate + sort phase with peers
+int      do_sort_species(Domain* d, SpeciesDev& s);
+} // namespace nixb200

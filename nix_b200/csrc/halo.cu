@@ -18,6 +18,8 @@
 // per-chunk API.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace nixb200
 {
 namespace
@@ -31,8 +33,36 @@ __device__ __forceinline__ size_t cell_off(const Geo& g, int ch, int iz, int iy,
   return (((size_t)ch * g.M[0] + iz) * g.M[1] + iy) * g.M[2] + ix;
 }
 
-// ---- same-device exchange ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __restrict__ cg, double* uf)
+// slab of direction index e (0/1/2) along axis a: first array index and width (chunk.cpp:171-207)
+__device__ __forceinline__ void slab_bounds(const Geo& g, int a, int e, bool recv, int& lo, int& n)
+{
+  const int Lb = g.nb, Ub = g.nb + g.N[a] - 1;
+  if (e == 1) {
+    lo = Lb;
+    n  = g.N[a];
+  } else if (recv) {
+    lo = (e == 0) ? Lb - g.nb : Ub + 1;
+    n  = g.nb;
+  } else {
+    lo = (e == 0) ? Lb : Ub - g.nb + 1;
+    n  = g.nb;
+  }
+}
+
+// position of array cell i inside the (row-major z,y,x) slab of slot `slot`
+__device__ __forceinline__ size_t slab_index(const Geo& g, int slot, bool recv, const int* i)
+{
+  int lo[3], n[3];
+  slab_bounds(g, 0, slot / 9, recv, lo[0], n[0]);
+  slab_bounds(g, 1, (slot / 3) % 3, recv, lo[1], n[1]);
+  slab_bounds(g, 2, slot % 3, recv, lo[2], n[2]);
+  return ((size_t)(i[0] - lo[0]) * n[1] + (i[1] - lo[1])) * n[2] + (i[2] - lo[2]);
+}
+
+// ---- exchange: same-device neighbours are read in place, neighbours on other ranks from the
+//      peer-major receive buffer (peer.cu) ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __restrict__ cg, double* uf, PeerTabs pt,
+                                                    const double* __restrict__ recvbuf)
 {
   const int ch    = blockIdx.y;
   const int ncell = g.M[0] * g.M[1] * g.M[2];
@@ -52,8 +82,14 @@ __global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __res
     int slot = 9 * e[0] + 3 * e[1] + e[2];
     if (slot == 13) continue;
     int nb = cg[ch].nbr[slot];
-    if (nb < 0) continue;
-    const double2* src = reinterpret_cast<const double2*>(uf + cell_off(g, nb, s[0], s[1], s[2]) * 6);
+    const double2* src;
+    if (nb >= 0) {
+      src = reinterpret_cast<const double2*>(uf + cell_off(g, nb, s[0], s[1], s[2]) * 6);
+    } else {
+      int j = (pt.recv_slot != nullptr) ? pt.recv_slot[ch * 27 + slot] : -1;
+      if (j < 0) continue;
+      src = reinterpret_cast<const double2*>(recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, true, i)) * 6);
+    }
     double2*       dst = reinterpret_cast<double2*>(uf + cell_off(g, ch, iz, iy, ix) * 6);
     double2        a = src[0], b = src[1], c = src[2];
     dst[0] = a;
@@ -62,7 +98,8 @@ __global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __res
   }
 }
 
-__global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __restrict__ cg, double* uj)
+__global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __restrict__ cg, double* uj, PeerTabs pt,
+                                                      const double* __restrict__ recvbuf)
 {
   const int ch    = blockIdx.y;
   const int ncell = g.N[0] * g.N[1] * g.N[2];
@@ -96,8 +133,14 @@ __global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __r
       }
       if (!in) continue;
       int nb = cg[ch].nbr[slot];
-      if (nb < 0) continue;
-      const double2* src = reinterpret_cast<const double2*>(uj + cell_off(g, nb, s[0], s[1], s[2]) * 4);
+      const double2* src;
+      if (nb >= 0) {
+        src = reinterpret_cast<const double2*>(uj + cell_off(g, nb, s[0], s[1], s[2]) * 4);
+      } else {
+        int j = (pt.recv_slot != nullptr) ? pt.recv_slot[ch * 27 + slot] : -1;
+        if (j < 0) continue;
+        src = reinterpret_cast<const double2*>(recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, false, i)) * 4);
+      }
       double2        a = src[0], b = src[1];
       // std::plus(buffer, cell)  xtensor_halo3d.hpp:125
       v0.x = __dadd_rn(a.x, v0.x);
@@ -110,22 +153,29 @@ __global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __r
   }
 }
 
-// ---- buffer (MpiBuffer layout) pack / unpack of one chunk ----------------------------------------
-__device__ __forceinline__ void slab_bounds(const Geo& g, int a, int e, bool recv, int& lo, int& n)
+// every slab bound for another rank -> the peer-major send buffer.  Field: SEND slabs (interior);
+// current: RECV slabs (ghost, where the deposit spilled).  blockIdx.y = send entry.
+__global__ void __launch_bounds__(256) k_peer_pack(Geo g, int ncomp, bool recv_slab, const double* __restrict__ data,
+                                                   const PeerEntry* __restrict__ ent, double* __restrict__ buf)
 {
-  const int Lb = g.nb, Ub = g.nb + g.N[a] - 1;
-  if (e == 1) {
-    lo = Lb;
-    n  = g.N[a];
-  } else if (recv) {
-    lo = (e == 0) ? Lb - g.nb : Ub + 1;
-    n  = g.nb;
-  } else {
-    lo = (e == 0) ? Lb : Ub - g.nb + 1;
-    n  = g.nb;
+  const PeerEntry en = ent[blockIdx.y];
+  int             lo[3], n[3];
+  slab_bounds(g, 0, en.dir / 9, recv_slab, lo[0], n[0]);
+  slab_bounds(g, 1, (en.dir / 3) % 3, recv_slab, lo[1], n[1]);
+  slab_bounds(g, 2, en.dir % 3, recv_slab, lo[2], n[2]);
+  const int total = en.cells * ncomp;
+  double*   dst   = buf + (size_t)en.celloff * ncomp;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    int c  = t % ncomp;
+    int r  = t / ncomp;
+    int ix = r % n[2] + lo[2];
+    int iy = (r / n[2]) % n[1] + lo[1];
+    int iz = r / (n[2] * n[1]) + lo[0];
+    dst[t] = data[cell_off(g, en.k, iz, iy, ix) * ncomp + c];
   }
 }
 
+// ---- buffer (MpiBuffer layout, chunk.cpp:257-286) pack / unpack of ONE chunk: the drop-in per-chunk API
 // pack: field packs the SEND slabs (interior), current packs the RECV slabs (ghost)
 __global__ void __launch_bounds__(256) k_halo_pack(Geo g, int ch, int ncomp, bool recv_slab,
                                                    const double* __restrict__ data, SlotTable tab,
@@ -223,20 +273,34 @@ SlotTable make_table(const Geo& g, int ncomp)
 }
 } // namespace
 
-int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, cudaStream_t st)
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, const PeerTabs& pt, const double* recvbuf,
+                      cudaStream_t st)
 {
   int  ncell = g.M[0] * g.M[1] * g.M[2];
   dim3 grid((ncell + 255) / 256, g.nchunk);
-  k_halo_field<<<grid, 256, 0, st>>>(g, cg, uf);
+  k_halo_field<<<grid, 256, 0, st>>>(g, cg, uf, pt, recvbuf);
   NIX_LAUNCHED();
   return 0;
 }
 
-int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, cudaStream_t st)
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, const PeerTabs& pt, const double* recvbuf,
+                        cudaStream_t st)
 {
   int  ncell = g.N[0] * g.N[1] * g.N[2];
   dim3 grid((ncell + 255) / 256, g.nchunk);
-  k_halo_current<<<grid, 256, 0, st>>>(g, cg, uj);
+  k_halo_current<<<grid, 256, 0, st>>>(g, cg, uj, pt, recvbuf);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_peer_pack(const Geo& g, int mode, const double* data, const PeerTabs& pt, double* sendbuf,
+                     cudaStream_t st)
+{
+  if (pt.nsend == 0) return 0;
+  const int ncomp = (mode == NIXB200_MODE_FIELD) ? 6 : 4;
+  int       big   = g.nb * std::max(g.N[0], std::max(g.N[1], g.N[2])) * std::max(g.N[1], g.N[2]) * ncomp;
+  dim3      grid(std::min(8, (big + 255) / 256), pt.nsend);
+  k_peer_pack<<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, data, pt.send_ent, sendbuf);
   NIX_LAUNCHED();
   return 0;
 }

@@ -124,15 +124,23 @@ __global__ void __launch_bounds__(128) k_mig_scan(Geo g, SpeciesDev sp)
 // (iz,iy,ix) order, xtensor_halo3d.hpp:440-461,507-524).  The message buffer is DESTINATION-major:
 // the particles chunk B receives sit in the order B appends them, so that the order of message
 // slots inside a chunk equals the order of the pre-sort indices (what the stable rank needs).
-__global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
+__global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt)
 {
+  // received from another rank: count table of this step, rcnt[] behind spoff[nsend+1] | rpoff[nrecv+1]
+  const int32_t* rcnt = (pt.recv_slot != nullptr) ? sp.ptab + (pt.nsend + 1) + (pt.nrecv + 1) : nullptr;
   __shared__ int s_part[1024];
   const int      tid = threadIdx.x;
   const int      per = (g.nchunk + blockDim.x - 1) / blockDim.x;
   const int      b = tid * per, e = min(g.nchunk, b + per);
   auto recv_cnt = [&](int ch, int s) {
     int nb = cg[ch].nbr[s];
-    return (s != 13 && nb >= 0) ? sp.sendcnt[nb * 27 + (26 - s)] : 0;
+    if (s == 13) return 0;
+    if (nb >= 0) return sp.sendcnt[nb * 27 + (26 - s)];
+    if (rcnt != nullptr) {
+      int j = pt.recv_slot[ch * 27 + s];
+      if (j >= 0) return rcnt[j];
+    }
+    return 0;
   };
   int sum = 0;
   for (int ch = b; ch < e; ch++)
@@ -162,9 +170,37 @@ __global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev
   }
 }
 
+// a migrating particle arrives in chunk B as its pre-sort particle ipB: periodic wrap, bin, count,
+// message slot m (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
+__device__ __forceinline__ void deliver(const Geo& g, const ChunkGeo* __restrict__ cg, const SpeciesDev& sp, int B,
+                                        int m, int ipB, double* v)
+{
+  // xtensor_particle.hpp:371-375   x += (x < X1)*L - (x >= X2)*L   (z,y,x stored as v[2],v[1],v[0])
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    double p  = v[2 - a];
+    double L  = g.glen[a];
+    double s1 = (p < g.glo[a]) ? L : 0.0;
+    double s2 = (p >= g.ghi[a]) ? L : 0.0;
+    v[2 - a]  = __dadd_rn(p, __dsub_rn(s1, s2));
+  }
+  const ChunkGeo& c    = cg[B];
+  int             lane = ipB & (LANES - 1);
+  int             key  = -1;
+  if (dir_code(c, v[0], v[1], v[2]) == 13) {
+    key = (B * g.ncell + cell_index(g, c, v[0], v[1], v[2])) * LANES + lane;
+    atomicAdd(&sp.hist[key], 1);
+  } else {
+    atomicAdd(&sp.oob[B * LANES + lane], 1);
+  }
+#pragma unroll
+  for (int k = 0; k < NC; k++) sp.msg[soa(k, sp.lcap, m)] = v[k];
+  sp.msgkey[m] = key;
+}
+
 // one thread per leaver: destination chunk, pre-sort index there, periodic wrap, count
 // (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
-__global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, int* err)
+__global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt, int* err)
 {
   const int nl = min(*sp.nleave, (int)sp.lcap);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nl; j += gridDim.x * blockDim.x) {
@@ -173,8 +209,21 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
     int  A    = r.y;
     int  dir  = r.w & 31;
     int  B    = cg[A].nbr[dir];
-    if (B < 0) continue; // no neighbour / other rank
     int idx   = sp.slabcnt[(size_t)A * g.slaboff[27] + r.z] + (r.w >> 5);
+    if (B < 0) {
+      // neighbour on another rank: raw payload (the receiver wraps and bins it) at the slot the
+      // reference's pack order gives it, peer-major
+      int js = (pt.send_slot != nullptr) ? pt.send_slot[A * 27 + dir] : -1;
+      if (js < 0) continue; // no neighbour
+      size_t pos = (size_t)sp.ptab[js] + idx;
+      if (pos >= (size_t)sp.lcap) {
+        atomicOr(err, NIXB200_ERR_CAPACITY);
+        continue;
+      }
+#pragma unroll
+      for (int k = 0; k < NC; k++) sp.paysend[pos * NC + k] = sp.xu[soa(k, sp.cap, i)];
+      continue;
+    }
     int m     = sp.msgoff[B * 27 + (26 - dir)] + idx;
     int ipB   = sp.recvoff[B * 27 + (26 - dir)] + idx;
     if (m >= sp.lcap) {
@@ -184,28 +233,43 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
     double v[NC];
 #pragma unroll
     for (int k = 0; k < NC; k++) v[k] = sp.xu[soa(k, sp.cap, i)];
-    // xtensor_particle.hpp:371-375   x += (x < X1)*L - (x >= X2)*L   (z,y,x stored as v[2],v[1],v[0])
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      double p  = v[2 - a];
-      double L  = g.glen[a];
-      double s1 = (p < g.glo[a]) ? L : 0.0;
-      double s2 = (p >= g.ghi[a]) ? L : 0.0;
-      v[2 - a]  = __dadd_rn(p, __dsub_rn(s1, s2));
-    }
-    const ChunkGeo& c    = cg[B];
-    int             lane = ipB & (LANES - 1);
-    int             key  = -1;
-    if (dir_code(c, v[0], v[1], v[2]) == 13) {
-      key = (B * g.ncell + cell_index(g, c, v[0], v[1], v[2])) * LANES + lane;
-      atomicAdd(&sp.hist[key], 1);
-    } else {
-      atomicAdd(&sp.oob[B * LANES + lane], 1);
-    }
-#pragma unroll
-    for (int k = 0; k < NC; k++) sp.msg[soa(k, sp.lcap, m)] = v[k];
-    sp.msgkey[m] = key;
+    deliver(g, cg, sp, B, m, ipB, v);
   }
+}
+
+// particles received from other ranks: one thread per particle of the peer-major payload
+__global__ void k_mig_recv(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt, int ntot, int* err)
+{
+  const int32_t* rpoff = sp.ptab + (pt.nsend + 1);
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += gridDim.x * blockDim.x) {
+    int lo = 0, hi = pt.nrecv; // rpoff[lo] <= t < rpoff[hi]
+    while (hi - lo > 1) {
+      int mid = (lo + hi) >> 1;
+      if (rpoff[mid] <= t) lo = mid;
+      else hi = mid;
+    }
+    const PeerEntry en  = pt.recv_ent[lo];
+    const int       idx = t - rpoff[lo];
+    const int       m   = sp.msgoff[en.k * 27 + en.dir] + idx;
+    const int       ipB = sp.recvoff[en.k * 27 + en.dir] + idx;
+    if (m >= sp.lcap) {
+      atomicOr(err, NIXB200_ERR_CAPACITY);
+      continue;
+    }
+    double v[NC];
+#pragma unroll
+    for (int k = 0; k < NC; k++) v[k] = sp.payrecv[(size_t)t * NC + k];
+    deliver(g, cg, sp, en.k, m, ipB, v);
+  }
+}
+
+// particle counts of the slabs bound for other ranks -> the count message of each peer
+__global__ void k_peer_counts(SpeciesDev sp, PeerTabs pt, int is, int32_t* __restrict__ out)
+{
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= pt.nsend) return;
+  const PeerEntry en = pt.send_ent[j];
+  out[en.cidx + is * en.cstride] = sp.sendcnt[en.k * 27 + en.dir];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,13 +491,38 @@ int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err
 }
 
 // after push_deposit (which filled key/hist for residents and the leaver records)
-int launch_migrate(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st)
+int launch_mig_scan(const Geo& g, SpeciesDev& sp, cudaStream_t st)
 {
   k_mig_scan<<<g.nchunk * 27, 128, 0, st>>>(g, sp);
   NIX_LAUNCHED();
-  k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp);
+  return 0;
+}
+
+int launch_peer_counts(const Geo& g, const SpeciesDev& sp, const PeerTabs& pt, int is, int32_t* cnt_send,
+                       cudaStream_t st)
+{
+  (void)g;
+  if (pt.nsend == 0) return 0;
+  k_peer_counts<<<(pt.nsend + 127) / 128, 128, 0, st>>>(sp, pt, is, cnt_send);
   NIX_LAUNCHED();
-  k_mig_key<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, err);
+  return 0;
+}
+
+int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int* err,
+                     cudaStream_t st)
+{
+  k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp, pt);
+  NIX_LAUNCHED();
+  k_mig_key<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, err);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int nrecv_particles,
+                    int* err, cudaStream_t st)
+{
+  if (nrecv_particles <= 0) return 0;
+  k_mig_recv<<<grid_for(nrecv_particles, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, nrecv_particles, err);
   NIX_LAUNCHED();
   return 0;
 }

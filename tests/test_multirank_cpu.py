@@ -1,0 +1,141 @@
+"""Host logic of the multi-rank path on CPU (no GPU): the plan of csrc/peer.cu (nix_b200.core.Plan) and
+the rank partition, exercised with world_size-2/3 `gloo` process groups.  Data plane = the CPU
+oracle split over ranks (tests/multirank_oracle.py); the result must equal the single-process
+oracle domain bit for bit, for every chunk a rank owns."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from nix_b200 import core  # noqa: E402
+from nix_b200.synth import Problem  # noqa: E402
+
+
+def _collect(q, procs, timeout):
+    """One result per rank; a rank that dies or hangs (e.g. inside a collective its peer never
+    entered) is reported and every process is reaped."""
+    import queue
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=timeout))
+    except queue.Empty:
+        got = {r[0] for r in res}
+        res += [(i, "fail: no result (crashed or hung)") + (0,) * (len(res[0]) - 2 if res else 0)
+                for i in range(len(procs)) if i not in got]
+    finally:
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
+    return res
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_uniform_boundary_matches_balancer_known_answer():
+    # unittest/test_balancer.cpp:41-44: uniform load over 8 ranks, 160 chunks -> boundary[i] == 20 i
+    assert list(core.uniform_boundary(160, 8)) == [20 * i for i in range(9)]
+
+
+@pytest.mark.parametrize("cdims,nrank", [((2, 2, 4), 2), ((3, 2, 2), 3), ((4, 4, 4), 8), ((2, 1, 2), 2), ((1, 1, 2), 2)])
+def test_plan_pairs_up(cdims, nrank):
+    """What rank r sends to rank p is, entry by entry, what p expects from r; every slab whose
+    neighbour lives elsewhere is listed exactly once."""
+    prob = Problem(cdims, (8, 6, 4), 2, ppc=1)
+    nchunk = int(np.prod(cdims))
+    bd = core.uniform_boundary(nchunk, nrank)
+    plans = [core.Plan(cdims, prob.dims, prob.nb, prob.coord, bd, r) for r in range(nrank)]
+    owner = lambda i: int(np.searchsorted(bd, i, side="right") - 1)  # noqa: E731  ChunkMap::get_rank
+    grid2id = {tuple(int(v) for v in c): i for i, c in enumerate(prob.coord)}
+    for r, pl in enumerate(plans):
+        ranks = [p["rank"] for p in pl.peers]
+        assert ranks == sorted(set(ranks)) and r not in ranks
+        expect = set()
+        for i in range(bd[r], bd[r + 1]):
+            for d in range(27):
+                if d == 13:
+                    continue
+                e = (d // 9 - 1, (d // 3) % 3 - 1, d % 3 - 1)
+                nid = grid2id[tuple((int(prob.coord[i][a]) + e[a]) % cdims[a] for a in range(3))]
+                if owner(nid) != r:
+                    expect.add((owner(nid), i, d))
+        got = {(p["rank"], i, d) for p in pl.peers for (i, d, _) in p["send"]}
+        assert got == expect
+        assert {(p["rank"], i, d) for p in pl.peers for (i, d, _) in p["recv"]} == expect
+        for p in pl.peers:
+            back = next(q for q in plans[p["rank"]].peers if q["rank"] == r)
+            assert len(p["send"]) == len(back["recv"])
+            for (i, d, n), (j, e, m) in zip(p["send"], back["recv"]):
+                assert e == 26 - d and n == m
+                dd = (d // 9 - 1, (d // 3) % 3 - 1, d % 3 - 1)
+                assert grid2id[tuple((int(prob.coord[i][a]) + dd[a]) % cdims[a] for a in range(3))] == j
+
+
+def test_plan_rejects_bad_boundary():
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=1)
+    with pytest.raises(core.NixB200Error):
+        core.Plan(prob.cdims, prob.dims, prob.nb, prob.coord, [0, 4, 7], 0)
+    with pytest.raises(core.NixB200Error):
+        core.Plan(prob.cdims, prob.dims, prob.nb, prob.coord, [0, 5, 3, 8], 1)
+
+
+def _worker(rank, world, port, cdims, dims, order, steps, q):
+    try:
+        import torch.distributed as dist
+        from oracle import nixoracle as no
+        from helpers import bits, oracle_domain
+        from multirank_oracle import RankOracle
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        lib = no.load("port")
+        prob = Problem(cdims, dims, order, ppc=6, seed=77, vth=(0.35, 0.08))
+        bd = core.uniform_boundary(prob.nchunk, world)
+        ro = RankOracle(lib, prob, bd, rank)
+        ro.load()
+        ro.exchange(no.MODE_FIELD)
+        ro.sort_only()
+        full = oracle_domain(lib, prob)  # the whole box in this process: the reference result
+        moved = 0
+        for _ in range(steps):
+            ro.step(0.5, 1.0)
+            full.step(0.5, 1.0)
+        for i in ro.ids:
+            a, b = ro.chunks[i], full.chunks[i]
+            assert np.array_equal(a.uf, b.uf), f"rank {rank} chunk {i}: E/B differ"
+            assert np.array_equal(bits(a.uj), bits(b.uj)), f"rank {rank} chunk {i}: J differs"
+            for s in range(prob.ns):
+                pa, pb = a.particles(s), b.particles(s)
+                assert pa.shape == pb.shape and np.array_equal(bits(pa), bits(pb)), f"rank {rank} chunk {i} sp {s}"
+                moved += int((pa[:, 6].view(np.int64) >> 32 & 0xFFFFFF != i).sum())
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok", moved))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: " + "".join(traceback.format_exception(exc)), 0))
+
+
+@pytest.mark.parametrize("world,cdims,dims,order", [(2, (2, 2, 2), (8, 8, 8), 2), (2, (1, 2, 3), (6, 8, 10), 1),
+                                                    (3, (3, 2, 2), (8, 8, 8), 3)])
+def test_rank_split_oracle_equals_single_process(oracle_port, world, cdims, dims, order):
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, cdims, dims, order, 3, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = _collect(q, procs, 240)
+    for rank, status, _ in res:
+        assert status == "ok", f"rank {rank}: {status}"
+    assert sum(m for _, _, m in res) > 0, "no particle changed chunk: the migration path was not exercised"

@@ -1,0 +1,149 @@
+"""Multi-rank GPU parity: chunks partitioned over ranks along the id order, J / E/B halo and particle
+migration across ranks over NCCL (csrc/peer.cu), against the single-process CPU oracle of the whole
+box.  Strict mode => particles, counts and E/B bit-exact; J <= 1e-12 of its maximum.
+
+The 2-rank tests need 2 GPUs (`gpurun --gpus 2`); on a 1-GPU box they skip and only the
+single-rank pass through the multi-rank code path runs."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from nix_b200.synth import Problem  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+JTOL = 1e-12
+
+
+def _collect(q, procs, timeout):
+    """One result per rank; a rank that dies or hangs (e.g. inside a collective its peer never
+    entered) is reported and every process is reaped."""
+    import queue
+    res = []
+    try:
+        for _ in procs:
+            res.append(q.get(timeout=timeout))
+    except queue.Empty:
+        got = {r[0] for r in res}
+        res += [(i, "fail: no result (crashed or hung)") + (0,) * (len(res[0]) - 2 if res else 0)
+                for i in range(len(procs)) if i not in got]
+    finally:
+        for p in procs:
+            p.join(timeout=10)
+            if p.is_alive():
+                p.terminate()
+    return res
+
+
+def free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _compare(rank, prob, od, gd, ids, what):
+    from helpers import bits, ref_pcount_before_sort
+    for k, i in enumerate(ids):
+        c = od.chunks[i]
+        uj = gd.get_current(k)
+        scale = np.abs(c.uj).max() or 1.0
+        assert np.abs(uj - c.uj).max() / scale < JTOL, f"{what} rank {rank} chunk {i}: J"
+        assert np.array_equal(gd.get_field(k), c.uf), f"{what} rank {rank} chunk {i}: E/B"
+        for s in range(prob.ns):
+            ref, got = c.particles(s), gd.get_particles(k, s)
+            assert got.shape == ref.shape, f"{what} rank {rank} chunk {i} sp {s}: Np {got.shape[0]} != {ref.shape[0]}"
+            assert np.array_equal(bits(got), bits(ref)), f"{what} rank {rank} chunk {i} sp {s}: particles"
+            assert np.array_equal(gd.get_pindex(k, s), c.pindex(s)), f"{what} rank {rank} chunk {i} sp {s}: pindex"
+            assert np.array_equal(gd.get_pcount(k, s), ref_pcount_before_sort(c, s))
+
+
+def _load(gd, prob, ids):
+    for k, i in enumerate(ids):
+        gd.set_field(k, prob.field(i))
+    gd.exchange_field()
+    for s in range(prob.ns):
+        gd.set_particles(s, [prob.particles(i, s) for i in ids])
+    gd.sort()
+
+
+def test_single_rank_through_the_multirank_path(oracle_port, gpu_lib):
+    """nrank = 1: no peers, but the step runs through peer_migrate (count tables, host sync)."""
+    from nix_b200 import core
+    from helpers import oracle_domain
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=8, seed=91, vth=(0.35, 0.08))
+    od = oracle_domain(oracle_port, prob)
+    gd = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, strict_fp=True)
+    gd.set_ranks([0, prob.nchunk], 0)
+    _load(gd, prob, list(range(prob.nchunk)))
+    for step in range(3):
+        od.step(0.5, 1.0)
+        gd.step(0.5)
+        assert gd.check() == 0
+        _compare(0, prob, od, gd, list(range(prob.nchunk)), f"step {step}")
+    assert gd.peer_traffic() == dict(halo_cells_sent=0, particles_sent=0, particles_received=0)
+    gd.close()
+
+
+def _worker(rank, world, port, cdims, dims, order, steps, q):
+    try:
+        import torch
+        import torch.distributed as dist
+        from nix_b200 import core
+        from oracle import nixoracle as no
+        from helpers import oracle_domain
+        torch.cuda.set_device(rank)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        prob = Problem(cdims, dims, order, ppc=8, seed=93 + order, vth=(0.35, 0.08))
+        bd = core.uniform_boundary(prob.nchunk, world)
+        ids = list(range(int(bd[rank]), int(bd[rank + 1])))
+        gd = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord,
+                         id_range=(ids[0], ids[-1] + 1), device=rank, strict_fp=True)
+        gd.set_ranks(bd, rank)
+        gd.comm_init_torch()
+        _load(gd, prob, ids)
+        od = oracle_domain(no.load("port"), prob)  # whole box on the CPU of every rank
+        _compare(rank, prob, od, gd, ids, "load")
+        sent = 0
+        for step in range(steps):
+            od.step(0.5, 1.0)
+            gd.step(0.5)
+            assert gd.check() == 0, f"rank {rank}: device error bits"
+            _compare(rank, prob, od, gd, ids, f"step {step}")
+            tr = gd.peer_traffic()
+            sent += tr["particles_sent"]
+            assert tr["halo_cells_sent"] > 0
+        tot = torch.tensor([gd.total_particles(), sent], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot[0]) == od.total_particles()
+        assert int(tot[1]) > 0, "no particle crossed a rank boundary"
+        gd.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: " + "".join(traceback.format_exception(exc))))
+
+
+@pytest.mark.parametrize("cdims,dims,order", [((2, 2, 2), (8, 8, 8), 2), ((1, 2, 3), (6, 8, 10), 1),
+                                              ((2, 2, 4), (8, 8, 8), 3), ((1, 1, 2), (8, 8, 8), 2)])
+def test_two_ranks_equal_single_process_oracle(oracle_port, gpu_lib, cdims, dims, order):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, cdims, dims, order, 3, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = _collect(q, procs, 240)
+    for rank, status in res:
+        assert status == "ok", f"rank {rank}: {status}"
