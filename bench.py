@@ -37,10 +37,32 @@ def workload(args):
     return dict(cdims=cd, dims=(16, 16, 16), order=2, ppc=64, ns=2)
 
 
-def make_problem(w, seed=2024, cdims=None):
+def make_problem(w, seed=2024, cdims=None, coord=None):
     from nix_b200.synth import Problem
     return Problem(cdims or w["cdims"], w["dims"], w["order"], ppc=w["ppc"], ns=w["ns"], seed=seed,
-                   vth=(0.1, 0.02))
+                   vth=(0.1, 0.02), coord=coord)
+
+
+def global_box(cd, world):
+    """Weak scaling: the per-GPU block of cd chunks is repeated world times (z first, then y, then x),
+    and the chunk order visits block after block (snake order inside a block), so that the uniform
+    rank boundaries of Balancer::assign_initial give every rank one compact block."""
+    from nix_b200.synth import gilbert_like_order
+    rep = [1, 1, 1]
+    a, n = 0, world
+    while n > 1:
+        if n % 2:
+            raise SystemExit("bench.py: --gpus must be a power of two")
+        rep[a % 3] *= 2
+        n //= 2
+        a += 1
+    inner = gilbert_like_order(cd)
+    coord = []
+    for bz in range(rep[0]):
+        for by in range(rep[1]):
+            for bx in range(rep[2]):
+                coord.append(inner + np.array([bz * cd[0], by * cd[1], bx * cd[2]], dtype=np.int32))
+    return tuple(cd[i] * rep[i] for i in range(3)), np.concatenate(coord).astype(np.int32)
 
 
 class ClockSampler:
@@ -179,10 +201,17 @@ def run_gpu(args):
     from nix_b200 import core
 
     w = workload(args)
-    prob = make_problem(w, seed=2024 + rank)
+    gcd, gcoord = global_box(w["cdims"], world)
+    prob = make_problem(w, seed=2024, cdims=gcd, coord=gcoord)
+    bd = core.uniform_boundary(prob.nchunk, world)
+    ids = list(range(int(bd[rank]), int(bd[rank + 1])))
     stream = torch.cuda.current_stream()
     dom = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, device=local,
-                      strict_fp=bool(args.strict), capacity_factor=1.15, stream=stream.cuda_stream)
+                      id_range=(ids[0], ids[-1] + 1), strict_fp=bool(args.strict), capacity_factor=1.15,
+                      stream=stream.cuda_stream)
+    if world > 1:
+        dom.set_ranks(bd, rank)
+        dom.comm_init_torch()
     nchunk = dom.nchunk
     cells = int(np.prod(dom.M))
     # pinned host mirrors of the grid arrays (the host-side field solver's view)
@@ -190,7 +219,7 @@ def run_gpu(args):
     uj_host = torch.empty((nchunk, cells, 4), dtype=torch.float64, pin_memory=True)
     ufn = uf_host.numpy()
     for k in range(nchunk):
-        ufn[k] = prob.field(k).reshape(cells, 6)
+        ufn[k] = prob.field(ids[k]).reshape(cells, 6)
     dom.field_upload_async(core.FIELD_UF, uf_host.data_ptr())
     dom.exchange_field()
     dom.field_download_async(core.FIELD_UF, uf_host.data_ptr())  # ghosts consistent on the host too
@@ -199,7 +228,7 @@ def run_gpu(args):
     for s in range(prob.ns):
         flat = np.empty((nchunk * npc, 7), dtype=np.float64)
         for k in range(nchunk):
-            flat[k * npc:(k + 1) * npc] = prob.particles(k, s)
+            flat[k * npc:(k + 1) * npc] = prob.particles(ids[k], s)
         dom.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
         del flat
     dom.sort()
@@ -258,9 +287,11 @@ def run_gpu(args):
     if err:
         raise SystemExit(f"bench.py: device error bits {err} during the timed region")
     ntot_end = dom.total_particles()
+    traffic = dom.peer_traffic()
 
     t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
-    n = torch.tensor([float(ntot)], dtype=torch.float64, device="cuda")
+    n = torch.tensor([float(ntot), float(ntot_end), float(traffic["particles_sent"]),
+                      float(traffic["halo_cells_sent"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
@@ -293,10 +324,15 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": "128^3 cells per GPU, 128 ppc (electrons+ions, 64 each), order 2, fp64, periodic "
-                            "thermal plasma, %dx%dx%d chunks of 16^3 per GPU" % prob.cdims,
-                "particles_per_gpu": ntot, "particles_end": ntot_end, "fp_contract": "off" if args.strict else "fma",
+                            "thermal plasma, %dx%dx%d chunks of 16^3 per GPU" % tuple(w["cdims"]),
+                "particles_per_gpu": ntot, "particles_end_all_ranks": int(n[1]),
+                "fp_contract": "off" if args.strict else "fma",
                 "l2": "inputs (%.1f GB of particles per GPU) larger than L2" % (ntot * 56 / 1e9),
-                "multi_gpu": "independent periodic box per rank" if world > 1 else "single GPU",
+                "multi_gpu": ("one periodic box of %dx%dx%d chunks partitioned over %d ranks along the chunk order "
+                              "(one compact block per rank); J / E/B halo and particle migration between ranks "
+                              "over NCCL send/recv, one message per peer and mode; last step: %d particles and "
+                              "%d ghost cells per exchange crossed rank boundaries"
+                              % (prob.cdims + (world, int(n[2]), int(n[3])))) if world > 1 else "single GPU",
             },
             "clocks": clocks,
             "e2e": {"value": nglobal * args.steps / (ms_e2e * 1e-3), "unit": "particle-updates/s",
