@@ -1,0 +1,349 @@
+// nixb200_host.hpp -- the C++ host side of the drop-in: what a nix application instantiates so that
+// its per-chunk PIC step runs on B200 through libnixb200.so (include/nixb200.h).
+//
+// It keeps the reference's own interfaces (north star: "the C++ host keeps the Chunk / ChunkMap /
+// Application / Balancer interfaces and the SFC chunk ordering"):
+//
+//   GpuChunk       : nix::Chunk                  chunk.hpp:100-432   (factory product, pack/unpack, load)
+//   GpuInterface   : nix::Application::Interface application.hpp:23-66 (create_chunk -> GpuChunk)
+//   GpuApplication : nix::Application            application.hpp:69-396 (push() override, rebalance hook)
+//
+// and calls ONLY the C ABI.  The reference drives every chunk separately (26 MPI messages per chunk
+// and mode); here all chunks of the rank live in ONE device-resident nixb200_domain and
+// Application::push() is a single nixb200_domain_step().  A GpuChunk is therefore a thin handle
+// (domain, local index) plus host staging in the reference's own containers (xtensor uf/uj,
+// XtensorParticle), which is what Chunk::pack / unpack (checkpoints, Balancer::sendrecv_chunk) and the
+// diagnostics read and write -- byte-compatible with the reference's formats because the
+// reference's own pack() writes them.
+//
+// Compile with the reference on the include path:  -I<nix> -I<nix>/thirdparty -I<repo>/include
+#pragma once
+
+#include "application.hpp"
+#include "chunk.hpp"
+#include "chunkmap.hpp"
+#include "diag.hpp"
+#include "xtensor_particle.hpp"
+
+#include "nixb200.h"
+
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace nixb200host
+{
+using nix::float64;
+using nix::json;
+
+/// ERROR-and-carry-on is the reference's convention on the hot path; set-up failures
+/// are fatal there (MPI_Abort), here they throw.
+inline void check(int rc, const char* what)
+{
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + nixb200_last_error());
+}
+
+struct SpeciesSpec {
+  float64 q, m;
+};
+
+/// RAII owner of one nixb200_domain = the chunks [id_begin, id_end) of this rank on one GPU
+class GpuDomain
+{
+public:
+  nixb200_domain* h = nullptr;
+  int             id_begin = 0, id_end = 0;
+
+  GpuDomain(nix::ChunkMap& chunkmap, const int cdims[3], const int dims[3], int nb, int order,
+            const std::vector<SpeciesSpec>& species, float64 delz, float64 dely, float64 delx, float64 cc,
+            int id_begin_, int id_end_, int device, bool strict_fp = false, double capacity_factor = 1.25)
+      : id_begin(id_begin_), id_end(id_end_)
+  {
+    const int        ncid = cdims[0] * cdims[1] * cdims[2];
+    std::vector<int> coord(3 * ncid);
+    for (int id = 0; id < ncid; id++) { // ChunkMap::get_coordinate = the Gilbert curve of sfc.cpp
+      auto [cz, cy, cx] = chunkmap.get_coordinate(id);
+      coord[3 * id + 0] = cz;
+      coord[3 * id + 1] = cy;
+      coord[3 * id + 2] = cx;
+    }
+    nixb200_domain_desc desc{};
+    for (int a = 0; a < 3; a++) {
+      desc.cdims[a] = cdims[a];
+      desc.dims[a]  = dims[a];
+    }
+    desc.nb              = nb;
+    desc.order           = order;
+    desc.ns              = (int)species.size();
+    desc.del[0]          = delz;
+    desc.del[1]          = dely;
+    desc.del[2]          = delx;
+    desc.cc              = cc;
+    desc.id_begin        = id_begin;
+    desc.id_end          = id_end;
+    desc.device          = device;
+    desc.strict_fp       = strict_fp ? 1 : 0;
+    desc.capacity_factor = capacity_factor;
+    std::vector<double> q, m;
+    for (auto& s : species) {
+      q.push_back(s.q);
+      m.push_back(s.m);
+    }
+    check(nixb200_domain_create(&desc, coord.data(), q.data(), m.data(), &h), "nixb200_domain_create");
+  }
+  GpuDomain(const GpuDomain&)            = delete;
+  GpuDomain& operator=(const GpuDomain&) = delete;
+  ~GpuDomain()
+  {
+    if (h) nixb200_domain_destroy(h);
+  }
+
+  /// several ranks: boundary = ChunkMap::get_rank_boundary(); id128 = the NCCL unique id every rank
+  /// received from rank 0 (MPI_Bcast of nixb200_comm_unique_id's 128 bytes)
+  void set_ranks(std::vector<int> boundary, int rank, const void* id128)
+  {
+    check(nixb200_domain_set_ranks(h, (int)boundary.size() - 1, boundary.data(), rank), "nixb200_domain_set_ranks");
+    if ((int)boundary.size() - 1 > 1) check(nixb200_domain_comm_init(h, id128), "nixb200_domain_comm_init");
+  }
+};
+
+/// Chunk whose fields and particles live in a GpuDomain.  Host staging uses the reference's own
+/// containers so that pack()/unpack() and diagnostics keep the reference's byte formats.
+class GpuChunk : public nix::Chunk
+{
+public:
+  using ParticlePtr = std::shared_ptr<nix::XtensorParticle>;
+
+  int                          order = 2;
+  xt::xtensor<float64, 4>      uf; ///< [Mz][My][Mx][6] host staging of E/B
+  xt::xtensor<float64, 4>      uj; ///< [Mz][My][Mx][4] host staging of rho/J
+  std::vector<ParticlePtr>     up; ///< host staging of the species (reference container)
+  std::shared_ptr<GpuDomain>   domain;
+  int                          local = -1; ///< index inside the domain
+  bool                         host_is_newer = true;
+
+  GpuChunk(nix::Dims3D dims, nix::Bool3D has_dim, int id = 0) : nix::Chunk(dims, has_dim, id)
+  {
+  }
+
+  int get_order() const // duck-typed by XtensorHaloParticle3D (xtensor_halo3d.hpp:545)
+  {
+    return order;
+  }
+
+  /// allocate the staging; the downstream application fills uf / up[is]->xu in its setup()
+  void allocate_staging(int order_, int nb, const std::vector<SpeciesSpec>& species, int np_required)
+  {
+    order = order_;
+    set_boundary_margin(nb);
+    size_t mz = dims[0] + 2 * nb, my = dims[1] + 2 * nb, mx = dims[2] + 2 * nb;
+    uf.resize({mz, my, mx, 6ul});
+    uj.resize({mz, my, mx, 4ul});
+    uf.fill(0);
+    uj.fill(0);
+    up.clear();
+    for (auto& s : species) {
+      auto p = std::make_shared<nix::XtensorParticle>(np_required, *this);
+      p->q   = s.q;
+      p->m   = s.m;
+      p->Np  = 0;
+      up.push_back(p);
+    }
+    load.assign(1, 0.0);
+  }
+
+  int64_t get_size_byte() const override
+  {
+    int64_t size = uf.size() * sizeof(float64) + uj.size() * sizeof(float64);
+    for (auto& p : up) size += p->get_size_byte();
+    return size;
+  }
+
+  /// device -> host staging (before pack, diagnostics, rebalance)
+  void sync_host()
+  {
+    if (!domain || local < 0 || host_is_newer) return;
+    check(nixb200_chunk_field_download(domain->h, local, NIXB200_FIELD_UF, uf.data()), "field_download");
+    check(nixb200_chunk_field_download(domain->h, local, NIXB200_FIELD_UJ, uj.data()), "field_download");
+    for (size_t is = 0; is < up.size(); is++) {
+      int64_t np = 0;
+      check(nixb200_chunk_get_particles(domain->h, local, (int)is, nullptr, 0, &np), "get_particles");
+      if (np > up[is]->Np_total - 1) up[is]->resize((int)np);
+      if (np > 0) check(nixb200_chunk_get_particles(domain->h, local, (int)is, up[is]->xu.data(), np, &np), "get_particles");
+      up[is]->Np = (int)np;
+      check(nixb200_chunk_get_pindex(domain->h, local, (int)is, up[is]->pindex.data()), "get_pindex");
+    }
+  }
+
+  // Chunk::pack / unpack (chunk.cpp:18-116): base header first, then this chunk's arrays in the
+  // reference's formats (XtensorParticle::pack, xtensor_particle.hpp:128-218)
+  int pack(void* buffer, int address) override
+  {
+    using nix::memcpy_count;
+    sync_host();
+    int ns = (int)up.size();
+    address = nix::Chunk::pack(buffer, address);
+    address += memcpy_count(buffer, &order, sizeof(int), address, 0);
+    address += memcpy_count(buffer, &ns, sizeof(int), address, 0);
+    address += memcpy_count(buffer, uf.data(), uf.size() * sizeof(float64), address, 0);
+    address += memcpy_count(buffer, uj.data(), uj.size() * sizeof(float64), address, 0);
+    for (auto& p : up) address = p->pack(buffer, address);
+    return address;
+  }
+
+  int unpack(void* buffer, int address) override
+  {
+    using nix::memcpy_count;
+    int ns = 0;
+    address = nix::Chunk::unpack(buffer, address);
+    address += memcpy_count(&order, buffer, sizeof(int), 0, address);
+    address += memcpy_count(&ns, buffer, sizeof(int), 0, address);
+    size_t mz = dims[0] + 2 * boundary_margin, my = dims[1] + 2 * boundary_margin, mx = dims[2] + 2 * boundary_margin;
+    uf.resize({mz, my, mx, 6ul});
+    uj.resize({mz, my, mx, 4ul});
+    address += memcpy_count(uf.data(), buffer, uf.size() * sizeof(float64), 0, address);
+    address += memcpy_count(uj.data(), buffer, uj.size() * sizeof(float64), 0, address);
+    up.resize(ns);
+    for (int is = 0; is < ns; is++) {
+      up[is]  = std::make_shared<nix::XtensorParticle>();
+      address = up[is]->unpack(buffer, address);
+    }
+    host_is_newer = true; // the next push() uploads it into the rank's domain
+    domain.reset();
+    local = -1;
+    return address;
+  }
+
+  void set_load_value(float64 v)
+  {
+    load.assign(1, v);
+  }
+
+  // the exchange of all chunk pairs happens inside nixb200_domain_step: the per-chunk hooks of the
+  // reference's main loop are satisfied trivially
+  void set_boundary_pack(int) override {}
+  void set_boundary_unpack(int) override {}
+  void set_boundary_begin(int) override {}
+  void set_boundary_end(int) override {}
+  bool set_boundary_probe(int, bool) override { return true; }
+};
+
+/// Application::Interface whose factory makes GpuChunks (application.hpp:45-48); used at set-up, on
+/// rebalance receive (balancer.hpp:216) and on checkpoint load (statehandler.hpp:297)
+class GpuInterface : public nix::Application::Interface
+{
+public:
+  PtrChunk create_chunk(nix::Dims3D dims, nix::Bool3D has_dim, int id) override
+  {
+    return std::make_unique<GpuChunk>(dims, has_dim, id);
+  }
+};
+
+/// Build (or rebuild) the rank's domain from its chunk vector and upload every chunk's staging.
+/// `chunks` are the rank-local chunks in ascending id order (ChunkVector keeps them sorted).
+template <typename ChunkVec>
+std::shared_ptr<GpuDomain> make_domain(ChunkVec& chunks, nix::ChunkMap& chunkmap, const int cdims[3], int nb, int order,
+                                       const std::vector<SpeciesSpec>& species, float64 cc, int device, bool strict_fp,
+                                       double capacity_factor = 1.25)
+{
+  if (chunks.size() == 0) return nullptr;
+  auto* first = static_cast<GpuChunk*>(chunks.front().get());
+  auto* last  = static_cast<GpuChunk*>(chunks.back().get());
+  std::vector<int> nd = first->get_dims();
+  int dims[3]         = {nd[0], nd[1], nd[2]};
+  auto dom = std::make_shared<GpuDomain>(chunkmap, cdims, dims, nb, order, species, first->get_delz(), first->get_dely(),
+                                         first->get_delx(), cc, first->get_id(), last->get_id() + 1, device, strict_fp,
+                                         capacity_factor);
+  const int ns = (int)species.size();
+  for (int k = 0; k < (int)chunks.size(); k++) {
+    auto* c = static_cast<GpuChunk*>(chunks[k].get());
+    if (c->get_id() != dom->id_begin + k) throw std::runtime_error("chunk ids of a rank must be contiguous");
+    c->domain = dom;
+    c->local  = k;
+    check(nixb200_chunk_field_upload(dom->h, k, NIXB200_FIELD_UF, c->uf.data()), "field_upload");
+  }
+  for (int is = 0; is < ns; is++) {
+    std::vector<int64_t> np(chunks.size());
+    int64_t              total = 0;
+    for (size_t k = 0; k < chunks.size(); k++) total += (np[k] = static_cast<GpuChunk*>(chunks[k].get())->up[is]->Np);
+    std::vector<double> flat((size_t)total * 7);
+    size_t              pos = 0;
+    for (size_t k = 0; k < chunks.size(); k++) {
+      auto* c = static_cast<GpuChunk*>(chunks[k].get());
+      std::copy(c->up[is]->xu.data(), c->up[is]->xu.data() + np[k] * 7, flat.begin() + pos);
+      pos += np[k] * 7;
+    }
+    check(nixb200_domain_set_particles(dom->h, is, flat.data(), np.data()), "set_particles");
+  }
+  check(nixb200_domain_exchange_field(dom->h), "exchange_field");
+  check(nixb200_domain_sort(dom->h), "sort");
+  for (auto& c : chunks) static_cast<GpuChunk*>(c.get())->host_is_newer = false;
+  return dom;
+}
+
+/// nix::Application with the PIC step on the GPU.  A downstream application derives from this
+/// instead of nix::Application, fills the staging of its GpuChunks in setup_chunks(), and keeps
+/// everything else (config, diagnostics, checkpoints, balancer) unchanged.
+class GpuApplication : public nix::Application
+{
+protected:
+  std::shared_ptr<GpuDomain> domain;
+  std::vector<SpeciesSpec>   species;
+  int                        order = 2, nb = 2, device = 0;
+  float64                    cc    = 1.0;
+  bool                       strict_fp = false;
+
+public:
+  GpuApplication(int argc, char** argv, PtrInterface interface = std::make_shared<GpuInterface>())
+      : nix::Application(argc, argv, interface)
+  {
+  }
+
+  /// Application::push() (application.hpp:343-346): one step of every local chunk
+  void push() override
+  {
+    bool stale = !domain;
+    for (auto& c : chunkvec) stale = stale || static_cast<GpuChunk*>(c.get())->domain != domain;
+    if (stale) {
+      domain = make_domain(chunkvec, *chunkmap, cdims, nb, order, species, cc, device, strict_fp);
+      if (domain && nprocess > 1) {
+        unsigned char id[128] = {0};
+        if (thisrank == 0) check(nixb200_comm_unique_id(id), "comm_unique_id");
+        MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
+        domain->set_ranks(chunkmap->get_rank_boundary(), thisrank, id);
+      }
+    }
+    if (!domain) return;
+    check(nixb200_domain_step(domain->h, cfgparser->get_delt()), "nixb200_domain_step");
+    // Chunk::load feeds the balancer (chunk.hpp:177-192): device time of the push, shared among
+    // the chunks in proportion to their particle counts
+    double ms = 0;
+    nixb200_domain_get_load(domain->h, &ms);
+    std::vector<int64_t> np(chunkvec.size());
+    std::vector<double>  w(chunkvec.size(), 0.0);
+    double               total = 0;
+    for (size_t is = 0; is < species.size(); is++) {
+      check(nixb200_domain_get_np(domain->h, (int)is, np.data()), "get_np");
+      for (size_t k = 0; k < np.size(); k++) {
+        w[k] += (double)np[k];
+        total += (double)np[k];
+      }
+    }
+    for (size_t k = 0; k < chunkvec.size(); k++) {
+      auto* c          = static_cast<GpuChunk*>(chunkvec[k].get());
+      c->host_is_newer = false;
+      c->set_load_value(total > 0 ? ms * w[k] / total : ms / chunkvec.size());
+    }
+  }
+
+  /// chunks are about to be shipped by Balancer::sendrecv_chunk through Chunk::pack (balancer.hpp:161-222)
+  bool rebalance() override
+  {
+    for (auto& c : chunkvec) static_cast<GpuChunk*>(c.get())->sync_host();
+    bool moved = nix::Application::rebalance();
+    if (moved) domain.reset(); // push() rebuilds it from the new chunk vector
+    return moved;
+  }
+};
+} // namespace nixb200host
