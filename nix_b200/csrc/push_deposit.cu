@@ -19,12 +19,17 @@
 //     Lane = particle: weights, gather from the E/B tile over the EXACT (O+1)^3 support of every
 //     component, Boris, move, store, bin of the new position (-> key + histogram, or a leaver record
 //     with its ordered rank inside the bin).
-//   * deposit: every lane keeps the Esirkepov current of ITS particles on the central (O+1)^3 nodes
-//     of the bin in REGISTERS (81 values for order 2; structural zeros are not stored), accumulated
-//     over all particles of the bin.  When the bin is done the lanes are summed with a butterfly
-//     transpose-reduction on warp shuffles (every lane ends up owning one node value per z-plane)
-//     and added to the J tile.  This is the GPU analogue of the reference's sorted `reduce_add`
-//     path (primitives.hpp:798-809): one scatter per bin instead of one per particle.
+//   * deposit: every lane evaluates the Esirkepov current of ITS particle on the central (O+1)^3
+//     nodes of the bin in REGISTERS, z-plane by z-plane (30 values per plane for order 2;
+//     structural zeros are not stored).  The 32 lanes are then summed through a small per-warp
+//     shared-memory transpose: lanes write [value][lane], pairs of lanes add up one row each
+//     (128-bit conflict-free loads) and keep a RUNNING sum per (plane, value) in registers for all
+//     iterations of the bin; when the bin is done one shared-memory atomic per value adds it to
+//     the J tile.  This is the GPU analogue of the reference's sorted `reduce_add` path
+//     (primitives.hpp:798-809): one scatter per bin instead of one per particle.
+//   * the particle data of the NEXT iteration is prefetched with cp.async straight into a per-warp
+//     staging buffer (no registers held across the iteration, nothing to spill), and the bins of a
+//     tile are handed out dynamically (shared counter) so that the warps of a CTA finish together.
 //   * particles that change bin ("movers", a few per cent) additionally touch nodes outside the
 //     central mesh.  Their 1-D weights go to a small per-warp record list; lanes = face nodes then
 //     add the extra values to the J tile (9 nodes per single-axis mover; the rare multi-axis mover
@@ -37,15 +42,23 @@ namespace nixb200
 {
 namespace
 {
-constexpr int THREADS = 128;
-constexpr int NWARP   = THREADS / 32;
-constexpr int MAXMOV  = 8; // mover records per warp
-constexpr unsigned FULL = 0xffffffffu;
-#ifndef NIX_GATHER_UNROLL
-#define NIX_GATHER_UNROLL 1 // 1: six copies of the gather body (no weight selects, larger code)
+#ifndef NIX_PUSH_WARPS
+#define NIX_PUSH_WARPS 6
 #endif
 #ifndef NIX_PUSH_MINB
-#define NIX_PUSH_MINB 3
+#define NIX_PUSH_MINB 2
+#endif
+constexpr int NWARP   = NIX_PUSH_WARPS;
+constexpr int THREADS = 32 * NWARP;
+constexpr int MAXMOV  = 4; // mover records per warp
+constexpr unsigned FULL = 0xffffffffu;
+// per-warp reduction scratch: RROWS rows (one per plane value) of 2 x 16 lane slots, each half padded
+// to 18 doubles: 64-bit stores of a half-warp and 128-bit loads of a quarter-warp are conflict-free
+constexpr int RROWS = 16, RHALF = 18, RSTRIDE = 2 * RHALF;
+constexpr int RED_DOUBLES_W = RROWS * RSTRIDE;
+constexpr int PF_DOUBLES_W  = 2 * 6 * 32; // cp.async staging: 2 stages x 6 components x 32 lanes
+#ifndef NIX_GATHER_UNROLL
+#define NIX_GATHER_UNROLL 1 // 1: six copies of the gather body (no weight selects, larger code)
 #endif
 
 template <int O>
@@ -60,6 +73,7 @@ struct Cfg {
   static constexpr int P_JY  = P_JX + N1 * (N1 - 1);
   static constexpr int P_JZ  = P_JY + (N1 - 1) * N1;
   static constexpr int PV    = P_JZ + N1 * N1;         // 12 / 30 / 56
+  static constexpr int NPASS = (PV + RROWS - 1) / RROWS; // reduction passes per plane
   // mover record (doubles): per axis (z,y,x): S0[NS] DS[NS] CP[NS]; then 2 doubles of ints
   static constexpr int REC = 9 * NS + 2;
   // bins per CTA (compile-time, so that every shared-memory offset of the gather is an immediate);
@@ -69,26 +83,38 @@ struct Cfg {
   static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
   static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
   static constexpr int J_DOUBLES   = (JZ * JY * JX * 4 + 15) / 16 * 16;
-  static constexpr int REC_DOUBLES = (4 * 8 * REC + 15) / 16 * 16;
+  static constexpr int REC_DOUBLES = (NWARP * MAXMOV * REC + 15) / 16 * 16;
 };
 
 struct SmemLayout {
-  int    eb_doubles, j_doubles, rec_doubles;
+  int    eb_doubles, j_doubles, rec_doubles, red_doubles, pf_doubles;
   size_t bytes;
 };
-constexpr int SMEM_INTS = 640;
-static_assert(256 + 4 * 4 * (9 + 1) <= 416 && 416 + sizeof(ChunkGeo) / 4 <= SMEM_INTS, "s_cs / s_cg must fit");
+// int region (offsets in ints)
+constexpr int I_BAR  = 0;                               // mbarrier (2 ints)
+constexpr int I_ANY  = 2;                               // tile has particles
+constexpr int I_NEXT = 3;                               // next bin to hand out
+constexpr int I_TBL  = 8;                               // [64]  J-tile offset of every plane value
+constexpr int I_DCNT = I_TBL + 64;                      // [NWARP][32] leavers of the current bin per direction
+constexpr int I_MLST = I_DCNT + NWARP * 32;             // [NWARP][MAXMOV] single-axis mover records
+constexpr int I_CS   = (I_MLST + NWARP * MAXMOV + 1) / 2 * 2; // [TZ*TY][TX+1] first particle of every bin
+constexpr int I_CG   = I_CS + 4 * 4 * (9 + 1);          // ChunkGeo (8-byte aligned)
+constexpr int SMEM_INTS = (I_CG + (int)((sizeof(ChunkGeo) + 7) / 8 * 2) + 3) / 4 * 4;
+static_assert(I_CG % 2 == 0, "s_cg must be 8-byte aligned");
 
 template <int O>
 __host__ __device__ inline SmemLayout smem_layout()
 {
   using C = Cfg<O>;
-  static_assert(NWARP == 4 && MAXMOV == 8, "REC_DOUBLES assumes 4 warps x 8 records");
+  static_assert(C::TZ * C::TY * (C::TX + 1) <= 160 && C::PV <= 64, "int region sizes");
   SmemLayout L;
   L.eb_doubles  = C::EB_DOUBLES;
   L.j_doubles   = C::J_DOUBLES;
   L.rec_doubles = C::REC_DOUBLES;
-  L.bytes       = sizeof(double) * ((size_t)L.eb_doubles + L.j_doubles + L.rec_doubles) + SMEM_INTS * sizeof(int);
+  L.red_doubles = NWARP * RED_DOUBLES_W;
+  L.pf_doubles  = NWARP * PF_DOUBLES_W;
+  L.bytes       = sizeof(double) * ((size_t)L.eb_doubles + L.j_doubles + L.rec_doubles + L.red_doubles + L.pf_doubles) +
+            SMEM_INTS * sizeof(int);
   return L;
 }
 
@@ -129,6 +155,19 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, 
       "%5, %6, %7}], [%2];" ::"r"(smem_u32(dst)),
       "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
+}
+
+__device__ __forceinline__ void cp_async8(void* dst, const void* src)
+{
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all()
+{
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
 // ---- shape functions (primitives.hpp:257-298), association order preserved ----------------------
@@ -249,45 +288,37 @@ __device__ __forceinline__ void plane_accumulate(const double s0z, const double 
   }
 }
 
-// butterfly transpose-reduction of v[0..PV) over the 32 lanes; afterwards lane l holds, at local
-// slot j, the warp-wide sum of original entry  j + sum over set bits of l of the half sizes
-template <int N>
-struct Halves {
-  static constexpr int h = (N + 1) / 2;
-};
-
-template <int N, int OFF>
-__device__ __forceinline__ void bfly_step(double* v, int lane)
+// Sum the plane values acc[0..PV) of the 32 lanes through the warp's scratch and add them to the
+// running sums of the bin: pass p handles the values [16p, 16p+16); lane l = (row l>>1, half l&1)
+// adds up 16 of the 32 lane slots of its row, the two halves meet with one shuffle.  Afterwards
+// BOTH lanes of a pair hold the sum of value 16p + (l>>1) in bsum[p].
+template <int O>
+__device__ __forceinline__ void plane_reduce(const double* acc, double* my_red, int lane, double* bsum)
 {
-  constexpr int h     = (N + 1) / 2;
-  const bool    upper = (lane & OFF) != 0;
+  using C = Cfg<O>;
+  const int col = (lane >> 4) * RHALF + (lane & 15);
+  const double2* src = reinterpret_cast<const double2*>(my_red + (lane >> 1) * RSTRIDE + (lane & 1) * RHALF);
 #pragma unroll
-  for (int j = 0; j < h; j++) {
-    const double lo   = v[j];
-    const double hi   = (j + h < N) ? v[j + h] : 0.0;
-    const double send = upper ? lo : hi;
-    const double keep = upper ? hi : lo;
-    v[j]              = keep + __shfl_xor_sync(FULL, send, OFF);
+  for (int p = 0; p < C::NPASS; p++) {
+#pragma unroll
+    for (int r = 0; r < RROWS; r++)
+      if (p * RROWS + r < C::PV) my_red[r * RSTRIDE + col] = acc[p * RROWS + r];
+    __syncwarp();
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const double2 a = src[i], b = src[i + 1];
+      s0 += a.x;
+      s1 += a.y;
+      s2 += b.x;
+      s3 += b.y;
+    }
+    double sum = (s0 + s1) + (s2 + s3);
+    sum += __shfl_xor_sync(FULL, sum, 1);
+    bsum[p] += sum;
+    __syncwarp();
   }
 }
-
-template <int PV>
-__device__ __forceinline__ void bfly_reduce(double* v, int lane, int& base)
-{
-  constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
-  bfly_step<PV, 16>(v, lane);
-  bfly_step<n1, 8>(v, lane);
-  bfly_step<n2, 4>(v, lane);
-  bfly_step<n3, 2>(v, lane);
-  bfly_step<n4, 1>(v, lane);
-  base = ((lane & 16) ? n1 : 0) + ((lane & 8) ? n2 : 0) + ((lane & 4) ? n3 : 0) + ((lane & 2) ? n4 : 0) +
-         ((lane & 1) ? (n4 + 1) / 2 : 0);
-}
-template <int PV>
-struct BflyOut {
-  static constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
-  static constexpr int nf = (n4 + 1) / 2; // values left per lane
-};
 
 // Add the extra values (outside the register-resident set) of the recorded movers of one warp to the
 // J tile.  Called once per bin (or when the record list is full): kept out of line so that the hot
@@ -407,14 +438,17 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   double*   s_eb   = smem_d;
   double*   s_j    = smem_d + L.eb_doubles;
   double*   s_rec  = s_j + L.j_doubles;
-  int*      s_int  = reinterpret_cast<int*>(s_rec + L.rec_doubles);
-  uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int); // 2 ints
-  int*      s_any  = s_int + 2;                          // [1]
-  int*      s_tbl  = s_int + 8;                          // [PV] J-tile offset of every plane value
-  int*      s_dcnt = s_int + 72;                         // [NWARP][32] leavers of the current bin per direction
-  int*      s_mlst = s_int + 72 + NWARP * 32;            // [NWARP][MAXMOV] single-axis mover records
-  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + 416); // 8-byte aligned
-  int*      s_cs   = s_int + 256;                        // [TZ*TY][TX+1] first particle of every bin of the tile
+  double*   s_red  = s_rec + L.rec_doubles;
+  double*   s_pf   = s_red + L.red_doubles;
+  int*      s_int  = reinterpret_cast<int*>(s_pf + L.pf_doubles);
+  uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int + I_BAR);
+  int*      s_any  = s_int + I_ANY;
+  int*      s_next = s_int + I_NEXT;
+  int*      s_tbl  = s_int + I_TBL;
+  int*      s_dcnt = s_int + I_DCNT;
+  int*      s_mlst = s_int + I_MLST;
+  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + I_CG);
+  int*      s_cs   = s_int + I_CS;
 
   const int32_t* __restrict__ start = P.sp.start;
   const int cellkey0 = ch * g.ncell;
@@ -422,7 +456,10 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   // ---- particle ranges of the tile's bins -> shared memory; empty tile? (e.g. the rounding-guard
   //      bin layer of even orders) ------------------------------------------------------------------
   constexpr int CSW = C::TX + 1; // row width of s_cs
-  if (tid == 0) *s_any = 0;
+  if (tid == 0) {
+    *s_any  = 0;
+    *s_next = NWARP; // the first NWARP bins are taken by the warps directly
+  }
   for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += THREADS)
     reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
   for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += THREADS) {
@@ -453,6 +490,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
   for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) s_j[t] = 0.0;
+  for (int t = tid; t < L.red_doubles; t += THREADS) s_red[t] = 0.0;
   for (int v = tid; v < PV; v += THREADS) {
     // plane value v -> (component, jy, jx) in mesh slots (central index + 1)
     int comp, jy, jx;
@@ -482,62 +520,85 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
 
   mbar_wait(s_bar, 0);
 
-  // add the reduced plane values of a bin to the J tile
-  auto flush_plane = [&](double* v, int jz, int cellbase) {
-    int base;
-    bfly_reduce<PV>(v, lane, base);
+  double* my_red = s_red + warp * RED_DOUBLES_W;
+  double* my_pf  = s_pf + warp * PF_DOUBLES_W;
+  constexpr int NPASS = C::NPASS;
+
+  // running sums of the current bin: bsum[z][p] = value 16p + (lane>>1) of plane z
+  double bsum[N1][NPASS];
 #pragma unroll
-    for (int j = 0; j < BflyOut<PV>::nf; j++) {
-      const int idx = base + j;
-      if (idx < PV && v[j] != 0.0) atomicAdd(s_j + cellbase + (jz + 1) * JY * JX * 4 + s_tbl[idx], v[j]);
-    }
+  for (int z = 0; z < N1; z++)
+#pragma unroll
+    for (int p = 0; p < NPASS; p++) bsum[z][p] = 0.0;
+  // add the running sums of a finished bin to the J tile (even lanes: one value per pair of lanes)
+  auto flush_bin = [&](int cellbase) {
+#pragma unroll
+    for (int z = 0; z < N1; z++)
+#pragma unroll
+      for (int p = 0; p < NPASS; p++) {
+        const int    v   = p * RROWS + (lane >> 1);
+        const double val = bsum[z][p];
+        if (!(lane & 1) && v < PV && val != 0.0)
+          atomicAdd(s_j + cellbase + (z + 1) * JY * JX * 4 + s_tbl[v], val);
+        bsum[z][p] = 0.0;
+      }
   };
 
-  // ---- bins of the tile, round robin over the warps; one iteration = up to 32 particles of one
-  //      bin.  The loop is flat and software-pipelined: the particle data of the NEXT iteration is
-  //      requested before the current one is processed (few resident warps, long DRAM latency).
+  // ---- bins of the tile, handed out dynamically; one iteration = up to 32 particles of one bin.
+  //      The loop is flat and software-pipelined: the particle data of the NEXT iteration is
+  //      requested (cp.async into the warp's staging buffer) before the current one is processed.
   const int ncell_t = nbn[0] * nbn[1] * nbn[2];
   // state of an iteration: bin cl = r * nbn[2] + lx (r = row lz * nbn[1] + ly), particles [i0, pe)
   auto advance = [&](int& cl, int& r, int& lx, int& i0, int& pe) -> bool {
     i0 += 32;
-    while (i0 >= pe) { // next non-empty bin of this warp
-      cl += NWARP;
-      lx += NWARP;
-      while (lx >= nbn[2]) {
-        lx -= nbn[2];
-        r++;
-      }
+    while (i0 >= pe) { // next non-empty bin
+      int nx = 0;
+      if (lane == 0) nx = atomicAdd(s_next, 1);
+      cl = __shfl_sync(FULL, nx, 0);
       if (cl >= ncell_t) return false;
+      r  = cl / nbn[2];
+      lx = cl - r * nbn[2];
       i0 = s_cs[r * CSW + lx];
       pe = s_cs[r * CSW + lx + 1];
     }
     return true;
   };
-  auto fetch = [&](double* d, int i) {
+  auto prefetch = [&](int stage, int i) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) d[k] = xu[soa(k, cap, i)];
+    for (int k = 0; k < 6; k++) cp_async8(my_pf + (stage * 6 + k) * 32 + lane, xu + soa(k, cap, i));
   };
 
-  int    ncl = warp - NWARP, nr = -1, nlx = warp - NWARP + nbn[2], ni0 = 0, npe = 0;
-  bool   have = advance(ncl, nr, nlx, ni0, npe);
-  double nxt[6] = {0, 0, 0, 0, 0, 0};
-  if (have && ni0 + lane < npe) fetch(nxt, ni0 + lane);
+  int  ncl = warp, nr = 0, nlx = 0, ni0 = 0, npe = 0;
+  bool have = ncl < ncell_t;
+  if (have) {
+    nr   = ncl / nbn[2];
+    nlx  = ncl - nr * nbn[2];
+    ni0  = s_cs[nr * CSW + nlx] - 32;
+    npe  = s_cs[nr * CSW + nlx + 1];
+    have = advance(ncl, nr, nlx, ni0, npe);
+  }
+  int stage = 0;
+  if (have && ni0 + lane < npe) prefetch(0, ni0 + lane);
+  cp_async_commit();
 
   int  prev_cl = -1, nrec = 0;
   int  bz = 0, by = 0, bx = 0, cellbase = 0;
   bool had_leav = false; // warp-uniform
   const double* ecell = s_eb;
-  double acc[PV];
 
   while (have) {
     const int cl = ncl, cr = nr, clx = nlx, i0 = ni0, pe = npe;
-    double    cur[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) cur[k] = nxt[k];
     have = advance(ncl, nr, nlx, ni0, npe);
-    if (have && ni0 + lane < npe) fetch(nxt, ni0 + lane);
+    cp_async_wait_all();
+    double cur[6];
+#pragma unroll
+    for (int k = 0; k < 6; k++) cur[k] = my_pf[(stage * 6 + k) * 32 + lane];
+    stage ^= 1;
+    if (have && ni0 + lane < npe) prefetch(stage, ni0 + lane);
+    cp_async_commit();
 
     if (cl != prev_cl) { // first iteration of a bin
+      if (prev_cl >= 0) flush_bin(cellbase);
       const int lx = clx, lz = (nbn[1] == C::TY) ? cr / C::TY : cr / nbn[1], ly = cr - lz * nbn[1];
       bz = b0[0] + lz, by = b0[1] + ly, bx = b0[2] + lx;
       cellbase = ((lz * JY + ly) * JX + lx) * 4; // J-tile offset of mesh slot (0,0,0)
@@ -734,24 +795,14 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       }
 
       // =============================== deposit ===============================
-      // one loop body for all z-planes; the z weights rotate through slot 0 (back in place after N1
-      // turns).  Every plane is summed over the lanes and added to the J tile right away.
-#pragma unroll 1
+      // plane by plane: evaluate on the lane's registers, sum the 32 lanes through the scratch
+#pragma unroll
       for (int z = 0; z < N1; z++) {
+        double acc[PV];
 #pragma unroll
         for (int v = 0; v < PV; v++) acc[v] = 0.0;
-        plane_accumulate<O>(w.s0[0][0], w.ds[0][0], w.cp[0][0], z >= 1, w, P.q, P.qdxdt, acc);
-        flush_plane(acc, z, cellbase);
-        const double t0 = w.s0[0][0], t1 = w.ds[0][0], t2 = w.cp[0][0];
-#pragma unroll
-        for (int j = 0; j < N1 - 1; j++) {
-          w.s0[0][j] = w.s0[0][j + 1];
-          w.ds[0][j] = w.ds[0][j + 1];
-          w.cp[0][j] = w.cp[0][j + 1];
-        }
-        w.s0[0][N1 - 1] = t0;
-        w.ds[0][N1 - 1] = t1;
-        w.cp[0][N1 - 1] = t2;
+        plane_accumulate<O>(w.s0[0][z], w.ds[0][z], w.cp[0][z], z >= 1, w, P.q, P.qdxdt, acc);
+        plane_reduce<O>(acc, my_red, lane, bsum[z]);
       }
 
       // ---- movers: record the full 1-D weights; flush the record list when it is full -----------
@@ -801,6 +852,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       }
     }
   }
+  if (prev_cl >= 0) flush_bin(cellbase);
   if (nrec) flush_movers<O>(s_j, myrec, myml, nrec, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
 
   // ---- flush the J tile: the CTA's single scatter to global memory --------------------------------
