@@ -31,9 +31,10 @@
 //     staging buffer (no registers held across the iteration, nothing to spill), and the bins of a
 //     tile are handed out dynamically (shared counter) so that the warps of a CTA finish together.
 //   * particles that change bin ("movers", a few per cent) additionally touch nodes outside the
-//     central mesh.  Their 1-D weights go to a small per-warp record list; lanes = face nodes then
-//     add the extra values to the J tile (9 nodes per single-axis mover; the rare multi-axis mover
-//     walks its whole (O+3)^3 mesh).
+//     central mesh.  They leave a compact record (old and new position, bin) in a per-warp list; when
+//     the list fills up, lanes = (mover, axis) expand ten records at a time into full 1-D weight
+//     tables and lanes = (mover, face node) add the extra values to the J tile (9 nodes per
+//     single-axis mover; the rare multi-axis mover walks its whole (O+3)^3 mesh).
 #include "common.cuh"
 
 #include <algorithm>
@@ -45,12 +46,17 @@ namespace
 #ifndef NIX_PUSH_WARPS
 #define NIX_PUSH_WARPS 6
 #endif
+#ifndef NIX_BATCH_CAS
+#define NIX_BATCH_CAS 0 // movers: run the compare-and-swap loops of a lane's fp64 shared atomics in lock step
+#endif
 #ifndef NIX_PUSH_MINB
 #define NIX_PUSH_MINB 2
 #endif
 constexpr int NWARP   = NIX_PUSH_WARPS;
 constexpr int THREADS = 32 * NWARP;
-constexpr int MAXMOV  = 4; // mover records per warp
+constexpr int MAXMOV  = 24; // compact mover records per warp (old + new position, bin: 64 bytes each)
+constexpr int CREC    = 8;  // doubles per compact record
+constexpr int XGROUP  = 10; // movers expanded to full 1-D weight records at a time (3 axes x 10 = 30 lanes)
 constexpr unsigned FULL = 0xffffffffu;
 // per-warp reduction scratch: RROWS rows (one per plane value) of 2 x 16 lane slots, each half padded
 // to 18 doubles: 64-bit stores of a half-warp and 128-bit loads of a quarter-warp are conflict-free
@@ -83,7 +89,7 @@ struct Cfg {
   static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
   static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
   static constexpr int J_DOUBLES   = (JZ * JY * JX * 4 + 15) / 16 * 16;
-  static constexpr int REC_DOUBLES = (NWARP * MAXMOV * REC + 15) / 16 * 16;
+  static constexpr int REC_DOUBLES = (NWARP * MAXMOV * CREC + 15) / 16 * 16;
 };
 
 struct SmemLayout {
@@ -320,12 +326,41 @@ __device__ __forceinline__ void plane_reduce(const double* acc, double* my_red, 
   }
 }
 
-// Add the extra values (outside the register-resident set) of the recorded movers of one warp to the
-// J tile.  Called once per bin (or when the record list is full): kept out of line so that the hot
-// per-particle loop stays small enough for the instruction cache.
+// N independent fp64 additions to shared memory.  fp64 shared-memory atomics are compare-and-swap
+// loops; running the N loops of a lane in lock step overlaps their round trips.
+template <int N>
+__device__ __forceinline__ void atomic_add_batch(double* const* ad, const double* val, bool* todo)
+{
+#if !NIX_BATCH_CAS
+#pragma unroll
+  for (int k = 0; k < N; k++)
+    if (todo[k]) atomicAdd(ad[k], val[k]);
+#else
+  unsigned long long old[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) old[k] = todo[k] ? *reinterpret_cast<const volatile unsigned long long*>(ad[k]) : 0ull;
+  bool any = true;
+  while (any) {
+    any = false;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      if (todo[k]) {
+        const unsigned long long want = __double_as_longlong(__longlong_as_double(old[k]) + val[k]);
+        const unsigned long long got  = atomicCAS(reinterpret_cast<unsigned long long*>(ad[k]), old[k], want);
+        todo[k]                       = got != old[k];
+        old[k]                        = got;
+        any                           = any || todo[k];
+      }
+    }
+  }
+#endif
+}
+
+// Add the extra values (outside the register-resident set) of up to XGROUP expanded mover records
+// (per axis z,y,x: S0[NS] DS[NS] CP[NS], then cellbase and mover code) to the J tile.
 template <int O>
-__device__ __noinline__ void flush_movers(double* s_j, const double* myrec, int* myml, int nrec, double q,
-                                          double qdz, double qdy, double qdx)
+__device__ __forceinline__ void flush_group(double* s_j, const double* myrec, int* myml, int nrec, double q,
+                                            double qdz, double qdy, double qdx)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1, NS = C::NS, JY = C::JY, JX = C::JX;
@@ -369,16 +404,13 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* myrec, int*
       node(r, jz, jy, jx, rho, wx, wy, wz);
       double*      dst = s_j + cbase + ((jz * JY + jy) * JX + jx) * 4;
       const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
-      if (rho != 0.0) atomicAdd(dst + 0, rho);
-      if (vx != 0.0) atomicAdd(dst + 1, vx);
-      if (vy != 0.0) atomicAdd(dst + 2, vy);
-      if (vz != 0.0) atomicAdd(dst + 3, vz);
-      if (o == 0) {
-        // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
-        const int    st = (ax == 0) ? JY * JX * 4 : ((ax == 1) ? JX * 4 : 4);
-        const double w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
-        if (w1 != 0.0) atomicAdd(dst + st + (3 - ax), w1);
-      }
+      // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
+      const int     st = (ax == 0) ? JY * JX * 4 : ((ax == 1) ? JX * 4 : 4);
+      const double  w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
+      double* const ad[5]   = {dst + 0, dst + 1, dst + 2, dst + 3, dst + st + (3 - ax)};
+      const double  val[5]  = {rho, vx, vy, vz, w1};
+      bool          todo[5] = {rho != 0.0, vx != 0.0, vy != 0.0, vz != 0.0, o == 0 && w1 != 0.0};
+      atomic_add_batch<5>(ad, val, todo);
     }
   }
   // multi-axis movers: the whole (O+3)^3 mesh minus what the register path already holds
@@ -403,12 +435,73 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* myrec, int*
   __syncwarp();
 }
 
+
+struct MoverGeo { // what the expansion needs of the geometry, by value (no param-space pointers)
+  double del[3], rdel[3];
+  int    is_odd;
+};
+
+// Flush the compact mover records of one warp: XGROUP at a time, lanes = (mover, axis) recompute the
+// 1-D deposit weights over the whole (O+3) mesh exactly as the main loop does for the central slots
+// (ss[0][.][1..O+1] = old weights, ss[1][.][1+shift..] = new weights, test_esirkepov.cpp:1060-1085;
+// DS and its running sum CP, esirkepov.hpp:167-174) into the warp's reduction scratch, then
+// flush_group adds the values outside the register-resident set.  Kept out of line: it runs once per
+// ~20 movers.
+template <int O, bool S>
+__device__ __noinline__ void flush_movers(double* s_j, const double* crec, double* xrec, int* myml, int nrec,
+                                          const ChunkGeo* c, MoverGeo mg, double q, double qdz, double qdy, double qdx)
+{
+  using C          = Cfg<O>;
+  constexpr int N1 = C::N1, NS = C::NS;
+  static_assert(XGROUP * C::REC <= RED_DOUBLES_W && XGROUP * 3 <= 32, "expanded records live in the reduction scratch");
+  const int lane = threadIdx.x & 31;
+  for (int m0 = 0; m0 < nrec; m0 += XGROUP) {
+    const int ng = min(XGROUP, nrec - m0);
+    __syncwarp();
+    if (lane < 3 * ng) {
+      const int     m = lane / 3, a = lane - 3 * m;
+      const double* cr = crec + (size_t)(m0 + m) * CREC;
+      const int*    ci = reinterpret_cast<const int*>(cr + 6);
+      const double  xo = cr[a], xn = cr[3 + a];
+      const int     bin = (a == 0) ? ci[2] : ((a == 1) ? (ci[3] & 0xffff) : (ci[3] >> 16));
+      const int     ki = bin - mg.is_odd;
+      const int     k1 = digitize(xn, c->off[a], mg.rdel[a]) - mg.is_odd;
+      const int     sft = k1 - ki;
+      double        wi[N1], wn[N1];
+      shape_mc<O, S>(xo, add<S>(c->imin[a], mul<S>((double)ki, mg.del[a])), mg.rdel[a], wi);
+      shape_mc<O, S>(xn, add<S>(c->imin[a], mul<S>((double)k1, mg.del[a])), mg.rdel[a], wn);
+      double* r  = xrec + m * C::REC + 3 * a * NS;
+      double  cp = 0.0;
+#pragma unroll
+      for (int j = 0; j < NS; j++) {
+        const double s0 = (j >= 1 && j <= O + 1) ? wi[j - 1] : 0.0;
+        const double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // shift -1: slot j <- wn[j]
+        const double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // shift  0
+        const double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // shift +1
+        const double s1 = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
+        const double ds = s1 - s0;
+        r[j]            = s0;
+        r[NS + j]       = ds;
+        r[2 * NS + j]   = cp;
+        cp += ds;
+      }
+      if (a == 0) {
+        int* ri = reinterpret_cast<int*>(xrec + m * C::REC + 9 * NS);
+        ri[0]   = ci[0];
+        ri[1]   = ci[1];
+      }
+    }
+    __syncwarp();
+    flush_group<O>(s_j, xrec, myml, ng, q, qdz, qdy, qdx);
+  }
+  __syncwarp();
+}
+
 template <int O, bool S>
 __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
                                                              const Kparams P)
 {
   using C          = Cfg<O>;
-  constexpr int NW = C::NW;
   constexpr int N1 = C::N1;
   constexpr int NS = C::NS;
   constexpr int PV = C::PV;
@@ -514,7 +607,11 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   const int       cb  = P.sp.cbase[ch];
   const size_t    cap = P.sp.cap;
   double* __restrict__ xu = P.sp.xu;
-  double* myrec = s_rec + (size_t)warp * MAXMOV * C::REC;
+  double* myrec = s_rec + (size_t)warp * MAXMOV * CREC;
+  MoverGeo mgeo;
+#pragma unroll
+  for (int a = 0; a < 3; a++) mgeo.del[a] = g.del[a], mgeo.rdel[a] = g.rdel[a];
+  mgeo.is_odd = g.is_odd;
   int*    mydc  = s_dcnt + warp * 32;
   int*    myml  = s_mlst + warp * MAXMOV;
 
@@ -616,7 +713,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       bool       dep_ok = false, mover = false;
       int        mcode = -1; // single-axis mover: axis*2 + (1 if high side); -1: multi-axis
       Wts<O>     w;
-      double     out0[3], outL[3], cpL[3]; // DS[0], DS[NS-1], CP[NS-1] per axis (movers only)
+      double     mvn[3] = {0.0, 0.0, 0.0}; // new position (z,y,x), for the mover record
 
       // =============================== push ===============================
       if (valid) {
@@ -695,6 +792,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
         pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
         pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
 
+        mvn[0] = pn[0], mvn[1] = pn[1], mvn[2] = pn[2];
         xu[soa(0, cap, i)] = pn[2];
         xu[soa(1, cap, i)] = pn[1];
         xu[soa(2, cap, i)] = pn[0];
@@ -758,11 +856,6 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
               w.ds[a][j - 1] = ds;
               w.cp[a][j - 1] = cp;
             }
-            if (j == 0) out0[a] = ds;
-            if (j == NS - 1) {
-              outL[a] = ds;
-              cpL[a]  = cp;
-            }
             cp += ds;
           }
         }
@@ -805,38 +898,27 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
         plane_reduce<O>(acc, my_red, lane, bsum[z]);
       }
 
-      // ---- movers: record the full 1-D weights; flush the record list when it is full -----------
+      // ---- movers: compact record (old / new position, bin); the list is flushed when it is full ----
       unsigned mm = __ballot_sync(FULL, mover);
       while (mm) {
-        const int room = MAXMOV - nrec;
-        const int rk   = __popc(mm & ((1u << lane) - 1));
+        const int  room = MAXMOV - nrec;
+        const int  rk   = __popc(mm & ((1u << lane) - 1));
         const bool take = mover && ((mm >> lane) & 1u) && rk < room;
         if (take) {
-          double* r = myrec + (nrec + rk) * C::REC;
-#pragma unroll
-          for (int a = 0; a < 3; a++) {
-            r[(3 * a + 0) * NS + 0] = 0.0;
-            r[(3 * a + 1) * NS + 0] = out0[a];
-            r[(3 * a + 2) * NS + 0] = 0.0;
-#pragma unroll
-            for (int j = 0; j < N1; j++) {
-              r[(3 * a + 0) * NS + 1 + j] = w.s0[a][j];
-              r[(3 * a + 1) * NS + 1 + j] = w.ds[a][j];
-              r[(3 * a + 2) * NS + 1 + j] = w.cp[a][j];
-            }
-            r[(3 * a + 0) * NS + NS - 1] = 0.0;
-            r[(3 * a + 1) * NS + NS - 1] = outL[a];
-            r[(3 * a + 2) * NS + NS - 1] = cpL[a];
-          }
-          int* ri = reinterpret_cast<int*>(r + 9 * NS);
+          double* r = myrec + (nrec + rk) * CREC;
+          r[0] = cur[2], r[1] = cur[1], r[2] = cur[0]; // old z, y, x
+          r[3] = mvn[0], r[4] = mvn[1], r[5] = mvn[2]; // new z, y, x
+          int* ri = reinterpret_cast<int*>(r + 6);
           ri[0]   = cellbase;
           ri[1]   = mcode;
+          ri[2]   = bz;
+          ri[3]   = by | (bx << 16);
         }
         const unsigned taken = __ballot_sync(FULL, take);
         nrec += __popc(taken);
         mm &= ~taken;
-        if (nrec == MAXMOV) { // records carry their bin, so the list is only flushed when it is full
-          flush_movers<O>(s_j, myrec, myml, nrec, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
+        if (mm || nrec > MAXMOV - 8) { // full (or nearly: the next iteration brings a few more)
+          flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
           nrec = 0;
         }
       }
@@ -853,7 +935,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     }
   }
   if (prev_cl >= 0) flush_bin(cellbase);
-  if (nrec) flush_movers<O>(s_j, myrec, myml, nrec, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
+  if (nrec) flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
 
   // ---- flush the J tile: the CTA's single scatter to global memory --------------------------------
   __syncthreads();
