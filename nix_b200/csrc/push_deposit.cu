@@ -88,7 +88,10 @@ struct Cfg {
   static constexpr int EZ = TZ + NW - 1, EY = TY + NW - 1, EX = TX + NW - 1; // staged E/B tile
   static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
   static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
-  static constexpr int J_DOUBLES   = (JZ * JY * JX * 4 + 15) / 16 * 16;
+  // J tile, component-major: s_j[comp * JC + node] -- lanes that add the same component of neighbouring
+  // nodes hit neighbouring banks (node-major [node][4] puts them 32 bytes apart: 4-way conflicts)
+  static constexpr int JN = JZ * JY * JX, JC = (JN + 7) / 8 * 8 + 2;
+  static constexpr int J_DOUBLES   = (4 * JC + 15) / 16 * 16;
   static constexpr int REC_DOUBLES = (NWARP * MAXMOV * CREC + 15) / 16 * 16;
 };
 
@@ -402,12 +405,12 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
       const int jx = (ax == 2) ? o : v;
       double    rho, wx, wy, wz;
       node(r, jz, jy, jx, rho, wx, wy, wz);
-      double*      dst = s_j + cbase + ((jz * JY + jy) * JX + jx) * 4;
+      double*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
       const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
       // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
-      const int     st = (ax == 0) ? JY * JX * 4 : ((ax == 1) ? JX * 4 : 4);
+      const int     st = (ax == 0) ? JY * JX : ((ax == 1) ? JX : 1);
       const double  w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
-      double* const ad[5]   = {dst + 0, dst + 1, dst + 2, dst + 3, dst + st + (3 - ax)};
+      double* const ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
       const double  val[5]  = {rho, vx, vy, vz, w1};
       bool          todo[5] = {rho != 0.0, vx != 0.0, vy != 0.0, vz != 0.0, o == 0 && w1 != 0.0};
       atomic_add_batch<5>(ad, val, todo);
@@ -424,12 +427,12 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
       const bool central = jz >= 1 && jz <= N1 && jy >= 1 && jy <= N1 && jx >= 1 && jx <= N1;
       double     rho, wx, wy, wz;
       node(r, jz, jy, jx, rho, wx, wy, wz);
-      double*      dst = s_j + cbase + ((jz * JY + jy) * JX + jx) * 4;
+      double*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
       const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
-      if (!central && rho != 0.0) atomicAdd(dst + 0, rho);
-      if (!(central && jx >= 2) && vx != 0.0) atomicAdd(dst + 1, vx);
-      if (!(central && jy >= 2) && vy != 0.0) atomicAdd(dst + 2, vy);
-      if (!(central && jz >= 2) && vz != 0.0) atomicAdd(dst + 3, vz);
+      if (!central && rho != 0.0) atomicAdd(dst, rho);
+      if (!(central && jx >= 2) && vx != 0.0) atomicAdd(dst + C::JC, vx);
+      if (!(central && jy >= 2) && vy != 0.0) atomicAdd(dst + 2 * C::JC, vy);
+      if (!(central && jz >= 2) && vz != 0.0) atomicAdd(dst + 3 * C::JC, vz);
     }
   }
   __syncwarp();
@@ -582,7 +585,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     mbar_expect_tx(s_bar, (uint32_t)(C::EZ * EY * EX * 6 * sizeof(double)));
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
-  for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) s_j[t] = 0.0;
+  for (int t = tid; t < L.j_doubles; t += THREADS) s_j[t] = 0.0;
   for (int t = tid; t < L.red_doubles; t += THREADS) s_red[t] = 0.0;
   for (int v = tid; v < PV; v += THREADS) {
     // plane value v -> (component, jy, jx) in mesh slots (central index + 1)
@@ -599,7 +602,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       int r = v - C::P_JZ;
       comp = 3, jy = r / N1, jx = r % N1;
     }
-    s_tbl[v] = ((jy + 1) * JX + (jx + 1)) * 4 + comp;
+    s_tbl[v] = comp * C::JC + (jy + 1) * JX + (jx + 1);
   }
   __syncthreads();
 
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   for (int z = 0; z < N1; z++)
 #pragma unroll
     for (int p = 0; p < NPASS; p++) bsum[z][p] = 0.0;
-  // add the running sums of a finished bin to the J tile (even lanes: one value per pair of lanes)
+  // add the running sums of a finished bin to the J tile (one lane of each pair per value)
   auto flush_bin = [&](int cellbase) {
 #pragma unroll
     for (int z = 0; z < N1; z++)
@@ -635,8 +638,8 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       for (int p = 0; p < NPASS; p++) {
         const int    v   = p * RROWS + (lane >> 1);
         const double val = bsum[z][p];
-        if (!(lane & 1) && v < PV && val != 0.0)
-          atomicAdd(s_j + cellbase + (z + 1) * JY * JX * 4 + s_tbl[v], val);
+        if ((lane & 1) == (p & 1) && v < PV && val != 0.0) // both lanes of a pair hold the sum: share the passes
+          atomicAdd(s_j + cellbase + (z + 1) * JY * JX + s_tbl[v], val);
         bsum[z][p] = 0.0;
       }
   };
@@ -698,7 +701,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
       if (prev_cl >= 0) flush_bin(cellbase);
       const int lx = clx, lz = (nbn[1] == C::TY) ? cr / C::TY : cr / nbn[1], ly = cr - lz * nbn[1];
       bz = b0[0] + lz, by = b0[1] + ly, bx = b0[2] + lx;
-      cellbase = ((lz * JY + ly) * JX + lx) * 4; // J-tile offset of mesh slot (0,0,0)
+      cellbase = (lz * JY + ly) * JX + lx; // J-tile node of mesh slot (0,0,0)
       ecell    = s_eb + (size_t)((lz * EY + ly) * EX + lx) * 6;
       had_leav = false;
       prev_cl  = cl;
@@ -941,7 +944,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   __syncthreads();
   double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
   for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) {
-    const double v = s_j[t];
+    const double v = s_j[(t & 3) * C::JC + (t >> 2)];
     if (v != 0.0) {
       const int k = t & 3, n = t >> 2;
       const int gx = jx0 + n % JX, gy = jy0 + (n / JX) % JY, gz = jz0 + n / (JX * JY);
