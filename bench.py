@@ -26,7 +26,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "particle-updates/s (push+deposit+sort)"
-ALGO_BYTES_PUSH = 116.0  # push+deposit+count reads 56 B, writes 56 B + 4 B per particle
+# Algorithmic bytes per particle (SURVEY.md 8(d) counts 116 B for a fused push+deposit+count):
+#   k_push     reads x y z ux uy uz (48 B), writes them back (48 B), the old position to the temporary
+#              array (24 B, the reference's xv[0:3] = xu[0:3]) and the sort key (4 B)
+#   k_deposit  reads the old and the new position (48 B)
+ALGO_BYTES = {"k_push": 124.0, "k_deposit": 48.0}
 
 
 def workload(args):
@@ -308,16 +312,27 @@ def run_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-        per_launch_ms = push_ms / max(push_calls, 1) / prob.ns  # one launch per species
-        achieved = ALGO_BYTES_PUSH * (ntot / prob.ns) / (per_launch_ms * 1e-3) / 1e9 if per_launch_ms > 0 else 0.0
-        traffic = None
+        # per kernel: CUDA events recorded by the library around every launch on the domain's stream
+        traffic_by_kernel = {}
         tpath = os.path.join(ROOT, "profiles", "push_deposit_traffic.json")
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic = json.load(f).get("dram_bytes_per_launch")
+                    traffic_by_kernel = json.load(f).get("dram_bytes_per_particle", {})
             except (OSError, ValueError):
-                traffic = None
+                traffic_by_kernel = {}
+        kern = []
+        for name in ("k_push", "k_deposit"):
+            k_ms, k_calls = phases[name]
+            launch_ms = k_ms / max(k_calls, 1)  # one call = one launch = one species
+            part = ntot / prob.ns
+            ach = ALGO_BYTES[name] * part / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+            tr = traffic_by_kernel.get(name)
+            kern.append({"kernel": name + "<2>", "launch_ms": launch_ms, "launches": k_calls,
+                         "algorithmic_bytes_per_particle": ALGO_BYTES[name], "particles_per_launch": part,
+                         "achieved": ach, "frac": ach / peak if peak else None,
+                         "traffic": tr * part if tr else None})
+        dom_k = max(kern, key=lambda k: k["launch_ms"])
         out = {
             "metric": METRIC, "value": nglobal * args.steps / (ms * 1e-3), "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -341,11 +356,14 @@ def run_gpu(args):
                     "what": "per step: E/B of every chunk from pinned host memory, one full step, J of every "
                             "chunk + per-chunk particle counts back to the host"},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "k_push_deposit<2>", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                         "peak_source": peak_src, "algorithmic_bytes_per_particle": ALGO_BYTES_PUSH,
-                         "launch_ms": per_launch_ms,
-                         "note": "fp64-pipe/shared-memory bound for order 2 (SURVEY.md 8d), not HBM bound"},
+            "roofline": {"bound": "hbm", "kernel": dom_k["kernel"], "achieved": dom_k["achieved"], "peak": peak,
+                         "unit": "GB/s", "frac": dom_k["frac"], "traffic": dom_k["traffic"],
+                         "peak_source": peak_src,
+                         "algorithmic_bytes_per_particle": dom_k["algorithmic_bytes_per_particle"],
+                         "launch_ms": dom_k["launch_ms"], "kernels": kern,
+                         "note": "dominant kernel by time; at order 2 / fp64 k_deposit is bound by the fp64 pipe "
+                                 "and issue latency and k_push by the shared-memory data pipe (the 2-wavefront "
+                                 "64-bit gathers), not by HBM (DESIGN.md 3.2, SURVEY.md 8d)"},
             "phases_ms_per_step": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in phases.items()},
         }
         if world == 1 and not args.no_cpu:

@@ -153,10 +153,11 @@ int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int
                                 int64_t* particles_received);
 
 /* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
- * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only).
+ * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only),
+ * 5 the k_push launches of phase 0 alone, 6 its k_deposit launches alone (one call = one launch = one species).
  * With profiling on, every phase call is bracketed by CUDA events on the domain's stream;
  * get_phase_ms synchronises, then returns and resets the accumulated milliseconds and call count. */
-#define NIXB200_NPHASE 5
+#define NIXB200_NPHASE 7
 int nixb200_domain_set_profiling(nixb200_domain* d, int on);
 int nixb200_domain_get_phase_ms(nixb200_domain* d, int phase, double* ms_sum, int* calls);
 

@@ -33,7 +33,7 @@ SYMBOLS = [
     "nixb200_domain_set_comm", "nixb200_domain_peer_traffic",
 ]
 
-PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort")
+PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit")
 
 
 class DomainDesc(C.Structure):

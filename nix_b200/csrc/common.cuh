@@ -202,7 +202,9 @@ struct PushArgs {
   int*             err;
 };
 
-int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st);
+// ev: null, or four events recorded around the two kernels: ev[0] k_push ev[1] | ev[2] k_deposit ev[3]
+int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st,
+                        cudaEvent_t* ev = nullptr);
 size_t push_smem_bytes(const Geo& g);
 void   push_tile_box(int order, int& tz, int& ty, int& tx);
 int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits

@@ -623,7 +623,13 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
     a.sp   = s;
     a.delt = delt;
     a.err  = d->err_dev;
-    if (launch_push_deposit(a, &d->tmap, d->desc.strict_fp != 0, d->stream)) return 1;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (d->profiling) {
+      for (auto& e : ev) cudaEventCreate(&e);
+      d->pending[5].push_back({ev[0], ev[1]});
+      d->pending[6].push_back({ev[2], ev[3]});
+    }
+    if (launch_push_deposit(a, &d->tmap, d->desc.strict_fp != 0, d->stream, d->profiling ? ev : nullptr)) return 1;
   }
   NIX_CUDA(cudaEventRecord(d->ev1, d->stream));
   d->timed = true;

@@ -33,8 +33,8 @@ struct Domain {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending[NIXB200_NPHASE];
   std::vector<int>        coord_all; // id -> (cz,cy,cx) of every chunk of the box
   PeerCtx*                peer = nullptr; // non-null after nixb200_domain_set_ranks with neighbours on other ranks
-  double                  phase_ms[NIXB200_NPHASE]    = {0, 0, 0, 0, 0};
-  int                     phase_calls[NIXB200_NPHASE] = {0, 0, 0, 0, 0};
+  double                  phase_ms[NIXB200_NPHASE]    = {};
+  int                     phase_calls[NIXB200_NPHASE] = {};
 };
 
 // RAII bracket: records an event pair around one phase when profiling is on

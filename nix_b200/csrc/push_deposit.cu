@@ -19,14 +19,17 @@
 //     Lane = particle: weights, gather from the E/B tile over the EXACT (O+1)^3 support of every
 //     component, Boris, move, store, bin of the new position (-> key + histogram, or a leaver record
 //     with its ordered rank inside the bin).
-//   * deposit: every lane evaluates the Esirkepov current of ITS particle on the central (O+1)^3
-//     nodes of the bin in REGISTERS, z-plane by z-plane (30 values per plane for order 2;
-//     structural zeros are not stored).  The 32 lanes are then summed through a small per-warp
-//     shared-memory transpose: lanes write [value][lane], pairs of lanes add up one row each
-//     (128-bit conflict-free loads) and keep a RUNNING sum per (plane, value) in registers for all
-//     iterations of the bin; when the bin is done one shared-memory atomic per value adds it to
-//     the J tile.  This is the GPU analogue of the reference's sorted `reduce_add` path
-//     (primitives.hpp:798-809): one scatter per bin instead of one per particle.
+//   * deposit: the lanes change roles.  Every lane leaves the 1-D deposit weights of its particle
+//     (per axis S0, DS and the running sum of DS) in a per-warp scratch; then lane = (particle slot,
+//     z-plane) -- 8 slots x 4 lanes for orders 2 and 3, 16 x 2 for order 1 -- evaluates, round by
+//     round, the Esirkepov current of one particle on ONE z-plane of the central (O+1)^3 nodes of
+//     the bin and adds it to a register-resident accumulator of that plane (30 values for order 2;
+//     structural zeros are not stored) that lives for ALL particles of the bin.  The lanes of a
+//     particle read the same scratch words, so the 64/128-bit loads of a round are broadcasts.
+//     When the bin is done the accumulators of the 8 (16) slots are summed with a halving butterfly
+//     of warp shuffles and one shared-memory atomic per value adds the bin's current to the J tile:
+//     the GPU analogue of the reference's sorted `reduce_add` path (primitives.hpp:798-809) with
+//     one scatter per BIN instead of one per particle, and no cross-lane reduction per iteration.
 //   * the particle data of the NEXT iteration is prefetched with cp.async straight into a per-warp
 //     staging buffer (no registers held across the iteration, nothing to spill), and the bins of a
 //     tile are handed out dynamically (shared counter) so that the warps of a CTA finish together.
@@ -43,30 +46,11 @@ namespace nixb200
 {
 namespace
 {
-#ifndef NIX_PUSH_WARPS
-#define NIX_PUSH_WARPS 6
-#endif
-#ifndef NIX_BATCH_CAS
-#define NIX_BATCH_CAS 0 // movers: run the compare-and-swap loops of a lane's fp64 shared atomics in lock step
-#endif
-#ifndef NIX_PUSH_MINB
-#define NIX_PUSH_MINB 2
-#endif
-constexpr int NWARP   = NIX_PUSH_WARPS;
-constexpr int THREADS = 32 * NWARP;
 constexpr int MAXMOV  = 24; // compact mover records per warp (old + new position, bin: 64 bytes each)
 constexpr int CREC    = 8;  // doubles per compact record
 constexpr int XGROUP  = 10; // movers expanded to full 1-D weight records at a time (3 axes x 10 = 30 lanes)
 constexpr unsigned FULL = 0xffffffffu;
-// per-warp reduction scratch: RROWS rows (one per plane value) of 2 x 16 lane slots, each half padded
-// to 18 doubles: 64-bit stores of a half-warp and 128-bit loads of a quarter-warp are conflict-free
-constexpr int RROWS = 16, RHALF = 18, RSTRIDE = 2 * RHALF;
-constexpr int RED_DOUBLES_W = RROWS * RSTRIDE;
-constexpr int PF_DOUBLES_W  = 2 * 6 * 32; // cp.async staging: 2 stages x 6 components x 32 lanes
-#ifndef NIX_GATHER_UNROLL
-#define NIX_GATHER_UNROLL 1 // 1: six copies of the gather body (no weight selects, larger code)
-#endif
-
+constexpr int PF_DOUBLES_W = 6 * 32; // cp.async staging: 6 components x 32 lanes (a lane re-fills its own slots)
 template <int O>
 struct Cfg {
   static constexpr int NW = O + 2; // stencil width the staged E/B tile is padded by (interp.hpp)
@@ -79,9 +63,19 @@ struct Cfg {
   static constexpr int P_JY  = P_JX + N1 * (N1 - 1);
   static constexpr int P_JZ  = P_JY + (N1 - 1) * N1;
   static constexpr int PV    = P_JZ + N1 * N1;         // 12 / 30 / 56
-  static constexpr int NPASS = (PV + RROWS - 1) / RROWS; // reduction passes per plane
   // mover record (doubles): per axis (z,y,x): S0[NS] DS[NS] CP[NS]; then 2 doubles of ints
   static constexpr int REC = 9 * NS + 2;
+  // deposit rounds: lane = (particle slot, z-plane); PLW lanes per particle, NPS particles per round
+  static constexpr int PLW = (N1 <= 2) ? 2 : 4;
+  static constexpr int NPS = 32 / PLW;
+  // per-warp weight scratch (doubles).  Axis record of y and x: S0[N1] DS[N1] CP[1..N1-1] as NPR
+  // 16-byte pairs, [axis][pair][particle][2]; z: [plane][particle][2] = (S0z, DSz); [plane-1][particle] = CPz
+  static constexpr int NPR   = (3 * N1) / 2;
+  static constexpr int WQ_Z  = 2 * NPR * 64;
+  static constexpr int WQ_ZC = WQ_Z + N1 * 64;
+  static constexpr int WQ_DOUBLES = WQ_ZC + (N1 - 1) * 32;
+  // the scratch also holds the expanded mover records of flush_movers
+  static constexpr int SCR = ((WQ_DOUBLES > XGROUP * REC ? WQ_DOUBLES : XGROUP * REC) + 15) / 16 * 16;
   // bins per CTA (compile-time, so that every shared-memory offset of the gather is an immediate);
   // smaller chunks simply use part of the box
   static constexpr int TZ = 4, TY = 4, TX = 9;
@@ -92,40 +86,7 @@ struct Cfg {
   // nodes hit neighbouring banks (node-major [node][4] puts them 32 bytes apart: 4-way conflicts)
   static constexpr int JN = JZ * JY * JX, JC = (JN + 7) / 8 * 8 + 2;
   static constexpr int J_DOUBLES   = (4 * JC + 15) / 16 * 16;
-  static constexpr int REC_DOUBLES = (NWARP * MAXMOV * CREC + 15) / 16 * 16;
 };
-
-struct SmemLayout {
-  int    eb_doubles, j_doubles, rec_doubles, red_doubles, pf_doubles;
-  size_t bytes;
-};
-// int region (offsets in ints)
-constexpr int I_BAR  = 0;                               // mbarrier (2 ints)
-constexpr int I_ANY  = 2;                               // tile has particles
-constexpr int I_NEXT = 3;                               // next bin to hand out
-constexpr int I_TBL  = 8;                               // [64]  J-tile offset of every plane value
-constexpr int I_DCNT = I_TBL + 64;                      // [NWARP][32] leavers of the current bin per direction
-constexpr int I_MLST = I_DCNT + NWARP * 32;             // [NWARP][MAXMOV] single-axis mover records
-constexpr int I_CS   = (I_MLST + NWARP * MAXMOV + 1) / 2 * 2; // [TZ*TY][TX+1] first particle of every bin
-constexpr int I_CG   = I_CS + 4 * 4 * (9 + 1);          // ChunkGeo (8-byte aligned)
-constexpr int SMEM_INTS = (I_CG + (int)((sizeof(ChunkGeo) + 7) / 8 * 2) + 3) / 4 * 4;
-static_assert(I_CG % 2 == 0, "s_cg must be 8-byte aligned");
-
-template <int O>
-__host__ __device__ inline SmemLayout smem_layout()
-{
-  using C = Cfg<O>;
-  static_assert(C::TZ * C::TY * (C::TX + 1) <= 160 && C::PV <= 64, "int region sizes");
-  SmemLayout L;
-  L.eb_doubles  = C::EB_DOUBLES;
-  L.j_doubles   = C::J_DOUBLES;
-  L.rec_doubles = C::REC_DOUBLES;
-  L.red_doubles = NWARP * RED_DOUBLES_W;
-  L.pf_doubles  = NWARP * PF_DOUBLES_W;
-  L.bytes       = sizeof(double) * ((size_t)L.eb_doubles + L.j_doubles + L.rec_doubles + L.red_doubles + L.pf_doubles) +
-            SMEM_INTS * sizeof(int);
-  return L;
-}
 
 // ---- mbarrier / TMA wrappers (inline PTX) -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p)
@@ -251,14 +212,17 @@ struct Wts {
   double s0[3][O + 1], ds[3][O + 1], cp[3][O + 1];
 };
 
-// Esirkepov current of one particle on z-plane jz of the central mesh, added into acc[PV]:
+// Esirkepov current of one particle on ONE z-plane of the central mesh, added into acc[PV]:
 //   rho[x] += q S1y S1z S1x[x]                                                   esirkepov.hpp:155-164
 //   Jx[x]  += -q dx/dt ((S0y+DSy/2) S0z + (S0y/2+DSy/3) DSz) CPx[x]                        :177-195
 //   Jy[x]  += -q dy/dt CPy ((S0z+DSz/2) S0x[x] + (S0z/2+DSz/3) DSx[x])                     :198-216
 //   Jz[x]  += -q dz/dt CPz ((S0x+DSx/2)[x] S0y + (S0x/2+DSx/3)[x] DSy)                     :219-237
+// ty / tx = axis records of y / x: S0[N1] DS[N1] CP[1..N1-1].  cpz is zero on plane 0 (structural
+// zero of the register set; the first face of a low-side mover is added by the mover path) and all
+// three z weights are zero on an idle lane, which then adds exact zeros.
 template <int O>
 __device__ __forceinline__ void plane_accumulate(const double s0z, const double dsz, const double cpz,
-                                                 const bool with_jz, const Wts<O>& w, const double q,
+                                                 const double* ty, const double* tx, const double q,
                                                  const double* qd, double* acc)
 {
   using C          = Cfg<O>;
@@ -269,63 +233,57 @@ __device__ __forceinline__ void plane_accumulate(const double s0z, const double 
   const double  fz  = -qd[0] * cpz;
 #pragma unroll
   for (int jy = 0; jy < N1; jy++) {
-    const double s0y = w.s0[1][jy], dsy = w.ds[1][jy];
+    const double s0y = ty[jy], dsy = ty[N1 + jy];
     const double ar  = qs1z * (s0y + dsy);
     const double wx  = -qd[2] * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
 #pragma unroll
     for (int jx = 0; jx < N1; jx++) {
-      const double s0x = w.s0[2][jx], dsx = w.ds[2][jx];
+      const double s0x = tx[jx], dsx = tx[N1 + jx];
       acc[C::P_RHO + jy * N1 + jx] = fma(ar, s0x + dsx, acc[C::P_RHO + jy * N1 + jx]);
-      if (jx >= 1) acc[C::P_JX + jy * (N1 - 1) + jx - 1] = fma(wx, w.cp[2][jx], acc[C::P_JX + jy * (N1 - 1) + jx - 1]);
+      if (jx >= 1)
+        acc[C::P_JX + jy * (N1 - 1) + jx - 1] = fma(wx, tx[2 * N1 + jx - 1], acc[C::P_JX + jy * (N1 - 1) + jx - 1]);
       if (jy >= 1) {
         const double wy = azy * s0x + bzy * dsx;
-        acc[C::P_JY + (jy - 1) * N1 + jx] = fma(wy, w.cp[1][jy], acc[C::P_JY + (jy - 1) * N1 + jx]);
+        acc[C::P_JY + (jy - 1) * N1 + jx] = fma(wy, ty[2 * N1 + jy - 1], acc[C::P_JY + (jy - 1) * N1 + jx]);
       }
-    }
-  }
-  if (with_jz) { // plane 0 carries no Jz of the register set (structural zero / mover extra)
-#pragma unroll
-    for (int jy = 0; jy < N1; jy++) {
-      const double s0y = w.s0[1][jy], dsy = w.ds[1][jy];
-#pragma unroll
-      for (int jx = 0; jx < N1; jx++) {
-        const double s0x = w.s0[2][jx], dsx = w.ds[2][jx];
-        const double wz  = (s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy;
-        acc[C::P_JZ + jy * N1 + jx] = fma(fz, wz, acc[C::P_JZ + jy * N1 + jx]);
-      }
+      const double wz = (s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy;
+      acc[C::P_JZ + jy * N1 + jx] = fma(fz, wz, acc[C::P_JZ + jy * N1 + jx]);
     }
   }
 }
 
-// Sum the plane values acc[0..PV) of the 32 lanes through the warp's scratch and add them to the
-// running sums of the bin: pass p handles the values [16p, 16p+16); lane l = (row l>>1, half l&1)
-// adds up 16 of the 32 lane slots of its row, the two halves meet with one shuffle.  Afterwards
-// BOTH lanes of a pair hold the sum of value 16p + (l>>1) in bsum[p].
+// One deposit round: lane = (slot ps, plane pl) adds plane pl of particle p = first + ps to acc.
 template <int O>
-__device__ __forceinline__ void plane_reduce(const double* acc, double* my_red, int lane, double* bsum)
+__device__ __forceinline__ void deposit_round(const double* wq, int p, int plc, bool pl_on, const double q,
+                                              const double* qd, double* acc)
 {
-  using C = Cfg<O>;
-  const int col = (lane >> 4) * RHALF + (lane & 15);
-  const double2* src = reinterpret_cast<const double2*>(my_red + (lane >> 1) * RSTRIDE + (lane & 1) * RHALF);
+  using C          = Cfg<O>;
+  constexpr int N1 = C::N1, NPR = C::NPR;
+  const double2* q2 = reinterpret_cast<const double2*>(wq);
+  double         ty[2 * NPR], tx[2 * NPR];
 #pragma unroll
-  for (int p = 0; p < C::NPASS; p++) {
+  for (int pr = 0; pr < NPR; pr++) {
+    const double2 a = q2[pr * 32 + p], b = q2[(NPR + pr) * 32 + p];
+    ty[2 * pr] = a.x, ty[2 * pr + 1] = a.y;
+    tx[2 * pr] = b.x, tx[2 * pr + 1] = b.y;
+  }
+  const double2 z2 = q2[C::WQ_Z / 2 + plc * 32 + p];
+  const double  zc = wq[C::WQ_ZC + (plc >= 1 ? plc - 1 : 0) * 32 + p];
+  const double  s0z = pl_on ? z2.x : 0.0, dsz = pl_on ? z2.y : 0.0, cpz = (pl_on && plc >= 1) ? zc : 0.0;
+  plane_accumulate<O>(s0z, dsz, cpz, ty, tx, q, qd, acc);
+}
+
+// One halving stage of the slot butterfly: x[0..N) -> x[0..(N+1)/2); the lane whose slot bit is set
+// keeps the upper half (index i + M), the other one the lower half.
+template <int N>
+__device__ __forceinline__ void bfly_stage(double* x, bool hi, int mask)
+{
+  constexpr int M = (N + 1) / 2;
 #pragma unroll
-    for (int r = 0; r < RROWS; r++)
-      if (p * RROWS + r < C::PV) my_red[r * RSTRIDE + col] = acc[p * RROWS + r];
-    __syncwarp();
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; i += 2) {
-      const double2 a = src[i], b = src[i + 1];
-      s0 += a.x;
-      s1 += a.y;
-      s2 += b.x;
-      s3 += b.y;
-    }
-    double sum = (s0 + s1) + (s2 + s3);
-    sum += __shfl_xor_sync(FULL, sum, 1);
-    bsum[p] += sum;
-    __syncwarp();
+  for (int i = 0; i < M; i++) {
+    const double lo = x[i], up = (i + M < N) ? x[i + M] : 0.0;
+    const double send = hi ? lo : up, keep = hi ? up : lo;
+    x[i] = keep + __shfl_xor_sync(FULL, send, mask);
   }
 }
 
@@ -456,7 +414,7 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* crec, doubl
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1, NS = C::NS;
-  static_assert(XGROUP * C::REC <= RED_DOUBLES_W && XGROUP * 3 <= 32, "expanded records live in the reduction scratch");
+  static_assert(XGROUP * C::REC <= C::SCR && XGROUP * 3 <= 32, "expanded records live in the weight scratch");
   const int lane = threadIdx.x & 31;
   for (int m0 = 0; m0 < nrec; m0 += XGROUP) {
     const int ng = min(XGROUP, nrec - m0);
@@ -500,20 +458,67 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* crec, doubl
   __syncwarp();
 }
 
+// =================================================================================================
+// Split path: k_push (gather + Boris + move + count + leaver classification) and k_deposit (Esirkepov
+// deposit from the old and new positions).  k_push keeps the reference's own data flow -- old
+// position to xv[0:3], new state in place (test_esirkepov.cpp:1046-1051) -- and needs neither the
+// deposit accumulators nor bin-aligned iterations: a warp streams through a whole x-row of bins, 32
+// consecutive particles at a time, every lane addressing the E/B tile from ITS bin.  k_deposit is
+// the bin-owned part (lane roles, accumulators, movers) fed by the 48 bytes of positions only.
+// =================================================================================================
+#ifndef NIX_P_WARPS
+#define NIX_P_WARPS 8
+#endif
+#ifndef NIX_P_MINB
+#define NIX_P_MINB 2
+#endif
+#ifndef NIX_D_WARPS
+#define NIX_D_WARPS 4
+#endif
+#ifndef NIX_D_MINB
+#define NIX_D_MINB 3
+#endif
+constexpr int PWARPS = NIX_P_WARPS, PTHREADS = 32 * PWARPS;
+constexpr int DWARPS = NIX_D_WARPS, DTHREADS = 32 * DWARPS;
+
+// int regions (offsets in ints)
+constexpr int IP_BAR = 0, IP_ANY = 2, IP_NEXT = 3;
+constexpr int IP_DCNT = 8;                          // [PWARPS][32] carried leaver counts of the open bin
+constexpr int IP_CS   = IP_DCNT + PWARPS * 32;      // [TZ*TY][TX+1]
+constexpr int IP_CG   = IP_CS + 4 * 4 * (9 + 1);
+constexpr int IP_INTS = (IP_CG + (int)((sizeof(ChunkGeo) + 7) / 8 * 2) + 3) / 4 * 4;
+static_assert(IP_CG % 2 == 0, "s_cg must be 8-byte aligned");
+constexpr int ID_ANY = 0, ID_NEXT = 1;
+constexpr int ID_TBL  = 8;                          // [64]
+constexpr int ID_MLST = ID_TBL + 64;                // [DWARPS][MAXMOV]
+constexpr int ID_CS   = (ID_MLST + DWARPS * MAXMOV + 1) / 2 * 2;
+constexpr int ID_CG   = ID_CS + 4 * 4 * (9 + 1);
+constexpr int ID_INTS = (ID_CG + (int)((sizeof(ChunkGeo) + 7) / 8 * 2) + 3) / 4 * 4;
+static_assert(ID_CG % 2 == 0, "s_cg must be 8-byte aligned");
+
+template <int O>
+__host__ __device__ inline size_t push_smem()
+{
+  return sizeof(double) * ((size_t)Cfg<O>::EB_DOUBLES + PWARPS * PF_DOUBLES_W) + IP_INTS * sizeof(int);
+}
+template <int O>
+__host__ __device__ inline size_t deposit_smem()
+{
+  using C = Cfg<O>;
+  return sizeof(double) * ((size_t)C::J_DOUBLES + (DWARPS * MAXMOV * CREC + 15) / 16 * 16 + DWARPS * C::SCR +
+                           DWARPS * PF_DOUBLES_W) + ID_INTS * sizeof(int);
+}
+
 template <int O, bool S>
-__global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const __grid_constant__ CUtensorMap tmap,
-                                                             const Kparams P)
+__global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_constant__ CUtensorMap tmap, const Kparams P)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1;
-  constexpr int NS = C::NS;
-  constexpr int PV = C::PV;
   const Geo&    g    = P.geo;
   const int     tid  = threadIdx.x;
   const int     lane = tid & 31;
   const int     warp = tid >> 5;
 
-  // ---- decode the work item -------------------------------------------------------------------
   const int tl = blockIdx.x % g.ntile;
   const int ch = blockIdx.x / g.ntile;
   int       b0[3], nbn[3];
@@ -526,39 +531,29 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     }
   }
   constexpr int EY = C::EY, EX = C::EX;
-  constexpr int JZ = C::JZ, JY = C::JY, JX = C::JX;
   constexpr int esy = EX * 6, esz = EY * EX * 6;
 
   extern __shared__ __align__(1024) double smem_d[];
-  const SmemLayout L = smem_layout<O>();
   double*   s_eb   = smem_d;
-  double*   s_j    = smem_d + L.eb_doubles;
-  double*   s_rec  = s_j + L.j_doubles;
-  double*   s_red  = s_rec + L.rec_doubles;
-  double*   s_pf   = s_red + L.red_doubles;
-  int*      s_int  = reinterpret_cast<int*>(s_pf + L.pf_doubles);
-  uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int + I_BAR);
-  int*      s_any  = s_int + I_ANY;
-  int*      s_next = s_int + I_NEXT;
-  int*      s_tbl  = s_int + I_TBL;
-  int*      s_dcnt = s_int + I_DCNT;
-  int*      s_mlst = s_int + I_MLST;
-  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + I_CG);
-  int*      s_cs   = s_int + I_CS;
+  double*   s_pf   = smem_d + C::EB_DOUBLES;
+  int*      s_int  = reinterpret_cast<int*>(s_pf + PWARPS * PF_DOUBLES_W);
+  uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int + IP_BAR);
+  int*      s_any  = s_int + IP_ANY;
+  int*      s_next = s_int + IP_NEXT;
+  int*      s_dcnt = s_int + IP_DCNT;
+  int*      s_cs   = s_int + IP_CS;
+  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + IP_CG);
 
   const int32_t* __restrict__ start = P.sp.start;
   const int cellkey0 = ch * g.ncell;
-
-  // ---- particle ranges of the tile's bins -> shared memory; empty tile? (e.g. the rounding-guard
-  //      bin layer of even orders) ------------------------------------------------------------------
-  constexpr int CSW = C::TX + 1; // row width of s_cs
+  constexpr int CSW = C::TX + 1;
   if (tid == 0) {
     *s_any  = 0;
-    *s_next = NWARP; // the first NWARP bins are taken by the warps directly
+    *s_next = PWARPS; // the first PWARPS rows are taken by the warps directly
   }
-  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += THREADS)
+  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += PTHREADS)
     reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
-  for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += THREADS) {
+  for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += PTHREADS) {
     const int r = t / CSW, x = t % CSW;
     if (x <= nbn[2]) {
       const int rz = b0[0] + r / nbn[1], ry = b0[1] + r % nbn[1];
@@ -570,12 +565,9 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   __syncthreads();
   if (*s_any == 0) return;
 
-  // tile origins (array indices)
   const int Lb  = g.nb;
   const int ez0 = b0[0] - g.is_odd - g.half + Lb, ey0 = b0[1] - g.is_odd - g.half + Lb,
             ex0 = b0[2] - g.is_odd - g.half + Lb;
-  const int jz0 = ez0 - 1, jy0 = ey0 - 1, jx0 = ex0 - 1;
-
   if (tid == 0) {
     mbar_init(s_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -585,10 +577,275 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     mbar_expect_tx(s_bar, (uint32_t)(C::EZ * EY * EX * 6 * sizeof(double)));
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
-  for (int t = tid; t < L.j_doubles; t += THREADS) s_j[t] = 0.0;
-  for (int t = tid; t < L.red_doubles; t += THREADS) s_red[t] = 0.0;
-  for (int v = tid; v < PV; v += THREADS) {
-    // plane value v -> (component, jy, jx) in mesh slots (central index + 1)
+
+  const ChunkGeo& c   = *s_cg;
+  const int       cb  = P.sp.cbase[ch];
+  const size_t    cap = P.sp.cap;
+  double* __restrict__ xu = P.sp.xu;
+  double* __restrict__ xv = P.sp.xv;
+  int*          mydc = s_dcnt + warp * 32;
+  double*       my_pf = s_pf + warp * PF_DOUBLES_W;
+  const double* mine  = my_pf + lane;
+  const int     nrow  = nbn[0] * nbn[1];
+
+  // rows of the tile, handed out dynamically; one iteration = 32 consecutive particles of the row
+  auto advance = [&](int& r, int& i0, int& pe) -> bool {
+    i0 += 32;
+    while (i0 >= pe) {
+      int nx = 0;
+      if (lane == 0) nx = atomicAdd(s_next, 1);
+      r = __shfl_sync(FULL, nx, 0);
+      if (r >= nrow) return false;
+      i0 = s_cs[r * CSW];
+      pe = s_cs[r * CSW + nbn[2]];
+    }
+    return true;
+  };
+  auto prefetch = [&](int i) {
+#pragma unroll
+    for (int k = 0; k < 6; k++) cp_async8(my_pf + k * 32 + lane, xu + soa(k, cap, i));
+  };
+
+  int  nr = warp, ni0 = 0, npe = 0;
+  bool have = nr < nrow;
+  if (have) {
+    ni0  = s_cs[nr * CSW] - 32;
+    npe  = s_cs[nr * CSW + nbn[2]];
+    have = advance(nr, ni0, npe);
+  }
+  if (have && ni0 + lane < npe) prefetch(ni0 + lane);
+  cp_async_commit();
+
+  mbar_wait(s_bar, 0);
+
+  int  prev_r = -1, open_lx = -1;
+  bool carry = false; // mydc may hold counts of the open bin
+  int  bz = 0, by = 0;
+  const double* erow = s_eb;
+  const int*    csrow = s_cs;
+
+  while (have) {
+    const int r = nr, i0 = ni0, pe = npe;
+    have = advance(nr, ni0, npe);
+    cp_async_wait_all();
+    if (r != prev_r) {
+      const int lz = (nbn[1] == C::TY) ? r / C::TY : r / nbn[1], ly = r - lz * nbn[1];
+      bz = b0[0] + lz, by = b0[1] + ly;
+      erow    = s_eb + (size_t)((lz * EY + ly) * EX) * 6;
+      csrow   = s_cs + r * CSW;
+      open_lx = -1;
+      carry   = false;
+      prev_r  = r;
+    }
+    const int  i     = i0 + lane;
+    const bool valid = i < pe;
+    int        dir   = 13;
+    int        lxc   = 0;
+
+    if (valid) {
+      const double pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // index 0,1,2 = z,y,x
+      int    ki[3], bh[3], ii[3];
+      double wi[3][N1], wh[3][N1];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        ii[a]  = digitize(pos[a], c.off[a], g.rdel[a]);
+        ki[a]  = ii[a] - g.is_odd;
+        int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
+        shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
+        shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
+        bh[a] = (hh - ki[a] > 0) ? 1 : 0;
+      }
+      // the particle must sit in the bin that owns its slot of the cell-sorted container
+      const int lx = ii[2] - b0[2];
+      lxc          = min(max(lx, 0), nbn[2] - 1);
+      const bool sorted_ok = ii[0] == bz && ii[1] == by && lx == lxc && i >= csrow[lxc] && i < csrow[lxc + 1];
+      if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
+      const double* ecell = erow + lxc * 6;
+
+      double f6[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const bool hz = (0x1C >> k) & 1, hy = (0x2A >> k) & 1, hx = (0x31 >> k) & 1;
+        double     wz[N1], wy[N1], wx[N1];
+#pragma unroll
+        for (int j = 0; j < N1; j++) {
+          wz[j] = hz ? wh[0][j] : wi[0][j];
+          wy[j] = hy ? wh[1][j] : wi[1][j];
+          wx[j] = hx ? wh[2][j] : wi[2][j];
+        }
+        const double* e = ecell + (hz ? bh[0] : 0) * esz + (hy ? bh[1] : 0) * esy + (hx ? bh[2] : 0) * 6 + k;
+        f6[k] = gather1<O, S>(e, wz, wy, wx);
+      }
+      double ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
+      double bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
+
+      // ---- push_boris (primitives.hpp:165-189) ----------------------------------------------
+      double ux = mine[3 * 32], uy = mine[4 * 32], uz = mine[5 * 32];
+      ux = add<S>(ux, ex);
+      uy = add<S>(uy, ey);
+      uz = add<S>(uz, ez);
+      double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+      bxx = mul<S>(bxx, gm);
+      byy = mul<S>(byy, gm);
+      bzz = mul<S>(bzz, gm);
+      double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+      double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+      double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+      double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+      ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
+      uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
+      uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
+
+      // ---- position update (lorentz_factor, primitives.hpp:158-161); the old position goes to the
+      //      temporary array like the reference's xv[0:3] = xu[0:3] (test_esirkepov.cpp:1046-1051)
+      double uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
+      double gam = sqrt_<S>(add<S>(1.0, mul<S>(mul<S>(uu, g.rc), g.rc)));
+      double dtg = div_<S>(P.delt, gam);
+      double pn[3];
+      pn[2] = add<S>(pos[2], mul<S>(ux, dtg));
+      pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
+      pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
+      xv[soa(0, cap, i)] = pos[2];
+      xv[soa(1, cap, i)] = pos[1];
+      xv[soa(2, cap, i)] = pos[0];
+      xu[soa(0, cap, i)] = pn[2];
+      xu[soa(1, cap, i)] = pn[1];
+      xu[soa(2, cap, i)] = pn[0];
+      xu[soa(3, cap, i)] = ux;
+      xu[soa(4, cap, i)] = uy;
+      xu[soa(5, cap, i)] = uz;
+
+      // ---- bin of the new position: count / classify ------------------------------------------
+      int  i1[3];
+      bool cfl_ok = true;
+      int  dcode  = 0;
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        i1[a]  = digitize(pn[a], c.off[a], g.rdel[a]);
+        int dd = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
+        dcode  = dcode * 3 + dd;
+        int sf = (i1[a] - g.is_odd) - ki[a];
+        cfl_ok = cfl_ok && (sf >= -1) && (sf <= 1);
+      }
+      dir            = dcode;
+      const int lnid = (i - cb) & (LANES - 1);
+      if (dir == 13) {
+        int key     = (cellkey0 + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
+        P.sp.key[i] = key;
+        atomicAdd(&P.sp.hist[key], 1);
+      } else {
+        P.sp.key[i] = -1;
+        atomicAdd(&P.sp.oob[ch * LANES + lnid], 1);
+      }
+      if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
+    }
+    __syncwarp();
+    // the staged particles have been consumed: request the next iteration's
+    if (have && ni0 + lane < npe) prefetch(ni0 + lane);
+    cp_async_commit();
+
+    // ---- leavers: ordered rank inside (bin, direction); the counts of the bin that continues into
+    //      the next iteration are carried in mydc ------------------------------------------------
+    const bool     leaver = valid && dir != 13;
+    const unsigned lm     = __ballot_sync(FULL, leaver);
+    if (lm || carry) {
+      const int last_lx = __shfl_sync(FULL, lxc, min(32, pe - i0) - 1);
+      int       rk = 0, cnt = 0;
+      if (leaver) {
+        const unsigned grpm = __match_any_sync(lm, lxc * 32 + dir);
+        rk                  = __popc(grpm & ((1u << lane) - 1));
+        cnt                 = __popc(grpm);
+        const int base      = (carry && lxc == open_lx) ? mydc[dir] : 0;
+        const int rr        = base + rk;
+        const int bb3[3]    = {bz, by, b0[2] + lxc};
+        const int se        = slab_entry(g, dir, bb3);
+        if (se < 0) atomicOr(P.err, NIXB200_ERR_CFL);
+        int slot = atomicAdd(P.sp.nleave, 1);
+        if (slot < P.sp.lcap && se >= 0) P.sp.lrec[slot] = make_int4(i, ch, se, (rr << 5) | dir);
+        else atomicOr(P.err, NIXB200_ERR_CAPACITY);
+        // leavers of (slab bin, direction) so far -> slab counts (scanned by k_mig_scan)
+        if (rk == 0 && se >= 0) atomicMax(&P.sp.slabcnt[(size_t)ch * g.slaboff[27] + se], base + cnt);
+      }
+      __syncwarp();
+      const bool keep = carry && last_lx == open_lx; // the open bin continues
+      if (!keep && lane < 27) mydc[lane] = 0;
+      open_lx = last_lx;
+      __syncwarp();
+      if (leaver && lxc == last_lx && rk == 0) mydc[dir] += cnt;
+      carry = keep || __any_sync(FULL, leaver && lxc == last_lx);
+      __syncwarp();
+    }
+  }
+}
+
+
+template <int O, bool S>
+__global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit(const Kparams P)
+{
+  using C          = Cfg<O>;
+  constexpr int N1 = C::N1;
+  constexpr int NS = C::NS;
+  constexpr int PV = C::PV;
+  const Geo&    g    = P.geo;
+  const int     tid  = threadIdx.x;
+  const int     lane = tid & 31;
+  const int     warp = tid >> 5;
+
+  const int tl = blockIdx.x % g.ntile;
+  const int ch = blockIdx.x / g.ntile;
+  int       b0[3], nbn[3];
+  {
+    int t[3] = {tl / (g.ntl[1] * g.ntl[2]), (tl / g.ntl[2]) % g.ntl[1], tl % g.ntl[2]};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      b0[a]  = t[a] * g.tile[a];
+      nbn[a] = min(g.tile[a], g.nc[a] - b0[a]);
+    }
+  }
+  constexpr int JZ = C::JZ, JY = C::JY, JX = C::JX;
+  constexpr int REC_D = (DWARPS * MAXMOV * CREC + 15) / 16 * 16;
+
+  extern __shared__ __align__(1024) double smem_d[];
+  double*   s_j    = smem_d;
+  double*   s_rec  = s_j + C::J_DOUBLES;
+  double*   s_red  = s_rec + REC_D;
+  double*   s_pf   = s_red + DWARPS * C::SCR;
+  int*      s_int  = reinterpret_cast<int*>(s_pf + DWARPS * PF_DOUBLES_W);
+  int*      s_any  = s_int + ID_ANY;
+  int*      s_next = s_int + ID_NEXT;
+  int*      s_tbl  = s_int + ID_TBL;
+  int*      s_mlst = s_int + ID_MLST;
+  int*      s_cs   = s_int + ID_CS;
+  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + ID_CG);
+
+  const int32_t* __restrict__ start = P.sp.start;
+  const int cellkey0 = ch * g.ncell;
+  constexpr int CSW = C::TX + 1;
+  if (tid == 0) {
+    *s_any  = 0;
+    *s_next = DWARPS;
+  }
+  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += DTHREADS)
+    reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
+  for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += DTHREADS) {
+    const int r = t / CSW, x = t % CSW;
+    if (x <= nbn[2]) {
+      const int rz = b0[0] + r / nbn[1], ry = b0[1] + r % nbn[1];
+      s_cs[t] = start[(cellkey0 + (rz * g.R[1] + ry) * g.R[2] + b0[2] + x) * LANES];
+    }
+  }
+  __syncthreads();
+  if (tid < nbn[0] * nbn[1] && s_cs[tid * CSW + nbn[2]] != s_cs[tid * CSW]) atomicOr(s_any, 1);
+  __syncthreads();
+  if (*s_any == 0) return;
+
+  const int Lb  = g.nb;
+  const int jz0 = b0[0] - g.is_odd - g.half + Lb - 1, jy0 = b0[1] - g.is_odd - g.half + Lb - 1,
+            jx0 = b0[2] - g.is_odd - g.half + Lb - 1;
+
+  for (int t = tid; t < C::J_DOUBLES; t += DTHREADS) s_j[t] = 0.0;
+  for (int t = tid; t < DWARPS * C::SCR; t += DTHREADS) s_red[t] = 0.0;
+  for (int v = tid; v < PV; v += DTHREADS) {
     int comp, jy, jx;
     if (v < C::P_JX) {
       comp = 0, jy = v / N1, jx = v % N1;
@@ -606,52 +863,60 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
   }
   __syncthreads();
 
-  const ChunkGeo& c   = *s_cg; // staged in shared memory: read again and again by every iteration
-  const int       cb  = P.sp.cbase[ch];
+  const ChunkGeo& c   = *s_cg;
   const size_t    cap = P.sp.cap;
-  double* __restrict__ xu = P.sp.xu;
+  const double* __restrict__ xu = P.sp.xu; // new positions
+  const double* __restrict__ xv = P.sp.xv; // old positions (written by k_push)
   double* myrec = s_rec + (size_t)warp * MAXMOV * CREC;
   MoverGeo mgeo;
 #pragma unroll
   for (int a = 0; a < 3; a++) mgeo.del[a] = g.del[a], mgeo.rdel[a] = g.rdel[a];
   mgeo.is_odd = g.is_odd;
-  int*    mydc  = s_dcnt + warp * 32;
   int*    myml  = s_mlst + warp * MAXMOV;
-
-  mbar_wait(s_bar, 0);
-
-  double* my_red = s_red + warp * RED_DOUBLES_W;
+  double* my_red = s_red + warp * C::SCR;
   double* my_pf  = s_pf + warp * PF_DOUBLES_W;
-  constexpr int NPASS = C::NPASS;
+  const double* mine = my_pf + lane;
 
-  // running sums of the current bin: bsum[z][p] = value 16p + (lane>>1) of plane z
-  double bsum[N1][NPASS];
+  // deposit role of the lane: particle slot ps, z-plane pl (lanes with pl >= N1 idle along)
+  constexpr int PLW = C::PLW, NPS = C::NPS;
+  const int     ps = lane / PLW, pl = lane % PLW;
+  const bool    pl_on = pl < N1;
+  const int     plc   = pl_on ? pl : N1 - 1;
+  double acc[PV];
 #pragma unroll
-  for (int z = 0; z < N1; z++)
-#pragma unroll
-    for (int p = 0; p < NPASS; p++) bsum[z][p] = 0.0;
-  // add the running sums of a finished bin to the J tile (one lane of each pair per value)
+  for (int v = 0; v < PV; v++) acc[v] = 0.0;
   auto flush_bin = [&](int cellbase) {
+    constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
+    const bool    h1 = lane & 16, h2 = lane & 8, h3 = lane & 4, h4 = lane & 2;
+    bfly_stage<PV>(acc, h1, 16);
+    bfly_stage<n1>(acc, h2, 8);
+    bfly_stage<n2>(acc, h3, 4);
+    if constexpr (PLW == 2) bfly_stage<n3>(acc, h4, 2);
+    constexpr int nf = (PLW == 2) ? n4 : n3;
+    double* const dst = s_j + cellbase + (pl + 1) * JY * JX;
 #pragma unroll
-    for (int z = 0; z < N1; z++)
-#pragma unroll
-      for (int p = 0; p < NPASS; p++) {
-        const int    v   = p * RROWS + (lane >> 1);
-        const double val = bsum[z][p];
-        if ((lane & 1) == (p & 1) && v < PV && val != 0.0) // both lanes of a pair hold the sum: share the passes
-          atomicAdd(s_j + cellbase + (z + 1) * JY * JX + s_tbl[v], val);
-        bsum[z][p] = 0.0;
+    for (int j = 0; j < nf; j++) {
+      int  i3 = j;
+      bool ok = true;
+      if constexpr (PLW == 2) {
+        i3 = j + (h4 ? n4 : 0);
+        ok = i3 < n3;
       }
+      const int i2 = i3 + (h3 ? n3 : 0);
+      const int i1 = i2 + (h2 ? n2 : 0);
+      const int v  = i1 + (h1 ? n1 : 0);
+      ok = ok && i2 < n2 && i1 < n1 && v < PV && pl_on;
+      const double val = acc[j];
+      if (ok && val != 0.0) atomicAdd(dst + s_tbl[v], val);
+    }
+#pragma unroll
+    for (int v = 0; v < PV; v++) acc[v] = 0.0;
   };
 
-  // ---- bins of the tile, handed out dynamically; one iteration = up to 32 particles of one bin.
-  //      The loop is flat and software-pipelined: the particle data of the NEXT iteration is
-  //      requested (cp.async into the warp's staging buffer) before the current one is processed.
   const int ncell_t = nbn[0] * nbn[1] * nbn[2];
-  // state of an iteration: bin cl = r * nbn[2] + lx (r = row lz * nbn[1] + ly), particles [i0, pe)
   auto advance = [&](int& cl, int& r, int& lx, int& i0, int& pe) -> bool {
     i0 += 32;
-    while (i0 >= pe) { // next non-empty bin
+    while (i0 >= pe) {
       int nx = 0;
       if (lane == 0) nx = atomicAdd(s_next, 1);
       cl = __shfl_sync(FULL, nx, 0);
@@ -663,9 +928,12 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     }
     return true;
   };
-  auto prefetch = [&](int stage, int i) {
+  auto prefetch = [&](int i) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) cp_async8(my_pf + (stage * 6 + k) * 32 + lane, xu + soa(k, cap, i));
+    for (int k = 0; k < 3; k++) {
+      cp_async8(my_pf + k * 32 + lane, xv + soa(k, cap, i));       // old x y z
+      cp_async8(my_pf + (3 + k) * 32 + lane, xu + soa(k, cap, i)); // new x y z
+    }
   };
 
   int  ncl = warp, nr = 0, nlx = 0, ni0 = 0, npe = 0;
@@ -677,228 +945,53 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
     npe  = s_cs[nr * CSW + nlx + 1];
     have = advance(ncl, nr, nlx, ni0, npe);
   }
-  int stage = 0;
-  if (have && ni0 + lane < npe) prefetch(0, ni0 + lane);
+  if (have && ni0 + lane < npe) prefetch(ni0 + lane);
   cp_async_commit();
 
-  int  prev_cl = -1, nrec = 0;
-  int  bz = 0, by = 0, bx = 0, cellbase = 0;
-  bool had_leav = false; // warp-uniform
-  const double* ecell = s_eb;
+  int prev_cl = -1, nrec = 0;
+  int bz = 0, by = 0, bx = 0, cellbase = 0;
 
   while (have) {
     const int cl = ncl, cr = nr, clx = nlx, i0 = ni0, pe = npe;
     have = advance(ncl, nr, nlx, ni0, npe);
     cp_async_wait_all();
-    double cur[6];
-#pragma unroll
-    for (int k = 0; k < 6; k++) cur[k] = my_pf[(stage * 6 + k) * 32 + lane];
-    stage ^= 1;
-    if (have && ni0 + lane < npe) prefetch(stage, ni0 + lane);
-    cp_async_commit();
-
     if (cl != prev_cl) { // first iteration of a bin
-      if (prev_cl >= 0) flush_bin(cellbase);
       const int lx = clx, lz = (nbn[1] == C::TY) ? cr / C::TY : cr / nbn[1], ly = cr - lz * nbn[1];
       bz = b0[0] + lz, by = b0[1] + ly, bx = b0[2] + lx;
       cellbase = (lz * JY + ly) * JX + lx; // J-tile node of mesh slot (0,0,0)
-      ecell    = s_eb + (size_t)((lz * EY + ly) * EX + lx) * 6;
-      had_leav = false;
       prev_cl  = cl;
-      __syncwarp();
-      if (lane < 27) mydc[lane] = 0;
-      __syncwarp();
     }
     {
       const int  i     = i0 + lane;
       const bool valid = i < pe;
-      int        dir   = 13;
       bool       dep_ok = false, mover = false;
       int        mcode = -1; // single-axis mover: axis*2 + (1 if high side); -1: multi-axis
-      Wts<O>     w;
-      double     mvn[3] = {0.0, 0.0, 0.0}; // new position (z,y,x), for the mover record
+      double     pn[3] = {0.0, 0.0, 0.0};
+      double     wi[3][N1];
+      int        ki[3] = {0, 0, 0}, sft[3] = {0, 0, 0};
 
-      // =============================== push ===============================
       if (valid) {
-        const double pos[3] = {cur[2], cur[1], cur[0]}; // index 0,1,2 = z,y,x
-        const double u[3]   = {cur[5], cur[4], cur[3]};
-
-        int    ki[3], bh[3];
-        double wi[3][N1], wh[3][N1];
-        bool   sorted_ok = true;
+        const double pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // old z,y,x
+        pn[0] = mine[5 * 32], pn[1] = mine[4 * 32], pn[2] = mine[3 * 32];
+        bool sorted_ok = true, cfl_ok = true;
+        int  nmove = 0;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          int ii = digitize(pos[a], c.off[a], g.rdel[a]);
-          ki[a]  = ii - g.is_odd;
-          int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
+          const int ii = digitize(pos[a], c.off[a], g.rdel[a]);
+          ki[a]        = ii - g.is_odd;
           shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
-          shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
-          // interp::shift_weights<O>(hh - ki, wh)  interp.hpp:154-160: the half-grid support starts
-          // one node later; kept as a base offset instead of moving the weights
-          bh[a]     = (hh - ki[a] > 0) ? 1 : 0;
           sorted_ok = sorted_ok && (ii == ((a == 0) ? bz : ((a == 1) ? by : bx)));
-        }
-        if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
-
-        // ---- gather: Ex Ey Ez Bx By Bz; half-grid axes: Ex x | Ey y | Ez z | Bx y,z | By x,z | Bz x,y
-        // one loop body for the six components (code size: the loop must stay instruction-cache
-        // resident); the results shift through f6 so that no register array is indexed dynamically
-        double f6[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) f6[k] = 0.0;
-#if NIX_GATHER_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1
-#endif
-        for (int k = 0; k < 6; k++) {
-          const bool hz = (0x1C >> k) & 1, hy = (0x2A >> k) & 1, hx = (0x31 >> k) & 1;
-          double     wz[N1], wy[N1], wx[N1];
-#pragma unroll
-          for (int j = 0; j < N1; j++) {
-            wz[j] = hz ? wh[0][j] : wi[0][j];
-            wy[j] = hy ? wh[1][j] : wi[1][j];
-            wx[j] = hx ? wh[2][j] : wi[2][j];
-          }
-          const double* e = ecell + (hz ? bh[0] : 0) * esz + (hy ? bh[1] : 0) * esy + (hx ? bh[2] : 0) * 6 + k;
-          const double  f = gather1<O, S>(e, wz, wy, wx);
-#pragma unroll
-          for (int q = 0; q < 5; q++) f6[q] = f6[q + 1];
-          f6[5] = f;
-        }
-        double ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
-        double bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
-
-        // ---- push_boris (primitives.hpp:165-189) ----------------------------------------------
-        double ux = u[2], uy = u[1], uz = u[0];
-        ux = add<S>(ux, ex);
-        uy = add<S>(uy, ey);
-        uz = add<S>(uz, ez);
-        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
-        bxx = mul<S>(bxx, gm);
-        byy = mul<S>(byy, gm);
-        bzz = mul<S>(bzz, gm);
-        double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
-        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
-        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
-        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
-        ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
-        uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
-        uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
-
-        // ---- position update (lorentz_factor, primitives.hpp:158-161) ------------------------
-        double uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
-        double gam = sqrt_<S>(add<S>(1.0, mul<S>(mul<S>(uu, g.rc), g.rc)));
-        double dtg = div_<S>(P.delt, gam);
-        double pn[3];
-        pn[2] = add<S>(pos[2], mul<S>(ux, dtg));
-        pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
-        pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
-
-        mvn[0] = pn[0], mvn[1] = pn[1], mvn[2] = pn[2];
-        xu[soa(0, cap, i)] = pn[2];
-        xu[soa(1, cap, i)] = pn[1];
-        xu[soa(2, cap, i)] = pn[0];
-        xu[soa(3, cap, i)] = ux;
-        xu[soa(4, cap, i)] = uy;
-        xu[soa(5, cap, i)] = uz;
-
-        // ---- bin of the new position: count / classify ------------------------------------------
-        int  i1[3], sft[3];
-        bool cfl_ok = true;
-        int  dcode  = 0, nmove = 0;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-          i1[a]  = digitize(pn[a], c.off[a], g.rdel[a]);
-          int dd = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
-          dcode  = dcode * 3 + dd;
-          sft[a] = (i1[a] - g.is_odd) - ki[a];
-          cfl_ok = cfl_ok && (sft[a] >= -1) && (sft[a] <= 1);
+          const int i1 = digitize(pn[a], c.off[a], g.rdel[a]);
+          sft[a]       = (i1 - g.is_odd) - ki[a];
+          cfl_ok       = cfl_ok && (sft[a] >= -1) && (sft[a] <= 1);
           if (sft[a] != 0) {
             nmove++;
             mcode = a * 2 + (sft[a] > 0 ? 1 : 0);
           }
         }
-        dir            = dcode;
-        const int lnid = (i - cb) & (LANES - 1);
-        if (dir == 13) {
-          int key     = (cellkey0 + (i1[0] * g.R[1] + i1[1]) * g.R[2] + i1[2]) * LANES + lnid;
-          P.sp.key[i] = key;
-          atomicAdd(&P.sp.hist[key], 1);
-        } else {
-          P.sp.key[i] = -1;
-          atomicAdd(&P.sp.oob[ch * LANES + lnid], 1);
-        }
-        if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
-        dep_ok = cfl_ok && sorted_ok;
+        dep_ok = cfl_ok && sorted_ok; // (both flags are raised by k_push)
         mover  = dep_ok && nmove > 0;
         if (nmove > 1) mcode = -1;
-
-        // ---- 1-D deposit weights -------------------------------------------------------------------
-        // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085)
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-          double wn[N1];
-          int    k1 = i1[a] - g.is_odd;
-          shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
-          double cp = 0.0;
-#pragma unroll
-          for (int j = 0; j < NS; j++) {
-            double s0 = (j >= 1 && j <= O + 1) ? wi[a][j - 1] : 0.0;
-            double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // sft = -1 : slot j <- wn[j]
-            double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // sft =  0
-            double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // sft = +1
-            double s1 = (sft[a] == 0) ? v0 : ((sft[a] < 0) ? vm : vp);
-            if (!dep_ok) {
-              s0 = 0.0;
-              s1 = 0.0;
-            }
-            const double ds = s1 - s0; // ds3d, esirkepov.hpp:167-174
-            if (j >= 1 && j <= N1) {
-              w.s0[a][j - 1] = s0;
-              w.ds[a][j - 1] = ds;
-              w.cp[a][j - 1] = cp;
-            }
-            cp += ds;
-          }
-        }
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int j = 0; j < N1; j++) w.s0[a][j] = w.ds[a][j] = w.cp[a][j] = 0.0;
-      }
-
-      // ---- leavers: ordered rank inside this bin per direction (warp shuffles) -----------------------
-      const bool     leaver = valid && dir != 13;
-      const unsigned lm     = __ballot_sync(FULL, leaver);
-      if (lm) {
-        had_leav = true;
-        if (leaver) {
-          const unsigned grpm = __match_any_sync(lm, dir);
-          const int      rk   = __popc(grpm & ((1u << lane) - 1));
-          const int      r    = mydc[dir] + rk;
-          const int      bb3[3] = {bz, by, bx};
-          const int      se   = slab_entry(g, dir, bb3);
-          if (se < 0) atomicOr(P.err, NIXB200_ERR_CFL);
-          int slot = atomicAdd(P.sp.nleave, 1);
-          if (slot < P.sp.lcap && se >= 0) P.sp.lrec[slot] = make_int4(i, ch, se, (r << 5) | dir);
-          else atomicOr(P.err, NIXB200_ERR_CAPACITY);
-          __syncwarp(lm);
-          if (rk == 0) mydc[dir] += __popc(grpm);
-        }
-        __syncwarp();
-      }
-
-      // =============================== deposit ===============================
-      // plane by plane: evaluate on the lane's registers, sum the 32 lanes through the scratch
-#pragma unroll
-      for (int z = 0; z < N1; z++) {
-        double acc[PV];
-#pragma unroll
-        for (int v = 0; v < PV; v++) acc[v] = 0.0;
-        plane_accumulate<O>(w.s0[0][z], w.ds[0][z], w.cp[0][z], z >= 1, w, P.q, P.qdxdt, acc);
-        plane_reduce<O>(acc, my_red, lane, bsum[z]);
       }
 
       // ---- movers: compact record (old / new position, bin); the list is flushed when it is full ----
@@ -909,8 +1002,8 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
         const bool take = mover && ((mm >> lane) & 1u) && rk < room;
         if (take) {
           double* r = myrec + (nrec + rk) * CREC;
-          r[0] = cur[2], r[1] = cur[1], r[2] = cur[0]; // old z, y, x
-          r[3] = mvn[0], r[4] = mvn[1], r[5] = mvn[2]; // new z, y, x
+          r[0] = mine[2 * 32], r[1] = mine[1 * 32], r[2] = mine[0]; // old z, y, x
+          r[3] = pn[0], r[4] = pn[1], r[5] = pn[2];                   // new z, y, x
           int* ri = reinterpret_cast<int*>(r + 6);
           ri[0]   = cellbase;
           ri[1]   = mcode;
@@ -925,25 +1018,75 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
           nrec = 0;
         }
       }
-    }
-
-    // last iteration of a bin: its leavers per direction -> slab counts (scanned by k_mig_scan)
-    if (had_leav && (!have || ncl != cl)) {
       __syncwarp();
-      if (lane < 27 && lane != 13 && mydc[lane] > 0) {
-        const int bb3[3] = {bz, by, bx};
-        const int se     = slab_entry(g, lane, bb3);
-        if (se >= 0) P.sp.slabcnt[(size_t)ch * g.slaboff[27] + se] = mydc[lane];
+      // the staged positions have been consumed: request the next iteration's
+      if (have && ni0 + lane < npe) prefetch(ni0 + lane);
+      cp_async_commit();
+
+      // ---- 1-D deposit weights, axis by axis straight into the warp's scratch --------------------
+      // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085);
+      // a particle that may not deposit (out of its bin / more than one bin per step) leaves zeros
+      {
+        double2* q2 = reinterpret_cast<double2*>(my_red);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+          double s0[N1], ds[N1], cp[N1];
+          if (valid && dep_ok) {
+            double wn[N1];
+            int    k1 = ki[a] + sft[a];
+            shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
+            double run = (sft[a] < 0) ? wn[0] : 0.0; // DS of mesh slot 0 (ds3d, esirkepov.hpp:167-174)
+#pragma unroll
+            for (int j = 0; j < N1; j++) { // central slots j + 1
+              const double vm = (j + 1 <= O) ? wn[j + 1] : 0.0; // sft = -1 : slot <- wn[slot]
+              const double v0 = wn[j];                           // sft =  0
+              const double vp = (j >= 1) ? wn[j - 1] : 0.0;      // sft = +1
+              const double s1 = (sft[a] == 0) ? v0 : ((sft[a] < 0) ? vm : vp);
+              s0[j] = wi[a][j];
+              ds[j] = s1 - s0[j];
+              cp[j] = run;
+              run += ds[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < N1; j++) s0[j] = ds[j] = cp[j] = 0.0;
+          }
+          if (a == 0) {
+#pragma unroll
+            for (int z = 0; z < N1; z++) {
+              q2[C::WQ_Z / 2 + z * 32 + lane] = make_double2(s0[z], ds[z]);
+              if (z >= 1) my_red[C::WQ_ZC + (z - 1) * 32 + lane] = cp[z];
+            }
+          } else {
+            constexpr int NPR = C::NPR;
+            double        t[2 * NPR];
+#pragma unroll
+            for (int j = 0; j < N1; j++) {
+              t[j]      = s0[j];
+              t[N1 + j] = ds[j];
+              if (j >= 1) t[2 * N1 + j - 1] = cp[j];
+            }
+            if (3 * N1 - 1 < 2 * NPR) t[2 * NPR - 1] = 0.0;
+#pragma unroll
+            for (int pr = 0; pr < NPR; pr++) q2[((a - 1) * NPR + pr) * 32 + lane] = make_double2(t[2 * pr], t[2 * pr + 1]);
+          }
+        }
       }
+      __syncwarp();
+      {
+        const int nround = (min(32, pe - i0) + NPS - 1) / NPS;
+        for (int r = 0; r < nround; r++) deposit_round<O>(my_red, r * NPS + ps, plc, pl_on, P.q, P.qdxdt, acc);
+      }
+      __syncwarp();
     }
+    if (!have || ncl != cl) flush_bin(cellbase); // last iteration of a bin: its current -> J tile
   }
-  if (prev_cl >= 0) flush_bin(cellbase);
   if (nrec) flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
 
   // ---- flush the J tile: the CTA's single scatter to global memory --------------------------------
   __syncthreads();
   double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
-  for (int t = tid; t < JZ * JY * JX * 4; t += THREADS) {
+  for (int t = tid; t < JZ * JY * JX * 4; t += DTHREADS) {
     const double v = s_j[(t & 3) * C::JC + (t >> 2)];
     if (v != 0.0) {
       const int k = t & 3, n = t >> 2;
@@ -955,7 +1098,7 @@ __global__ void __launch_bounds__(THREADS, NIX_PUSH_MINB) k_push_deposit(const _
 }
 
 template <int O, bool S>
-int launch_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st)
+int launch_split_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st, cudaEvent_t* ev)
 {
   Kparams P;
   P.geo  = a.geo;
@@ -967,25 +1110,34 @@ int launch_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st)
   P.q    = a.sp.q;
   for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
   P.err = a.err;
-  size_t smem = smem_layout<O>().bytes;
   static bool attr_set = false;
   if (!attr_set) {
-    NIX_CUDA(cudaFuncSetAttribute(k_push_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    NIX_CUDA(cudaFuncSetAttribute(k_push<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    NIX_CUDA(cudaFuncSetAttribute(k_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     attr_set = true;
   }
   int nblocks = a.geo.nchunk * a.geo.ntile;
-  k_push_deposit<O, S><<<nblocks, THREADS, smem, st>>>(*tmap, P);
+  if (ev) cudaEventRecord(ev[0], st);
+  k_push<O, S><<<nblocks, PTHREADS, push_smem<O>(), st>>>(*tmap, P);
   NIX_LAUNCHED();
+  if (ev) {
+    cudaEventRecord(ev[1], st);
+    cudaEventRecord(ev[2], st);
+  }
+  k_deposit<O, S><<<nblocks, DTHREADS, deposit_smem<O>(), st>>>(P);
+  NIX_LAUNCHED();
+  if (ev) cudaEventRecord(ev[3], st);
   return 0;
 }
+
 } // namespace
 
 size_t push_smem_bytes(const Geo& g)
 {
   switch (g.order) {
-  case 1: return smem_layout<1>().bytes;
-  case 2: return smem_layout<2>().bytes;
-  default: return smem_layout<3>().bytes;
+  case 1: return std::max(push_smem<1>(), deposit_smem<1>());
+  case 2: return std::max(push_smem<2>(), deposit_smem<2>());
+  default: return std::max(push_smem<3>(), deposit_smem<3>());
   }
 }
 
@@ -1015,16 +1167,16 @@ int choose_push_tile(Geo& g)
   return 0;
 }
 
-int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st)
+int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st, cudaEvent_t* ev)
 {
   // leaver bookkeeping of this step
   NIX_CUDA(cudaMemsetAsync(a.sp.slabcnt, 0, sizeof(int32_t) * (size_t)a.geo.nchunk * a.geo.slaboff[27], st));
   NIX_CUDA(cudaMemsetAsync(a.sp.oob, 0, sizeof(int32_t) * a.geo.nchunk * LANES, st));
   NIX_CUDA(cudaMemsetAsync(a.sp.nleave, 0, sizeof(int32_t), st));
   switch (a.geo.order) {
-  case 1: return strict ? launch_t<1, true>(a, tmap, st) : launch_t<1, false>(a, tmap, st);
-  case 2: return strict ? launch_t<2, true>(a, tmap, st) : launch_t<2, false>(a, tmap, st);
-  case 3: return strict ? launch_t<3, true>(a, tmap, st) : launch_t<3, false>(a, tmap, st);
+  case 1: return strict ? launch_split_t<1, true>(a, tmap, st, ev) : launch_split_t<1, false>(a, tmap, st, ev);
+  case 2: return strict ? launch_split_t<2, true>(a, tmap, st, ev) : launch_split_t<2, false>(a, tmap, st, ev);
+  case 3: return strict ? launch_split_t<3, true>(a, tmap, st, ev) : launch_split_t<3, false>(a, tmap, st, ev);
   default: set_error("order must be 1, 2 or 3"); return 1;
   }
 }
