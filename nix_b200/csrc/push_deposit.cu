@@ -273,20 +273,6 @@ __device__ __forceinline__ void deposit_round(const double* wq, int p, int plc, 
   plane_accumulate<O>(s0z, dsz, cpz, ty, tx, q, qd, acc);
 }
 
-// One halving stage of the slot butterfly: x[0..N) -> x[0..(N+1)/2); the lane whose slot bit is set
-// keeps the upper half (index i + M), the other one the lower half.
-template <int N>
-__device__ __forceinline__ void bfly_stage(double* x, bool hi, int mask)
-{
-  constexpr int M = (N + 1) / 2;
-#pragma unroll
-  for (int i = 0; i < M; i++) {
-    const double lo = x[i], up = (i + M < N) ? x[i + M] : 0.0;
-    const double send = hi ? lo : up, keep = hi ? up : lo;
-    x[i] = keep + __shfl_xor_sync(FULL, send, mask);
-  }
-}
-
 // N independent fp64 additions to shared memory.  fp64 shared-memory atomics are compare-and-swap
 // loops; running the N loops of a lane in lock step overlaps their round trips.
 template <int N>
@@ -328,14 +314,11 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
   const int     lane = threadIdx.x & 31;
   __syncwarp();
   // single-axis movers: lanes = (record, face node (u,v)), N1*N1 nodes each
-  int nsingle = 0;
-  for (int m = 0; m < nrec; m++) {
-    const int* ri = reinterpret_cast<const int*>(myrec + m * C::REC + 9 * NS);
-    if (ri[1] >= 0) {
-      if (lane == 0) myml[nsingle] = m;
-      nsingle++;
-    }
-  }
+  const int      mycode = (lane < nrec) ? reinterpret_cast<const int*>(myrec + lane * C::REC + 9 * NS)[1] : 0;
+  const unsigned single = __ballot_sync(FULL, lane < nrec && mycode >= 0);
+  unsigned       multi  = __ballot_sync(FULL, lane < nrec && mycode < 0);
+  const int      nsingle = __popc(single);
+  if (lane < nrec && mycode >= 0) myml[__popc(single & ((1u << lane) - 1))] = lane;
   __syncwarp();
   const double A = 1.0 / 2, B = 1.0 / 3;
   auto         node = [&](const double* r, int jz, int jy, int jx, double& rho, double& wx, double& wy, double& wz) {
@@ -375,10 +358,11 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
     }
   }
   // multi-axis movers: the whole (O+3)^3 mesh minus what the register path already holds
-  for (int m = 0; m < nrec; m++) {
+  while (multi) {
+    const int m = __ffs(multi) - 1;
+    multi &= multi - 1;
     const double* r  = myrec + m * C::REC;
     const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
-    if (ri[1] >= 0) continue;
     const int cbase = ri[0];
     for (int n = lane; n < NS * NS * NS; n += 32) {
       const int  jz = n / (NS * NS), jy = (n / NS) % NS, jx = n % NS;
@@ -885,30 +869,37 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   double acc[PV];
 #pragma unroll
   for (int v = 0; v < PV; v++) acc[v] = 0.0;
+  // bin finished: sum the accumulators of the NPS slots through the (now idle) scratch -- lanes store
+  // [value][lane], then lane g adds up the NPS entries of (value, plane) group g -- and add the sums
+  // to the J tile.  Row stride 32 + N1: the strided 64-bit loads of 16 consecutive groups hit 16
+  // different bank pairs.
   auto flush_bin = [&](int cellbase) {
-    constexpr int n1 = (PV + 1) / 2, n2 = (n1 + 1) / 2, n3 = (n2 + 1) / 2, n4 = (n3 + 1) / 2;
-    const bool    h1 = lane & 16, h2 = lane & 8, h3 = lane & 4, h4 = lane & 2;
-    bfly_stage<PV>(acc, h1, 16);
-    bfly_stage<n1>(acc, h2, 8);
-    bfly_stage<n2>(acc, h3, 4);
-    if constexpr (PLW == 2) bfly_stage<n3>(acc, h4, 2);
-    constexpr int nf = (PLW == 2) ? n4 : n3;
-    double* const dst = s_j + cellbase + (pl + 1) * JY * JX;
+    constexpr int RS  = 32 + N1;
+    constexpr int NCH = (PV * RS + C::SCR - 1) / C::SCR; // chunks of values that fit the scratch
+    constexpr int VCH = (PV + NCH - 1) / NCH;
+    constexpr int G   = VCH * N1;
+    static_assert(VCH * RS <= C::SCR, "value chunk must fit the scratch");
 #pragma unroll
-    for (int j = 0; j < nf; j++) {
-      int  i3 = j;
-      bool ok = true;
-      if constexpr (PLW == 2) {
-        i3 = j + (h4 ? n4 : 0);
-        ok = i3 < n3;
+    for (int ch = 0; ch < NCH; ch++) {
+      __syncwarp();
+#pragma unroll
+      for (int vv = 0; vv < VCH; vv++)
+        if (ch * VCH + vv < PV) my_red[vv * RS + lane] = acc[ch * VCH + vv];
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < (G + 31) / 32; k++) {
+        const int gi = lane + 32 * k;
+        const int vv = gi / N1, plg = gi - vv * N1, v = ch * VCH + vv;
+        if (gi < G && v < PV) {
+          const double* src = my_red + vv * RS + plg;
+          double        sum = 0.0;
+#pragma unroll
+          for (int q = 0; q < NPS; q++) sum += src[q * PLW];
+          if (sum != 0.0) atomicAdd(s_j + cellbase + (plg + 1) * JY * JX + s_tbl[v], sum);
+        }
       }
-      const int i2 = i3 + (h3 ? n3 : 0);
-      const int i1 = i2 + (h2 ? n2 : 0);
-      const int v  = i1 + (h1 ? n1 : 0);
-      ok = ok && i2 < n2 && i1 < n1 && v < PV && pl_on;
-      const double val = acc[j];
-      if (ok && val != 0.0) atomicAdd(dst + s_tbl[v], val);
     }
+    __syncwarp();
 #pragma unroll
     for (int v = 0; v < PV; v++) acc[v] = 0.0;
   };
