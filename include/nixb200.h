@@ -86,6 +86,15 @@ int nixb200_chunk_field_download(nixb200_domain* d, int k, int which, double* ho
  * call nixb200_domain_synchronize before reusing / reading the host buffer */
 int nixb200_domain_field_upload_async(nixb200_domain* d, int which, const double* host);
 int nixb200_domain_field_download_async(nixb200_domain* d, int which, double* host);
+/* Overlapped variants: the copy runs on a second stream of the domain and is ordered by events against
+ * the phases that touch the array (uf: push_deposit / exchange_field, uj: clear_current / push_deposit /
+ * exchange_current).  A download of uj issued after exchange_current and an upload of the next step's uf
+ * issued after exchange_field run while the main stream migrates and sorts particles (the slot where
+ * Chunk-side code of a nix application solves the fields, application.cpp:63-69).  `host` must be
+ * page-locked for the copy to be asynchronous; copy_synchronize waits for the copies only. */
+int nixb200_domain_field_upload_overlapped(nixb200_domain* d, int which, const double* host);
+int nixb200_domain_field_download_overlapped(nixb200_domain* d, int which, double* host);
+int nixb200_domain_copy_synchronize(nixb200_domain* d);
 /* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each */
 int nixb200_domain_set_particles(nixb200_domain* d, int is, const double* xu_aos,
                                  const int64_t* np_chunk);

@@ -335,6 +335,11 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
   if (cudaMalloc(&d->halo_buf, d->halo_buf_bytes) != cudaSuccess) return fail("cudaMalloc halo");
   cudaEventCreate(&d->ev0);
   cudaEventCreate(&d->ev1);
+  if (cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking) != cudaSuccess) return fail("copy stream");
+  for (int w = 0; w < 2; w++) {
+    cudaEventCreateWithFlags(&d->ev_main_done[w], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&d->ev_copy_done[w], cudaEventDisableTiming);
+  }
 
   d->sp.resize(desc->ns);
   for (int is = 0; is < desc->ns; is++) {
@@ -374,6 +379,11 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->halo_buf) cudaFree(d->halo_buf);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
+  for (int w = 0; w < 2; w++) {
+    if (d->ev_main_done[w]) cudaEventDestroy(d->ev_main_done[w]);
+    if (d->ev_copy_done[w]) cudaEventDestroy(d->ev_copy_done[w]);
+  }
+  if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
   return 0;
@@ -446,6 +456,60 @@ int nixb200_domain_field_download_async(nixb200_domain* dd, int which, double* h
   int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
   const double* src = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
   NIX_CUDA(cudaMemcpyAsync(host, src, sizeof(double) * nc * d->cells_per_chunk * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
+  return 0;
+}
+
+// ---- overlapped transfers: the copy runs on the domain's second stream, ordered against the phases
+//      that touch the array (uf: push_deposit, exchange_field; uj: clear_current, push_deposit,
+//      exchange_current) by events, so that e.g. the download of J and the upload of the next E/B
+//      run while the main stream is still migrating and sorting particles ------------------------
+static int field_index(int which) { return which == NIXB200_FIELD_UF ? 0 : 1; }
+
+// main-stream phases call this before touching the array
+static int wait_copy(Domain* d, int w)
+{
+  if (d->copy_pending[w]) {
+    NIX_CUDA(cudaStreamWaitEvent(d->stream, d->ev_copy_done[w], 0));
+    d->copy_pending[w] = false;
+  }
+  return 0;
+}
+// ... and this after their last access of the step
+static int mark_main_done(Domain* d, int w)
+{
+  NIX_CUDA(cudaEventRecord(d->ev_main_done[w], d->stream));
+  return 0;
+}
+
+static int field_copy_overlapped(Domain* d, int which, double* host, bool upload)
+{
+  if (!d || !host) return 1;
+  const int    w     = field_index(which);
+  const size_t bytes = sizeof(double) * (w == 0 ? 6 : 4) * d->cells_per_chunk * d->geo.nchunk;
+  double*      dev   = (w == 0) ? d->uf : d->uj;
+  NIX_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_main_done[w], 0)); // no-op before the first phase
+  if (upload) NIX_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+  else NIX_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+  NIX_CUDA(cudaEventRecord(d->ev_copy_done[w], d->copy_stream));
+  d->copy_pending[w] = true;
+  return 0;
+}
+
+int nixb200_domain_field_upload_overlapped(nixb200_domain* dd, int which, const double* host)
+{
+  return field_copy_overlapped(D(dd), which, const_cast<double*>(host), true);
+}
+
+int nixb200_domain_field_download_overlapped(nixb200_domain* dd, int which, double* host)
+{
+  return field_copy_overlapped(D(dd), which, host, false);
+}
+
+int nixb200_domain_copy_synchronize(nixb200_domain* dd)
+{
+  Domain* d = D(dd);
+  if (!d) return 1;
+  NIX_CUDA(cudaStreamSynchronize(d->copy_stream));
   return 0;
 }
 
@@ -604,6 +668,7 @@ int nixb200_domain_clear_current(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  if (wait_copy(d, 1)) return 1;
   NIX_CUDA(cudaMemsetAsync(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * d->geo.nchunk, d->stream));
   return 0;
 }
@@ -612,6 +677,7 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
 {
   Domain* d = D(dd);
   if (!d) return 1;
+  if (wait_copy(d, 0) || wait_copy(d, 1)) return 1;
   PhaseTimer pt(d, 0);
   NIX_CUDA(cudaEventRecord(d->ev0, d->stream));
   for (auto& s : d->sp) {
@@ -640,18 +706,26 @@ int nixb200_domain_exchange_current(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
-  PhaseTimer pt(d, 1);
-  if (peer_exchange_halo(d, NIXB200_MODE_CURRENT)) return 1;
-  return launch_halo_current(d->geo, d->cg_dev, d->uj, peer_tabs(d), peer_recvbuf(d), d->stream);
+  if (wait_copy(d, 1)) return 1;
+  {
+    PhaseTimer pt(d, 1);
+    if (peer_exchange_halo(d, NIXB200_MODE_CURRENT)) return 1;
+    if (launch_halo_current(d->geo, d->cg_dev, d->uj, peer_tabs(d), peer_recvbuf(d), d->stream)) return 1;
+  }
+  return mark_main_done(d, 1);
 }
 
 int nixb200_domain_exchange_field(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 1;
-  PhaseTimer pt(d, 2);
-  if (peer_exchange_halo(d, NIXB200_MODE_FIELD)) return 1;
-  return launch_halo_field(d->geo, d->cg_dev, d->uf, peer_tabs(d), peer_recvbuf(d), d->stream);
+  if (wait_copy(d, 0)) return 1;
+  {
+    PhaseTimer pt(d, 2);
+    if (peer_exchange_halo(d, NIXB200_MODE_FIELD)) return 1;
+    if (launch_halo_field(d->geo, d->cg_dev, d->uf, peer_tabs(d), peer_recvbuf(d), d->stream)) return 1;
+  }
+  return mark_main_done(d, 0);
 }
 
 int nixb200_domain_migrate_sort(nixb200_domain* dd)

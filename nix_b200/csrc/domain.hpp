@@ -26,6 +26,12 @@ struct Domain {
   double*                 halo_buf    = nullptr; // device staging for the per-chunk buffer API
   size_t                  halo_buf_bytes = 0;
   cudaEvent_t             ev0 = nullptr, ev1 = nullptr;
+  // overlapped host transfers (field_upload/download_overlapped): a second stream, per field (uf, uj)
+  // the event after which the main stream has finished with the array for this step, and the event
+  // after which the last overlapped copy of it is complete
+  cudaStream_t            copy_stream = nullptr;
+  cudaEvent_t             ev_main_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
+  bool                    copy_pending[2] = {false, false};
   bool                    timed = false;
   size_t                  cells_per_chunk = 0;
   bool                    particles_set   = false;

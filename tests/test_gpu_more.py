@@ -237,3 +237,89 @@ def test_properties_at_scale(gpu_lib, order):
     assert all(np.array_equal(a, b) for a, b in zip(ids_before, ids_after))
     assert gd.total_particles() == ntot
     gd.close()
+
+
+class WeibelProblem(Problem):
+    """BASELINE.json configs[3] in miniature: two counter-streaming electron species, u_z = +-0.5 c,
+    cold (T = 0.001), 3rd-order shape."""
+
+    def __init__(self, cdims, dims, ppc, seed=77):
+        super().__init__(cdims, dims, 3, ppc=ppc, ns=2, seed=seed, vth=(0.03, 0.03), q=(-1.0, -1.0), m=(1.0, 1.0))
+
+    def particles(self, k, s):
+        xu = super().particles(k, s)
+        xu[:, 5] += 0.5 if s == 0 else -0.5
+        return xu
+
+
+def test_weibel_counter_streaming_order3(oracle_port, gpu_lib):
+    """Counter-streaming beams at order 3 against the oracle: every particle crosses a bin boundary every
+    few steps along z (the mover path of k_deposit and the z-direction migration carry the load)."""
+    prob = WeibelProblem((2, 2, 2), (8, 8, 8), ppc=8)
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True)
+    for step in range(5):
+        od.step(0.5, 1.0)
+        gd.step(0.5)
+        assert gd.check() == 0
+        for k, c in enumerate(od.chunks):
+            err = np.abs(gd.get_current(k) - c.uj).max() / np.abs(c.uj).max()
+            assert err < 1e-12, f"step {step} J chunk {k}: {err:.2e}"
+        assert_particles_equal(od, gd, f"weibel step {step}")
+    gd.close()
+
+
+def test_chunks_of_32_cubed_in_gilbert_order(oracle_port, gpu_lib):
+    """BASELINE.json configs[2] in miniature: 32^3-cell chunks (several push tiles per axis, 33 bins per
+    row) visited in space-filling-curve order, order 2, against the oracle over steps with migration."""
+    prob = Problem((2, 2, 2), (32, 32, 32), 2, ppc=3, seed=321, vth=(0.3, 0.06))
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True)
+    for step in range(2):
+        od.step(0.5, 1.0)
+        gd.step(0.5)
+        assert gd.check() == 0
+        for k, c in enumerate(od.chunks):
+            err = np.abs(gd.get_current(k) - c.uj).max() / np.abs(c.uj).max()
+            assert err < 1e-12, f"step {step} J chunk {k}: {err:.2e}"
+            for s in range(prob.ns):
+                assert np.array_equal(gd.get_pindex(k, s), c.pindex(s))
+        assert_particles_equal(od, gd, f"32^3 step {step}")
+    gd.close()
+
+
+def test_overlapped_field_transfers(gpu_lib):
+    """The pipelined host loop of bench.py's e2e leg (E/B up and J down on the domain's copy stream while
+    the device migrates and sorts) gives the results of the plain step: particles bit for bit, J to
+    round-off (the deposit adds with atomics), and the uploaded E/B arrives unchanged."""
+    import torch
+    from nix_b200 import core
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=16, seed=9, vth=(0.3, 0.05))
+    ga = gpu_domain(prob, strict=True)
+    gb = gpu_domain(prob, strict=True)
+    cells = int(np.prod(prob.M))
+    uf_host = torch.empty((gb.nchunk, cells, 6), dtype=torch.float64, pin_memory=True)
+    uj_host = torch.zeros((gb.nchunk, cells, 4), dtype=torch.float64, pin_memory=True)
+    for k in range(gb.nchunk):
+        uf_host.numpy()[k] = ga.get_field(k).reshape(cells, 6)
+    gb.field_upload_overlapped(core.FIELD_UF, uf_host.data_ptr())
+    for step in range(3):
+        ga.step(0.5)
+        gb.clear_current()
+        gb.push_deposit(0.5)
+        gb.exchange_current()
+        gb.field_download_overlapped(core.FIELD_UJ, uj_host.data_ptr())
+        gb.exchange_field()
+        gb.migrate_sort()
+        gb.copy_synchronize()
+        gb.field_upload_overlapped(core.FIELD_UF, uf_host.data_ptr())
+        assert ga.check() == 0 and gb.check() == 0
+        for k in range(ga.nchunk):
+            ja = ga.get_current(k)
+            jb = uj_host.numpy()[k].reshape(ja.shape)
+            assert np.abs(ja - jb).max() <= 1e-12 * np.abs(ja).max(), f"step {step} chunk {k}"
+            assert np.array_equal(bits(ga.get_field(k)), bits(gb.get_field(k)))
+            for s in range(prob.ns):
+                assert np.array_equal(bits(ga.get_particles(k, s)), bits(gb.get_particles(k, s)))
+    ga.close()
+    gb.close()
