@@ -22,6 +22,10 @@ import time
 
 import numpy as np
 
+# stdout carries ONE JSON line: keep NCCL's version banner out of it (NCCL_DEBUG=INFO still works)
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
