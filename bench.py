@@ -42,7 +42,8 @@ def workload(args):
     cd = (2, 2, 2) if small else (8, 8, 8)
     if args.cdims:
         cd = tuple(int(v) for v in args.cdims.split(","))
-    return dict(cdims=cd, dims=(16, 16, 16), order=2, ppc=64, ns=2)
+    dims = tuple(int(v) for v in args.chunk.split(",")) if args.chunk else (16, 16, 16)
+    return dict(cdims=cd, dims=dims, order=args.order, ppc=args.ppc, ns=2)
 
 
 def make_problem(w, seed=2024, cdims=None, coord=None):
@@ -342,18 +343,24 @@ def run_gpu(args):
             part = ntot / prob.ns
             ach = ALGO_BYTES[name] * part / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
             tr = traffic_by_kernel.get(name)
-            kern.append({"kernel": name + "<2>", "launch_ms": launch_ms, "launches": k_calls,
+            kern.append({"kernel": name + "<%d>" % w["order"], "launch_ms": launch_ms, "launches": k_calls,
                          "algorithmic_bytes_per_particle": ALGO_BYTES[name], "particles_per_launch": part,
                          "achieved": ach, "frac": ach / peak if peak else None,
                          "traffic": tr * part if tr else None})
         dom_k = max(kern, key=lambda k: k["launch_ms"])
+        cells = int(np.prod(w["cdims"])) * int(np.prod(w["dims"]))
+        side = round(cells ** (1.0 / 3.0))
+        workload_name = ("%s cells per GPU, %d ppc (electrons+ions, %d each), order %d, fp64, periodic thermal "
+                         "plasma, %dx%dx%d chunks of %s per GPU"
+                         % ("%d^3" % side if side ** 3 == cells else str(cells), 2 * w["ppc"], w["ppc"], w["order"],
+                            w["cdims"][0], w["cdims"][1], w["cdims"][2],
+                            "%d^3" % w["dims"][0] if len(set(w["dims"])) == 1 else "x".join(map(str, w["dims"]))))
         out = {
             "metric": METRIC, "value": nglobal * args.steps / (ms * 1e-3), "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": "128^3 cells per GPU, 128 ppc (electrons+ions, 64 each), order 2, fp64, periodic "
-                            "thermal plasma, %dx%dx%d chunks of 16^3 per GPU" % tuple(w["cdims"]),
+                "workload": workload_name,
                 "particles_per_gpu": ntot, "particles_end_all_ranks": int(n[1]),
                 "fp_contract": "off" if args.strict else "fma",
                 "l2": "inputs (%.1f GB of particles per GPU) larger than L2" % (ntot * 56 / 1e9),
@@ -401,6 +408,10 @@ def main():
     ap.add_argument("--small", action="store_true", help="2x2x2 chunks (smoke / profiling)")
     ap.add_argument("--cdims", default="", help="override chunks per axis, e.g. 4,4,4")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    # exploration only (the contract line is the default: order 2, 16^3-cell chunks, 64 ppc per species)
+    ap.add_argument("--order", type=int, default=2, help="shape order 1/2/3 (default 2 = BASELINE configs[1])")
+    ap.add_argument("--chunk", default="", help="cells per chunk, e.g. 32,32,32")
+    ap.add_argument("--ppc", type=int, default=64, help="particles per cell and species")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
