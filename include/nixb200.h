@@ -41,6 +41,11 @@ extern "C" {
 #define NIXB200_ERR_CFL 2      /* a particle moved more than one cell (c*dt > dx)          */
 #define NIXB200_ERR_CAPACITY 4 /* a particle / message buffer overflowed                   */
 
+/* momentum update of the push: the reference's three interchangeable primitives */
+#define NIXB200_PUSH_BORIS 0        /* push_boris         primitives.hpp:165-189 */
+#define NIXB200_PUSH_VAY 1          /* push_vay           primitives.hpp:193-224 */
+#define NIXB200_PUSH_HIGUERA_CARY 2 /* push_higuera_cary  primitives.hpp:227-253 */
+
 typedef struct nixb200_domain nixb200_domain;
 
 /* A domain = the chunks of ONE rank (one GPU): a contiguous range of chunk ids along the
@@ -60,6 +65,7 @@ typedef struct {
   int    strict_fp;  /* 1: push arithmetic without FMA contraction, bit-identical to the reference's
                         scalar templates; 0: contracted (<=1e-12 relative)                           */
   double capacity_factor; /* particle storage = factor * initial count (>=1; 0 -> 1.25)            */
+  int    pusher;     /* NIXB200_PUSH_BORIS / _VAY / _HIGUERA_CARY               primitives.hpp:165-253 */
 } nixb200_domain_desc;
 
 const char* nixb200_last_error(void);

@@ -37,6 +37,9 @@ SYMBOLS = [
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit")
 
 
+PUSH_BORIS, PUSH_VAY, PUSH_HIGUERA_CARY = 0, 1, 2  # primitives.hpp:165-253
+
+
 class DomainDesc(C.Structure):
     _fields_ = [
         ("cdims", C.c_int * 3),
@@ -51,6 +54,7 @@ class DomainDesc(C.Structure):
         ("device", C.c_int),
         ("strict_fp", C.c_int),
         ("capacity_factor", C.c_double),
+        ("pusher", C.c_int),
     ]
 
 
@@ -175,7 +179,7 @@ class Domain:
     nix::Application, application.hpp:114, behind the Chunk API)."""
 
     def __init__(self, cdims, dims, nb, order, q, m, delh=(1.0, 1.0, 1.0), cc=1.0, coord=None,
-                 id_range=None, device=0, strict_fp=True, capacity_factor=1.25, stream=None):
+                 id_range=None, device=0, strict_fp=True, capacity_factor=1.25, stream=None, pusher=0):
         self.lib = load_library()
         self.cdims = tuple(int(v) for v in cdims)
         self.dims = tuple(int(v) for v in dims)
@@ -200,6 +204,7 @@ class Domain:
         desc.device = int(device)
         desc.strict_fp = int(bool(strict_fp))
         desc.capacity_factor = float(capacity_factor)
+        desc.pusher = int(pusher)  # PUSH_BORIS / PUSH_VAY / PUSH_HIGUERA_CARY
         self.h = C.c_void_p()
         self._ck(self.lib.nixb200_domain_create(
             C.byref(desc), self.coord.ctypes.data_as(C.POINTER(C.c_int)),

@@ -200,6 +200,7 @@ struct PushArgs {
   SpeciesDev       sp;
   double           delt;
   int*             err;
+  int              pusher; // NIXB200_PUSH_*
 };
 
 // ev: null, or four events recorded around the two kernels: ev[0] k_push ev[1] | ev[2] k_deposit ev[3]

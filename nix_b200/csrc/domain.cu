@@ -207,6 +207,10 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
               "; this library is built for sm_100a only");
     return 1;
   }
+  if (desc->pusher < NIXB200_PUSH_BORIS || desc->pusher > NIXB200_PUSH_HIGUERA_CARY) {
+    set_error("pusher must be NIXB200_PUSH_BORIS, _VAY or _HIGUERA_CARY");
+    return 1;
+  }
   if (desc->order < 1 || desc->order > 3) {
     set_error("order must be 1, 2 or 3");
     return 1;
@@ -689,6 +693,7 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
     a.sp   = s;
     a.delt = delt;
     a.err  = d->err_dev;
+    a.pusher = d->desc.pusher;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (d->profiling) {
       for (auto& e : ev) cudaEventCreate(&e);

@@ -203,6 +203,7 @@ struct Kparams {
   double          delt, dt1, q;
   double          qdxdt[3]; // q * del/dt per axis (z,y,x)
   int*            err;
+  int             pusher;   // NIXB200_PUSH_*
 };
 
 // 1-D deposit weights of one particle on the central slots 1..N1 of the (O+3) mesh, per axis (z,y,x):
@@ -663,22 +664,63 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
       double ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
       double bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
 
-      // ---- push_boris (primitives.hpp:165-189) ----------------------------------------------
+      // ---- momentum update: the reference's three pushers, association order preserved ---------
       double ux = mine[3 * 32], uy = mine[4 * 32], uz = mine[5 * 32];
-      ux = add<S>(ux, ex);
-      uy = add<S>(uy, ey);
-      uz = add<S>(uz, ez);
-      double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
-      bxx = mul<S>(bxx, gm);
-      byy = mul<S>(byy, gm);
-      bzz = mul<S>(bzz, gm);
-      double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
-      double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
-      double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
-      double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
-      ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
-      uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
-      uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
+      if (P.pusher == NIXB200_PUSH_BORIS) { // push_boris, primitives.hpp:165-189
+        ux = add<S>(ux, ex);
+        uy = add<S>(uy, ey);
+        uz = add<S>(uz, ez);
+        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+        bxx = mul<S>(bxx, gm);
+        byy = mul<S>(byy, gm);
+        bzz = mul<S>(bzz, gm);
+        double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+        ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
+        uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
+        uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
+      } else if (P.pusher == NIXB200_PUSH_VAY) { // push_vay, primitives.hpp:193-224
+        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+        double vx = add<S>(add<S>(ux, mul<S>(2.0, ex)), mul<S>(gm, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy))));
+        double vy = add<S>(add<S>(uy, mul<S>(2.0, ey)), mul<S>(gm, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz))));
+        double vz = add<S>(add<S>(uz, mul<S>(2.0, ez)), mul<S>(gm, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx))));
+        gm        = add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(vx, vx)), mul<S>(vy, vy)), mul<S>(vz, vz));
+        double bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
+        double bu = add<S>(add<S>(mul<S>(bxx, vx), mul<S>(byy, vy)), mul<S>(bzz, vz));
+        double xx = sub<S>(gm, bb);
+        double yy = add<S>(bb, mul<S>(bu, bu));
+        gm = div_<S>(1.0, sqrt_<S>(mul<S>(0.5, add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(4.0, yy)))))));
+        bxx = mul<S>(bxx, gm);
+        byy = mul<S>(byy, gm);
+        bzz = mul<S>(bzz, gm);
+        bu  = add<S>(add<S>(mul<S>(bxx, vx), mul<S>(byy, vy)), mul<S>(bzz, vz));
+        bb  = div_<S>(1.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        ux  = mul<S>(add<S>(add<S>(vx, mul<S>(bu, bxx)), sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy))), bb);
+        uy  = mul<S>(add<S>(add<S>(vy, mul<S>(bu, byy)), sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz))), bb);
+        uz  = mul<S>(add<S>(add<S>(vz, mul<S>(bu, bzz)), sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx))), bb);
+      } else { // push_higuera_cary, primitives.hpp:227-253
+        ux = add<S>(ux, ex);
+        uy = add<S>(uy, ey);
+        uz = add<S>(uz, ez);
+        double gm = add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz));
+        double bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
+        double bu = add<S>(add<S>(mul<S>(bxx, ux), mul<S>(byy, uy)), mul<S>(bzz, uz));
+        double xx = sub<S>(gm, bb);
+        double yy = add<S>(bb, mul<S>(bu, bu));
+        gm = div_<S>(1.0, sqrt_<S>(mul<S>(0.5, add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(4.0, yy)))))));
+        bxx = mul<S>(bxx, gm);
+        byy = mul<S>(byy, gm);
+        bzz = mul<S>(bzz, gm);
+        bb  = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+        ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
+        uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
+        uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
+      }
 
       // ---- position update (lorentz_factor, primitives.hpp:158-161); the old position goes to the
       //      temporary array like the reference's xv[0:3] = xu[0:3] (test_esirkepov.cpp:1046-1051)
@@ -1101,6 +1143,7 @@ int launch_split_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st, 
   P.q    = a.sp.q;
   for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
   P.err = a.err;
+  P.pusher = a.pusher;
   static bool attr_set = false;
   if (!attr_set) {
     NIX_CUDA(cudaFuncSetAttribute(k_push<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));

@@ -113,6 +113,12 @@ double nixo_lorentz_factor(double ux, double uy, double uz, double rc)
   return sqrt(1 + (ux * ux + uy * uy + uz * uz) * rc * rc);
 }
 
+/* pusher used by the composed step: 0 = Boris, 1 = Vay (2008), 2 = Higuera-Cary (2017); the
+ * reference offers the three as interchangeable primitives (primitives.hpp:165-253) */
+static int g_pusher = 0;
+void nixo_set_pusher(int pusher) { g_pusher = pusher; }
+int  nixo_get_pusher(void) { return g_pusher; }
+
 /* primitives.hpp:165-189 */
 void nixo_push_boris(double* u, const double* eb, double cc)
 {
@@ -139,6 +145,71 @@ void nixo_push_boris(double* u, const double* eb, double cc)
   uy += (vz * bx - vx * bz) * bb + ey;
   uz += (vx * by - vy * bx) * bb + ez;
 
+  u[0] = ux;
+  u[1] = uy;
+  u[2] = uz;
+}
+
+/* primitives.hpp:193-224 */
+void nixo_push_vay(double* u, const double* eb, double cc)
+{
+  double ux = u[0], uy = u[1], uz = u[2];
+  double ex = eb[0], ey = eb[1], ez = eb[2], bx = eb[3], by = eb[4], bz = eb[5];
+  double gm, bb, bu, xx, yy, vx, vy, vz;
+
+  gm = 1 / sqrt(cc * cc + ux * ux + uy * uy + uz * uz);
+  vx = ux + 2 * ex + gm * (uy * bz - uz * by);
+  vy = uy + 2 * ey + gm * (uz * bx - ux * bz);
+  vz = uz + 2 * ez + gm * (ux * by - uy * bx);
+
+  gm = (cc * cc + vx * vx + vy * vy + vz * vz);
+  bb = bx * bx + by * by + bz * bz;
+  bu = bx * vx + by * vy + bz * vz;
+  xx = gm - bb;
+  yy = bb + bu * bu;
+  gm = 1 / sqrt(0.5 * (xx + sqrt(xx * xx + 4 * yy)));
+
+  bx *= gm;
+  by *= gm;
+  bz *= gm;
+  bu = bx * vx + by * vy + bz * vz;
+  bb = 1.0 / (1.0 + bx * bx + by * by + bz * bz);
+
+  u[0] = (vx + bu * bx + (vy * bz - vz * by)) * bb;
+  u[1] = (vy + bu * by + (vz * bx - vx * bz)) * bb;
+  u[2] = (vz + bu * bz + (vx * by - vy * bx)) * bb;
+}
+
+/* primitives.hpp:227-253 */
+void nixo_push_higuera_cary(double* u, const double* eb, double cc)
+{
+  double ux = u[0], uy = u[1], uz = u[2];
+  double ex = eb[0], ey = eb[1], ez = eb[2], bx = eb[3], by = eb[4], bz = eb[5];
+  double gm, bb, bu, xx, yy, vx, vy, vz;
+
+  ux += ex;
+  uy += ey;
+  uz += ez;
+
+  gm = cc * cc + ux * ux + uy * uy + uz * uz;
+  bb = bx * bx + by * by + bz * bz;
+  bu = bx * ux + by * uy + bz * uz;
+  xx = gm - bb;
+  yy = bb + bu * bu;
+  gm = 1 / sqrt(0.5 * (xx + sqrt(xx * xx + 4 * yy)));
+
+  bx *= gm;
+  by *= gm;
+  bz *= gm;
+  bb = 2.0 / (1.0 + bx * bx + by * by + bz * bz);
+
+  vx = ux + (uy * bz - uz * by);
+  vy = uy + (uz * bx - ux * bz);
+  vz = uz + (ux * by - uy * bx);
+
+  ux += (vy * bz - vz * by) * bb + ex;
+  uy += (vz * bx - vx * bz) * bb + ey;
+  uz += (vx * by - vy * bx) * bb + ez;
   u[0] = ux;
   u[1] = uy;
   u[2] = uz;
@@ -630,7 +701,9 @@ static void push_deposit_one(nixo_chunk* c, particle_t* p, int ip, double delt, 
   eb[4] = nixo_interp3d(order, c->uf, my, mx, iz0, iy0, ix0, 4, whz, wiy, whx, dt1);
   eb[5] = nixo_interp3d(order, c->uf, my, mx, iz0, iy0, ix0, 5, wiz, why, whx, dt1);
 
-  nixo_push_boris(u, eb, cc);
+  if (g_pusher == 1) nixo_push_vay(u, eb, cc);
+  else if (g_pusher == 2) nixo_push_higuera_cary(u, eb, cc);
+  else nixo_push_boris(u, eb, cc);
 
   double gam = nixo_lorentz_factor(u[0], u[1], u[2], rc);
   double dtg = delt / gam;

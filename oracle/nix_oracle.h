@@ -71,6 +71,10 @@ void     nixo_particle_set_boundary_periodic(nixo_chunk* c, int is, int lbp, int
 int    nixo_digitize(double x, double xmin, double rdx);                 /* primitives.hpp:46-58  */
 void   nixo_shape_mc(int order, double x, double X, double rdx, double* s); /* :257-298,519-532  */
 void   nixo_push_boris(double* u, const double* eb, double cc);          /* primitives.hpp:165-189 */
+void   nixo_push_vay(double* u, const double* eb, double cc);            /* primitives.hpp:193-224 */
+void   nixo_push_higuera_cary(double* u, const double* eb, double cc);   /* primitives.hpp:227-253 */
+void   nixo_set_pusher(int pusher); /* composed step: 0 Boris, 1 Vay, 2 Higuera-Cary */
+int    nixo_get_pusher(void);
 double nixo_lorentz_factor(double ux, double uy, double uz, double rc);  /* primitives.hpp:158-161 */
 /* esirkepov::deposit3d<order> on ss[2][3][order+3] -> cur[(order+3)^3][4] (esirkepov.hpp:326-340) */
 void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs, double* ss,

@@ -112,6 +112,10 @@ def load(name="port"):
     sig("nixo_digitize", I, D, D, D)
     sig("nixo_shape_mc", None, I, D, D, D, PD)
     sig("nixo_push_boris", None, PD, PD, D)
+    sig("nixo_push_vay", None, PD, PD, D)
+    sig("nixo_push_higuera_cary", None, PD, PD, D)
+    sig("nixo_set_pusher", None, I)
+    sig("nixo_get_pusher", I)
     sig("nixo_lorentz_factor", D, D, D, D, D)
     sig("nixo_deposit3d", None, I, D, D, D, D, PD, PD)
     sig("nixo_interp3d", D, I, PD, I, I, I, I, I, I, PD, PD, PD, D)

@@ -85,6 +85,10 @@ public:
   void push_deposit(int is, float64 delt, float64 cc);
 };
 
+// pusher of the composed step: 0 = push_boris, 1 = push_vay, 2 = push_higuera_cary
+// (primitives.hpp:165-253; the reference offers the three as interchangeable primitives)
+static int g_pusher = 0;
+
 //
 // composed per-particle step, scalar instantiation of the reference templates
 //
@@ -152,7 +156,9 @@ static void push_deposit_scalar(RefChunk& c, XtensorParticle& p, int ip, float64
   float64 by = interp::interp3d<Order>(c.uf, iz0, iy0, ix0, 4, whz, wiy, whx, dt1);
   float64 bz = interp::interp3d<Order>(c.uf, iz0, iy0, ix0, 5, wiz, why, whx, dt1);
 
-  push_boris(ux, uy, uz, ex, ey, ez, bx, by, bz, cc);
+  if (g_pusher == 1) push_vay(ux, uy, uz, ex, ey, ez, bx, by, bz, cc);
+  else if (g_pusher == 2) push_higuera_cary(ux, uy, uz, ex, ey, ez, bx, by, bz, cc);
+  else push_boris(ux, uy, uz, ex, ey, ez, bx, by, bz, cc);
 
   float64 gam = lorentz_factor(ux, uy, uz, rc);
   float64 dtg = delt / gam;
@@ -266,7 +272,9 @@ static void push_deposit_simd_cell(RefChunk& c, XtensorParticle& p, int ip0, flo
   V by = interp::interp3d<Order>(c.uf, iz0, iy0, ix0, 4, whz, wiy, whx, dt1);
   V bz = interp::interp3d<Order>(c.uf, iz0, iy0, ix0, 5, wiz, why, whx, dt1);
 
-  push_boris(ux, uy, uz, ex, ey, ez, bx, by, bz, V(cc));
+  if (g_pusher == 1) push_vay(ux, uy, uz, ex, ey, ez, bx, by, bz, V(cc));
+  else if (g_pusher == 2) push_higuera_cary(ux, uy, uz, ex, ey, ez, bx, by, bz, V(cc));
+  else push_boris(ux, uy, uz, ex, ey, ez, bx, by, bz, V(cc));
 
   V gam = lorentz_factor(ux, uy, uz, rc);
   V dtg = V(delt) / gam;
@@ -457,6 +465,16 @@ void nixo_push_boris(double* u, const double* eb, double cc)
 {
   primitives::push_boris(u[0], u[1], u[2], eb[0], eb[1], eb[2], eb[3], eb[4], eb[5], cc);
 }
+void nixo_push_vay(double* u, const double* eb, double cc)
+{
+  primitives::push_vay(u[0], u[1], u[2], eb[0], eb[1], eb[2], eb[3], eb[4], eb[5], cc);
+}
+void nixo_push_higuera_cary(double* u, const double* eb, double cc)
+{
+  primitives::push_higuera_cary(u[0], u[1], u[2], eb[0], eb[1], eb[2], eb[3], eb[4], eb[5], cc);
+}
+void nixo_set_pusher(int pusher) { g_pusher = pusher; }
+int  nixo_get_pusher(void) { return g_pusher; }
 
 double nixo_lorentz_factor(double ux, double uy, double uz, double rc)
 {

@@ -114,3 +114,50 @@ def test_full_steps_strict(oracle_port, gpu_lib, order, cdims, dims):
                 assert np.array_equal(gd.get_pcount(k, s), ref_pcount_before_sort(c, s)), f"step {step} pcount {k} {s}"
         assert_particles_equal(od, gd, f"step {step}")
         assert gd.total_particles() == ntot == od.total_particles()
+
+
+@pytest.mark.parametrize("pusher", [1, 2])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_other_pushers_strict(oracle_port, gpu_lib, order, pusher):
+    """push_vay / push_higuera_cary (primitives.hpp:193-253) instead of push_boris: full steps with
+    migration, particles bit for bit, J to round-off."""
+    prob = Problem((2, 2, 2), (8, 8, 8), order, ppc=8, seed=61 + order, vth=(0.35, 0.08))
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True, pusher=pusher)
+    oracle_port.nixo_set_pusher(pusher)
+    try:
+        for step in range(3):
+            od.step(0.5, 1.0)
+            gd.step(0.5)
+            assert gd.check() == 0
+            for k, c in enumerate(od.chunks):
+                assert rel_err(gd.get_current(k), c.uj) < JTOL, f"step {step} J chunk {k}"
+            assert_particles_equal(od, gd, f"pusher {pusher} step {step}")
+    finally:
+        oracle_port.nixo_set_pusher(0)
+        gd.close()
+
+
+@pytest.mark.parametrize("pusher", [1, 2])
+def test_other_pushers_fast(oracle_port, gpu_lib, pusher):
+    """Contracted (FMA) arithmetic: <= 1e-12 relative on positions and momenta after one push."""
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=12, seed=33, vth=(0.3, 0.05))
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=False, pusher=pusher)
+    oracle_port.nixo_set_pusher(pusher)
+    try:
+        od.clear_current()
+        od.push_deposit(0.5, 1.0)
+    finally:
+        oracle_port.nixo_set_pusher(0)
+    gd.clear_current()
+    gd.push_deposit(0.5)
+    assert gd.check() == 0
+    for k, c in enumerate(od.chunks):
+        for s in range(prob.ns):
+            ref, got = c.particles(s), gd.get_particles(k, s)
+            assert got.shape == ref.shape
+            scale = np.maximum(np.abs(ref[:, :6]), 1.0)
+            assert (np.abs(got[:, :6] - ref[:, :6]) / scale).max() < 1e-12
+        assert rel_err(gd.get_current(k), c.uj) < JTOL
+    gd.close()

@@ -100,3 +100,45 @@ def test_halo_buffers_bit_exact(oracle_port, oracle_ref):
         ca.halo_pack(no.MODE_PARTICLE); cb.halo_pack(no.MODE_PARTICLE)
         assert np.array_equal(ca.bufsize(no.MODE_PARTICLE), cb.bufsize(no.MODE_PARTICLE))
         assert np.array_equal(ca.sendbuf(no.MODE_PARTICLE), cb.sendbuf(no.MODE_PARTICLE))
+
+
+@pytest.mark.parametrize("name", ["nixo_push_vay", "nixo_push_higuera_cary"])
+def test_other_pushers_bit_exact(oracle_port, oracle_ref, name):
+    """push_vay / push_higuera_cary (primitives.hpp:193-253): the restatement against the reference's own
+    templates, bit for bit; and both reduce to push_boris when B = 0 up to round-off."""
+    rng = np.random.default_rng(17)
+    for _ in range(300):
+        u = rng.normal(0, 2.0, 3)
+        eb = np.ascontiguousarray(rng.normal(0, 0.5, 6))
+        ua, ub = u.copy(), u.copy()
+        getattr(oracle_port, name)(ua.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.5)
+        getattr(oracle_ref, name)(ub.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.5)
+        assert np.array_equal(bits(ua), bits(ub))
+    for _ in range(20):
+        u = rng.normal(0, 1.0, 3)
+        eb = np.ascontiguousarray(np.concatenate([rng.normal(0, 0.3, 3), np.zeros(3)]))
+        ua, ub = u.copy(), u.copy()
+        getattr(oracle_port, name)(ua.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.0)
+        oracle_port.nixo_push_boris(ub.ctypes.data_as(PD), eb.ctypes.data_as(PD), 1.0)
+        assert np.allclose(ua, ub, rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("pusher", [1, 2])
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_full_steps_other_pushers_bit_exact(oracle_port, oracle_ref, order, pusher):
+    prob = Problem((2, 2, 2), (6, 6, 6), order, ppc=5, seed=80 + order, vth=(0.35, 0.08))
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    oracle_port.nixo_set_pusher(pusher)
+    oracle_ref.nixo_set_pusher(pusher)
+    try:
+        for step in range(3):
+            a.step(0.5, 1.0)
+            b.step(0.5, 1.0)
+            for ca, cb in zip(a.chunks, b.chunks):
+                assert np.array_equal(bits(ca.uj), bits(cb.uj)), f"step {step}: J"
+                for s in range(prob.ns):
+                    assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s))), f"step {step}: particles"
+    finally:
+        oracle_port.nixo_set_pusher(0)
+        oracle_ref.nixo_set_pusher(0)
