@@ -225,7 +225,9 @@ def run_gpu(args):
     cells = int(np.prod(dom.M))
     # pinned host mirrors of the grid arrays (the host-side field solver's view)
     uf_host = torch.empty((nchunk, cells, 6), dtype=torch.float64, pin_memory=True)
-    uj_host = torch.empty((nchunk, cells, 4), dtype=torch.float64, pin_memory=True)
+    icells = prob.ncell()
+    ufi_host = torch.empty((nchunk, icells, 6), dtype=torch.float64, pin_memory=True)  # interior cells only
+    uji_host = torch.empty((nchunk, icells, 4), dtype=torch.float64, pin_memory=True)
     ufn = uf_host.numpy()
     for k in range(nchunk):
         ufn[k] = prob.field(ids[k]).reshape(cells, 6)
@@ -233,6 +235,9 @@ def run_gpu(args):
     dom.exchange_field()
     dom.field_download_async(core.FIELD_UF, uf_host.data_ptr())  # ghosts consistent on the host too
     dom.synchronize()
+    nbh = prob.nb
+    ufi_host.numpy()[...] = ufn.reshape((nchunk,) + tuple(prob.M) + (6,))[
+        :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
     npc = prob.ncell() * prob.ppc
     for s in range(prob.ns):
         flat = np.empty((nchunk * npc, 7), dtype=np.float64)
@@ -284,20 +289,21 @@ def run_gpu(args):
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    # The host-side field solver of a nix application sits between the J halo and the E/B halo; the
-    # copies run on the domain's second stream, so J goes down and the next E/B comes up while the
-    # device migrates and sorts particles.  Every step moves the full E/B in and the full J + counts out.
-    dom.field_upload_overlapped(core.FIELD_UF, uf_host.data_ptr())
+    # The host-side field solver of a nix application works on the interior cells: every step the interior
+    # J of every chunk goes down after the J halo and the interior E/B of every chunk comes up for the next
+    # step (its ghost cells are filled by the E/B halo on the device).  The copies run on the domain's
+    # second stream while the device migrates and sorts particles.
+    dom.interior_upload_overlapped(core.FIELD_UF, ufi_host.data_ptr())
     for k in range(args.steps):
+        dom.exchange_field()  # ghosts of the E/B that has just arrived
         dom.clear_current()
         dom.push_deposit(dt)
         dom.exchange_current()
-        dom.field_download_overlapped(core.FIELD_UJ, uj_host.data_ptr())
-        dom.exchange_field()
+        dom.interior_download_overlapped(core.FIELD_UJ, uji_host.data_ptr())
         dom.migrate_sort()
         dom.copy_synchronize()  # J is on the host: the field solver would run here
         if k + 1 < args.steps:
-            dom.field_upload_overlapped(core.FIELD_UF, uf_host.data_ptr())  # its result, for the next step
+            dom.interior_upload_overlapped(core.FIELD_UF, ufi_host.data_ptr())  # its result, for the next step
         dom.get_np(0)  # Chunk::get_total_load-style read back (synchronises the step)
     e3.record(stream)
     barrier()
@@ -372,11 +378,11 @@ def run_gpu(args):
             },
             "clocks": clocks,
             "e2e": {"value": nglobal * args.steps / (ms_e2e * 1e-3), "unit": "particle-updates/s",
-                    "h2d_bytes_per_step": int(uf_host.numel() * 8),
-                    "d2h_bytes_per_step": int(uj_host.numel() * 8 + nchunk * 4 + 4),
-                    "what": "per step: E/B of every chunk from pinned host memory, one full step, J of every "
-                            "chunk + per-chunk particle counts back to the host; the copies run on a second "
-                            "stream (J down after the J halo, next E/B up after the E/B halo) while the "
+                    "h2d_bytes_per_step": int(ufi_host.numel() * 8),
+                    "d2h_bytes_per_step": int(uji_host.numel() * 8 + nchunk * 4 + 4),
+                    "what": "per step: interior E/B of every chunk from pinned host memory, E/B halo, one full "
+                            "step, interior J of every chunk + per-chunk particle counts back to the host (what "
+                            "a host-side field solver exchanges); the copies run on a second stream while the "
                             "device migrates and sorts"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_k["kernel"], "achieved": dom_k["achieved"], "peak": peak,

@@ -100,6 +100,11 @@ int nixb200_domain_field_download_async(nixb200_domain* d, int which, double* ho
  * page-locked for the copy to be asynchronous; copy_synchronize waits for the copies only. */
 int nixb200_domain_field_upload_overlapped(nixb200_domain* d, int which, const double* host);
 int nixb200_domain_field_download_overlapped(nixb200_domain* d, int which, double* host);
+/* The same for the INTERIOR cells only: host layout [chunk][Nz][Ny][Nx][6 or 4], no ghost cells (a host-side
+ * solver needs the interior J -- the J halo has folded the ghosts in -- and produces the interior E/B, whose
+ * ghosts nixb200_domain_exchange_field fills on the device).  About half the bytes at Nb = 2, N = 16. */
+int nixb200_domain_interior_upload_overlapped(nixb200_domain* d, int which, const double* host);
+int nixb200_domain_interior_download_overlapped(nixb200_domain* d, int which, double* host);
 int nixb200_domain_copy_synchronize(nixb200_domain* d);
 /* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each */
 int nixb200_domain_set_particles(nixb200_domain* d, int is, const double* xu_aos,

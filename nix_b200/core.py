@@ -28,7 +28,8 @@ SYMBOLS = [
     "nixb200_halo_layout", "nixb200_chunk_halo_pack", "nixb200_chunk_halo_unpack",
     "nixb200_domain_get_load", "nixb200_domain_total_particles", "nixb200_domain_field_upload_async",
     "nixb200_domain_field_download_async", "nixb200_domain_field_upload_overlapped",
-    "nixb200_domain_field_download_overlapped", "nixb200_domain_copy_synchronize", "nixb200_domain_set_profiling", "nixb200_domain_get_phase_ms",
+    "nixb200_domain_field_download_overlapped", "nixb200_domain_interior_upload_overlapped",
+    "nixb200_domain_interior_download_overlapped", "nixb200_domain_copy_synchronize", "nixb200_domain_set_profiling", "nixb200_domain_get_phase_ms",
     "nixb200_plan_create", "nixb200_plan_destroy", "nixb200_plan_npeer", "nixb200_plan_peer",
     "nixb200_plan_entries", "nixb200_domain_set_ranks", "nixb200_comm_unique_id", "nixb200_domain_comm_init",
     "nixb200_domain_set_comm", "nixb200_domain_peer_traffic",
@@ -109,6 +110,8 @@ def load_library():
     sig("nixb200_domain_field_download_async", I, P, I, P)
     sig("nixb200_domain_field_upload_overlapped", I, P, I, P)
     sig("nixb200_domain_field_download_overlapped", I, P, I, P)
+    sig("nixb200_domain_interior_upload_overlapped", I, P, I, P)
+    sig("nixb200_domain_interior_download_overlapped", I, P, I, P)
     sig("nixb200_domain_copy_synchronize", I, P)
     sig("nixb200_domain_set_profiling", I, P, I)
     sig("nixb200_domain_get_phase_ms", I, P, I, PD, PI)
@@ -386,6 +389,13 @@ class Domain:
 
     def field_download_overlapped(self, which, host_ptr):
         self._ck(self.lib.nixb200_domain_field_download_overlapped(self.h, which, C.c_void_p(int(host_ptr))))
+
+    def interior_upload_overlapped(self, which, host_ptr):
+        """Interior cells only, host layout [chunk][Nz][Ny][Nx][6 or 4] (page-locked)."""
+        self._ck(self.lib.nixb200_domain_interior_upload_overlapped(self.h, which, C.c_void_p(int(host_ptr))))
+
+    def interior_download_overlapped(self, which, host_ptr):
+        self._ck(self.lib.nixb200_domain_interior_download_overlapped(self.h, which, C.c_void_p(int(host_ptr))))
 
     def copy_synchronize(self):
         self._ck(self.lib.nixb200_domain_copy_synchronize(self.h))

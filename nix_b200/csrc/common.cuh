@@ -232,6 +232,8 @@ int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* 
 int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
                        const int* nbvalid_dev, cudaStream_t st);
 
+// interior cells of all chunks <-> dense [chunk][Nz][Ny][Nx][ncomp] (pack: full -> dense)
+int launch_interior(bool pack, double* full, double* dense, const Geo& g, int ncomp, cudaStream_t st);
 int launch_aos_to_soa(const double* aos, double* soa_base, size_t cap, size_t first, size_t n,
                       cudaStream_t st);
 int launch_soa_to_aos(const double* soa_base, double* aos, size_t cap, size_t first, size_t n,

@@ -387,6 +387,8 @@ int nixb200_domain_destroy(nixb200_domain* dd)
     if (d->ev_main_done[w]) cudaEventDestroy(d->ev_main_done[w]);
     if (d->ev_copy_done[w]) cudaEventDestroy(d->ev_copy_done[w]);
   }
+  for (int w = 0; w < 2; w++)
+    if (d->dense[w]) cudaFree(d->dense[w]);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
   if (d->stream) cudaStreamDestroy(d->stream);
   delete d;
@@ -485,15 +487,28 @@ static int mark_main_done(Domain* d, int w)
   return 0;
 }
 
-static int field_copy_overlapped(Domain* d, int which, double* host, bool upload)
+static int field_copy_overlapped(Domain* d, int which, double* host, bool upload, bool interior)
 {
   if (!d || !host) return 1;
   const int    w     = field_index(which);
-  const size_t bytes = sizeof(double) * (w == 0 ? 6 : 4) * d->cells_per_chunk * d->geo.nchunk;
-  double*      dev   = (w == 0) ? d->uf : d->uj;
+  const int    nc    = (w == 0) ? 6 : 4;
+  const Geo&   g     = d->geo;
+  const size_t cells = interior ? (size_t)g.N[0] * g.N[1] * g.N[2] : d->cells_per_chunk;
+  const size_t bytes = sizeof(double) * nc * cells * g.nchunk;
+  double*      full  = (w == 0) ? d->uf : d->uj;
+  double*      dev   = full;
+  if (interior) {
+    if (!d->dense[w]) NIX_CUDA(cudaMalloc(&d->dense[w], bytes));
+    dev = d->dense[w];
+  }
   NIX_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_main_done[w], 0)); // no-op before the first phase
-  if (upload) NIX_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, d->copy_stream));
-  else NIX_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+  if (upload) {
+    NIX_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, d->copy_stream));
+    if (interior && launch_interior(false, full, dev, g, nc, d->copy_stream)) return 1;
+  } else {
+    if (interior && launch_interior(true, full, dev, g, nc, d->copy_stream)) return 1;
+    NIX_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
+  }
   NIX_CUDA(cudaEventRecord(d->ev_copy_done[w], d->copy_stream));
   d->copy_pending[w] = true;
   return 0;
@@ -501,12 +516,22 @@ static int field_copy_overlapped(Domain* d, int which, double* host, bool upload
 
 int nixb200_domain_field_upload_overlapped(nixb200_domain* dd, int which, const double* host)
 {
-  return field_copy_overlapped(D(dd), which, const_cast<double*>(host), true);
+  return field_copy_overlapped(D(dd), which, const_cast<double*>(host), true, false);
+}
+
+int nixb200_domain_interior_upload_overlapped(nixb200_domain* dd, int which, const double* host)
+{
+  return field_copy_overlapped(D(dd), which, const_cast<double*>(host), true, true);
+}
+
+int nixb200_domain_interior_download_overlapped(nixb200_domain* dd, int which, double* host)
+{
+  return field_copy_overlapped(D(dd), which, host, false, true);
 }
 
 int nixb200_domain_field_download_overlapped(nixb200_domain* dd, int which, double* host)
 {
-  return field_copy_overlapped(D(dd), which, host, false);
+  return field_copy_overlapped(D(dd), which, host, false, false);
 }
 
 int nixb200_domain_copy_synchronize(nixb200_domain* dd)
@@ -704,7 +729,7 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
   }
   NIX_CUDA(cudaEventRecord(d->ev1, d->stream));
   d->timed = true;
-  return 0;
+  return mark_main_done(d, 0); // the push is a reader of uf: an overlapped upload must wait for it
 }
 
 int nixb200_domain_exchange_current(nixb200_domain* dd)

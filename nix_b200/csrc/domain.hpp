@@ -32,6 +32,7 @@ struct Domain {
   cudaStream_t            copy_stream = nullptr;
   cudaEvent_t             ev_main_done[2] = {nullptr, nullptr}, ev_copy_done[2] = {nullptr, nullptr};
   bool                    copy_pending[2] = {false, false};
+  double*                 dense[2] = {nullptr, nullptr}; // interior-only staging of uf / uj (allocated on first use)
   bool                    timed = false;
   size_t                  cells_per_chunk = 0;
   bool                    particles_set   = false;
