@@ -22,9 +22,8 @@ import time
 
 import numpy as np
 
-# stdout carries ONE JSON line: keep NCCL's version banner out of it (NCCL_DEBUG=INFO still works)
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries ONE JSON line: NCCL's version banner / debug output goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
