@@ -22,8 +22,15 @@ import time
 
 import numpy as np
 
-# stdout carries ONE JSON line: NCCL's version banner / debug output goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner
+# comes from C code) is sent to stderr; emit() writes the line to the real stdout
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -190,7 +197,7 @@ def run_reference(args):
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_gpu(args):
@@ -397,7 +404,7 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu:
             r = cpu_reference_run(w, steps=3, warmup=1, budget_s=25.0)
             out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes")}
-        print(json.dumps(out))
+        emit(out)
     dom.close()
     if world > 1:
         dist.destroy_process_group()
