@@ -46,7 +46,13 @@ namespace nixb200
 {
 namespace
 {
-constexpr int MAXMOV  = 24; // compact mover records per warp (old + new position, bin: 64 bytes each)
+#ifndef NIX_MAXMOV
+#define NIX_MAXMOV 20
+#endif
+#ifndef NIX_MOV_FLUSH
+#define NIX_MOV_FLUSH NIX_MAXMOV // flush whole groups of XGROUP records: the expansion and face-node lanes stay busy
+#endif
+constexpr int MAXMOV  = NIX_MAXMOV; // compact mover records per warp (old + new position, bin: 64 bytes each)
 constexpr int CREC    = 8;  // doubles per compact record
 constexpr int XGROUP  = 10; // movers expanded to full 1-D weight records at a time (3 axes x 10 = 30 lanes)
 constexpr unsigned FULL = 0xffffffffu;
@@ -1046,7 +1052,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
         const unsigned taken = __ballot_sync(FULL, take);
         nrec += __popc(taken);
         mm &= ~taken;
-        if (mm || nrec > MAXMOV - 8) { // full (or nearly: the next iteration brings a few more)
+        if (mm || nrec >= NIX_MOV_FLUSH) { // full batches: whole groups of XGROUP records keep the flush lanes busy
           flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
           nrec = 0;
         }
