@@ -264,8 +264,8 @@ template <int O>
 __device__ __forceinline__ void deposit_round(const double* wq, int p, int plc, bool pl_on, const double q,
                                               const double* qd, double* acc)
 {
-  using C          = Cfg<O>;
-  constexpr int N1 = C::N1, NPR = C::NPR;
+  using C           = Cfg<O>;
+  constexpr int NPR = C::NPR;
   const double2* q2 = reinterpret_cast<const double2*>(wq);
   double         ty[2 * NPR], tx[2 * NPR];
 #pragma unroll
@@ -818,6 +818,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   constexpr int N1 = C::N1;
   constexpr int NS = C::NS;
   constexpr int PV = C::PV;
+  (void)NS;
   const Geo&    g    = P.geo;
   const int     tid  = threadIdx.x;
   const int     lane = tid & 31;
