@@ -1,41 +1,49 @@
-// push_deposit.cu -- fused gather + Boris push + position update + Esirkepov deposit + count (sm_100a)
+// push_deposit.cu -- gather + Boris push + position update + count (k_push) and the Esirkepov
+// deposit (k_deposit), two kernels per species and step (sm_100a)
 //
-// Replaces, per particle (composition: oracle/ref/ref_driver.cpp):
+// Replace, per particle (composition: oracle/ref/ref_driver.cpp):
 //   digitize / shape_mc<O>      primitives.hpp:46-58,257-298,519-532
 //   interp::shift_weights<O>    interp.hpp:149-172
 //   interp::interp3d<O>         interp.hpp:95-113,217-230
-//   push_boris, lorentz_factor  primitives.hpp:158-189
+//   push_boris / push_vay / push_higuera_cary, lorentz_factor    primitives.hpp:158-253
 //   esirkepov::deposit3d<O>     esirkepov.hpp:155-237,326-340
 //   append_current3d<O>         primitives.hpp:778-834
 //   XtensorParticle::count      xtensor_particle.hpp:324-357   (of the NEW positions)
 //   XtensorHaloParticle3D::pre_pack classification  xtensor_halo3d.hpp:288-302
 //
-// Work item = one (tz x ty x tx) tile of bins of one chunk, one CTA of 4 warps:
+// Work item of both kernels = one (tz x ty x tx) tile of bins of one chunk = one CTA.
+//
+// k_push (8 warps, 2 CTAs/SM):
 //   * TMA (cp.async.bulk.tensor.5d) stages the E/B tile of the CTA -- ghosts included -- into shared
-//     memory; an mbarrier signals arrival.  A J tile of the CTA's deposit footprint lives in shared
-//     memory next to it and is flushed to global memory ONCE per CTA with red.global.add.f64.
-//   * a WARP owns one bin (cell) at a time; its particles are contiguous because the container is
-//     cell-sorted, so the 32 lanes read 32 consecutive particles (coalesced SoA loads / stores).
-//     Lane = particle: weights, gather from the E/B tile over the EXACT (O+1)^3 support of every
-//     component, Boris, move, store, bin of the new position (-> key + histogram, or a leaver record
-//     with its ordered rank inside the bin).
-//   * deposit: the lanes change roles.  Every lane leaves the 1-D deposit weights of its particle
-//     (per axis S0, DS and the running sum of DS) in a per-warp scratch; then lane = (particle slot,
-//     z-plane) -- 8 slots x 4 lanes for orders 2 and 3, 16 x 2 for order 1 -- evaluates, round by
-//     round, the Esirkepov current of one particle on ONE z-plane of the central (O+1)^3 nodes of
-//     the bin and adds it to a register-resident accumulator of that plane (30 values for order 2;
-//     structural zeros are not stored) that lives for ALL particles of the bin.  The lanes of a
-//     particle read the same scratch words, so the 64/128-bit loads of a round are broadcasts.
-//     When the bin is done the accumulators of the 8 (16) slots are summed with a halving butterfly
-//     of warp shuffles and one shared-memory atomic per value adds the bin's current to the J tile:
-//     the GPU analogue of the reference's sorted `reduce_add` path (primitives.hpp:798-809) with
-//     one scatter per BIN instead of one per particle, and no cross-lane reduction per iteration.
-//   * the particle data of the NEXT iteration is prefetched with cp.async straight into a per-warp
-//     staging buffer (no registers held across the iteration, nothing to spill), and the bins of a
-//     tile are handed out dynamically (shared counter) so that the warps of a CTA finish together.
+//     memory; an mbarrier signals arrival.
+//   * a WARP owns one x-row of bins at a time (rows are handed out dynamically).  The container is
+//     cell-sorted, so a row is one contiguous particle range: the warp streams through it 32
+//     consecutive particles at a time (coalesced SoA loads through a two-stage cp.async staging
+//     buffer, coalesced stores), every lane addressing the E/B tile from ITS bin.
+//   * lane = particle: weights, gather over the EXACT (O+1)^3 support of every component, momentum
+//     update, move; the old position goes to xv[0:3] (the reference's temporary array,
+//     test_esirkepov.cpp:1046-1051), the new state in place; bin of the new position -> key +
+//     histogram, or a leaver record with its ordered rank inside (bin, direction).
+//
+// k_deposit (4 warps, 3 CTAs/SM): a J tile of the CTA's deposit footprint lives in shared memory and
+// is flushed to global memory ONCE per CTA with red.global.add.f64.
+//   * a WARP owns one bin at a time (bins are handed out dynamically); per iteration its lanes load
+//     old and new position of 32 particles and leave the 1-D deposit weights (per axis S0, DS and the
+//     running sum of DS) in a per-warp scratch.
+//   * then the lanes change roles: lane = (particle slot, z-plane) -- 8 slots x 4 lanes for orders 2
+//     and 3, 16 x 2 for order 1 -- evaluates, round by round, the Esirkepov current of one particle on
+//     ONE z-plane of the central (O+1)^3 nodes of the bin and adds it to a register-resident
+//     accumulator of that plane (30 values for order 2; structural zeros are not stored) that lives
+//     for ALL particles of the bin.  The lanes of a slot read the same scratch words, so the
+//     64/128-bit loads of a round are broadcasts.
+//   * when the bin is done the accumulators of the slots are summed through the idle scratch
+//     (conflict-free strided loads) and one shared-memory atomic per value adds the bin's current to
+//     the J tile: the GPU analogue of the reference's sorted `reduce_add` path
+//     (primitives.hpp:798-809) with one scatter per BIN instead of one per particle, and no
+//     cross-lane reduction per iteration.
 //   * particles that change bin ("movers", a few per cent) additionally touch nodes outside the
 //     central mesh.  They leave a compact record (old and new position, bin) in a per-warp list; when
-//     the list fills up, lanes = (mover, axis) expand ten records at a time into full 1-D weight
+//     the list is full, lanes = (mover, axis) expand ten records at a time into full 1-D weight
 //     tables and lanes = (mover, face node) add the extra values to the J tile (9 nodes per
 //     single-axis mover; the rare multi-axis mover walks its whole (O+3)^3 mesh).
 #include "common.cuh"
@@ -56,7 +64,7 @@ constexpr int MAXMOV  = NIX_MAXMOV; // compact mover records per warp (old + new
 constexpr int CREC    = 8;  // doubles per compact record
 constexpr int XGROUP  = 10; // movers expanded to full 1-D weight records at a time (3 axes x 10 = 30 lanes)
 constexpr unsigned FULL = 0xffffffffu;
-constexpr int PF_DOUBLES_W = 6 * 32; // cp.async staging: 6 components x 32 lanes (a lane re-fills its own slots)
+constexpr int PF_DOUBLES_W = 6 * 32; // one cp.async staging stage: 6 components x 32 lanes (a lane fills its own slots)
 template <int O>
 struct Cfg {
   static constexpr int NW = O + 2; // stencil width the staged E/B tile is padded by (interp.hpp)
@@ -490,7 +498,7 @@ static_assert(ID_CG % 2 == 0, "s_cg must be 8-byte aligned");
 template <int O>
 __host__ __device__ inline size_t push_smem()
 {
-  return sizeof(double) * ((size_t)Cfg<O>::EB_DOUBLES + PWARPS * PF_DOUBLES_W) + IP_INTS * sizeof(int);
+  return sizeof(double) * ((size_t)Cfg<O>::EB_DOUBLES + PWARPS * 2 * PF_DOUBLES_W) + IP_INTS * sizeof(int);
 }
 template <int O>
 __host__ __device__ inline size_t deposit_smem()
@@ -527,7 +535,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   extern __shared__ __align__(1024) double smem_d[];
   double*   s_eb   = smem_d;
   double*   s_pf   = smem_d + C::EB_DOUBLES;
-  int*      s_int  = reinterpret_cast<int*>(s_pf + PWARPS * PF_DOUBLES_W);
+  int*      s_int  = reinterpret_cast<int*>(s_pf + PWARPS * 2 * PF_DOUBLES_W); // two staging stages
   uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int + IP_BAR);
   int*      s_any  = s_int + IP_ANY;
   int*      s_next = s_int + IP_NEXT;
@@ -575,8 +583,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   double* __restrict__ xu = P.sp.xu;
   double* __restrict__ xv = P.sp.xv;
   int*          mydc = s_dcnt + warp * 32;
-  double*       my_pf = s_pf + warp * PF_DOUBLES_W;
-  const double* mine  = my_pf + lane;
+  double*       my_pf = s_pf + warp * 2 * PF_DOUBLES_W;
   const int     nrow  = nbn[0] * nbn[1];
 
   // rows of the tile, handed out dynamically; one iteration = 32 consecutive particles of the row
@@ -592,9 +599,9 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     }
     return true;
   };
-  auto prefetch = [&](int i) {
+  auto prefetch = [&](int stage, int i) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) cp_async8(my_pf + k * 32 + lane, xu + soa(k, cap, i));
+    for (int k = 0; k < 6; k++) cp_async8(my_pf + (stage * 6 + k) * 32 + lane, xu + soa(k, cap, i));
   };
 
   int  nr = warp, ni0 = 0, npe = 0;
@@ -604,7 +611,8 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     npe  = s_cs[nr * CSW + nbn[2]];
     have = advance(nr, ni0, npe);
   }
-  if (have && ni0 + lane < npe) prefetch(ni0 + lane);
+  int stage = 0;
+  if (have && ni0 + lane < npe) prefetch(0, ni0 + lane);
   cp_async_commit();
 
   mbar_wait(s_bar, 0);
@@ -619,6 +627,11 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     const int r = nr, i0 = ni0, pe = npe;
     have = advance(nr, ni0, npe);
     cp_async_wait_all();
+    // two staging stages: the next iteration's particles are requested before this one's are used
+    const double* mine = my_pf + stage * 6 * 32 + lane;
+    stage ^= 1;
+    if (have && ni0 + lane < npe) prefetch(stage, ni0 + lane);
+    cp_async_commit();
     if (r != prev_r) {
       const int lz = (nbn[1] == C::TY) ? r / C::TY : r / nbn[1], ly = r - lz * nbn[1];
       bz = b0[0] + lz, by = b0[1] + ly;
@@ -771,11 +784,6 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
       }
       if (!cfl_ok) atomicOr(P.err, NIXB200_ERR_CFL);
     }
-    __syncwarp();
-    // the staged particles have been consumed: request the next iteration's
-    if (have && ni0 + lane < npe) prefetch(ni0 + lane);
-    cp_async_commit();
-
     // ---- leavers: ordered rank inside (bin, direction); the counts of the bin that continues into
     //      the next iteration are carried in mydc ------------------------------------------------
     const bool     leaver = valid && dir != 13;
