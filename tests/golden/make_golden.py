@@ -54,6 +54,12 @@ def primitives(lib):
         lib.nixo_push_boris(uo[i].ctypes.data_as(no.C.POINTER(no.C.c_double)),
                             eb[i].ctypes.data_as(no.C.POINTER(no.C.c_double)), CC)
     out["boris_u"], out["boris_eb"], out["boris_out"] = u, eb, uo
+    # push_vay / push_higuera_cary (primitives.hpp:193-253) on the same inputs
+    for name, fn in (("vay", lib.nixo_push_vay), ("hc", lib.nixo_push_higuera_cary)):
+        uo = u.copy()
+        for i in range(32):
+            fn(uo[i].ctypes.data_as(no.C.POINTER(no.C.c_double)), eb[i].ctypes.data_as(no.C.POINTER(no.C.c_double)), CC)
+        out[f"{name}_out"] = uo
     # deposit3d<1..3> (esirkepov.hpp:326-340) on random valid weight sets
     for order in (1, 2, 3):
         ns = order + 3
@@ -80,8 +86,10 @@ def primitives(lib):
     return out
 
 
-def full_steps(lib, order):
-    prob = Problem((2, 1, 2), (4, 4, 4), order, ppc=2, seed=900 + order, vth=(0.4, 0.1))
+def full_steps(lib, order, pusher=0):
+    """pusher: 0 push_boris, 1 push_vay, 2 push_higuera_cary (the composed step of oracle/ref/ref_driver.cpp)"""
+    lib.nixo_set_pusher(pusher)
+    prob = Problem((2, 1, 2), (4, 4, 4), order, ppc=2, seed=900 + order + 10 * pusher, vth=(0.4, 0.1))
     dom = no.Domain(lib, prob.cdims, prob.dims, prob.nb, prob.order, prob.ns, prob.q, prob.m, prob.coord,
                     prob.ncell() * prob.ppc)
     out = {"cdims": np.array(prob.cdims), "dims": np.array(prob.dims), "nb": np.array(prob.nb),
@@ -103,6 +111,8 @@ def full_steps(lib, order):
             out[f"sorted_pindex_{k}_{s}"] = c.pindex(s).copy()
     for _ in range(NSTEP):
         dom.step(DELT, CC, False)
+    lib.nixo_set_pusher(0)
+    out["pusher"] = np.array(pusher)
     for k, c in enumerate(dom.chunks):
         out[f"out_uf_{k}"] = c.uf.copy()
         out[f"out_uj_{k}"] = c.uj.copy()
@@ -121,6 +131,8 @@ def main():
     np.savez_compressed(os.path.join(HERE, "primitives.npz"), **primitives(lib))
     for order in (1, 2, 3):
         np.savez_compressed(os.path.join(HERE, f"steps_order{order}.npz"), **full_steps(lib, order))
+    for pusher, name in ((1, "vay"), (2, "hc")):
+        np.savez_compressed(os.path.join(HERE, f"steps_order2_{name}.npz"), **full_steps(lib, 2, pusher))
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))
 

@@ -76,7 +76,8 @@ def gpu_domain_from_golden(g, order, strict=True):
     from nix_b200 import core
     cdims, dims, nb = tuple(int(v) for v in g["cdims"]), tuple(int(v) for v in g["dims"]), int(g["nb"])
     q, m = g["q"], g["m"]
-    d = core.Domain(cdims, dims, nb, order, q, m, coord=g["coord"], strict_fp=strict)
+    pusher = int(g["pusher"]) if "pusher" in g.files else 0
+    d = core.Domain(cdims, dims, nb, order, q, m, coord=g["coord"], strict_fp=strict, pusher=pusher)
     for k in range(d.nchunk):
         d.set_field(k, g[f"in_uf_{k}"])
     d.exchange_field()

@@ -64,3 +64,32 @@ def test_full_steps_golden(oracle_port, order):
         for s in range(ns):
             assert np.array_equal(bits(c.particles(s)), bits(g[f"out_xu_{k}_{s}"]))
             assert np.array_equal(c.pindex(s), g[f"out_pindex_{k}_{s}"])
+
+
+@pytest.mark.parametrize("name", ["vay", "hc"])
+def test_other_pushers_golden(oracle_port, prim, name):
+    """push_vay / push_higuera_cary (primitives.hpp:193-253) against values written by the reference."""
+    fn = oracle_port.nixo_push_vay if name == "vay" else oracle_port.nixo_push_higuera_cary
+    u, eb, ref = prim["boris_u"], prim["boris_eb"], prim[f"{name}_out"]
+    for i in range(len(u)):
+        v = u[i].copy()
+        fn(v.ctypes.data_as(PD), np.ascontiguousarray(eb[i]).ctypes.data_as(PD), 1.0)
+        assert np.array_equal(bits(v), bits(ref[i]))
+    assert not np.array_equal(bits(ref), bits(prim["boris_out"]))
+
+
+@pytest.mark.parametrize("name", ["vay", "hc"])
+def test_full_steps_other_pushers_golden(oracle_port, name):
+    g = np.load(os.path.join(GOLD, f"steps_order2_{name}.npz"))
+    dom, ns = load_golden_domain(oracle_port, g, 2)
+    oracle_port.nixo_set_pusher(int(g["pusher"]))
+    try:
+        for _ in range(int(g["nstep"])):
+            dom.step(float(g["delt"]), float(g["cc"]))
+    finally:
+        oracle_port.nixo_set_pusher(0)
+    for k, c in enumerate(dom.chunks):
+        assert np.array_equal(bits(c.uj), bits(g[f"out_uj_{k}"]))
+        for s in range(ns):
+            assert np.array_equal(bits(c.particles(s)), bits(g[f"out_xu_{k}_{s}"]))
+            assert np.array_equal(c.pindex(s), g[f"out_pindex_{k}_{s}"])

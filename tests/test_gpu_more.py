@@ -16,10 +16,11 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
-def test_golden_fixture_from_reference(gpu_lib, order):
-    """tests/golden/steps_order*.npz were written by the reference's own templates (oracle/_ref)."""
-    g = np.load(os.path.join(GOLD, f"steps_order{order}.npz"))
+@pytest.mark.parametrize("order,tag", [(1, ""), (2, ""), (3, ""), (2, "_vay"), (2, "_hc")])
+def test_golden_fixture_from_reference(gpu_lib, order, tag):
+    """tests/golden/steps_order*.npz were written by the reference's own templates (oracle/_ref); the
+    _vay / _hc fixtures use push_vay / push_higuera_cary instead of push_boris."""
+    g = np.load(os.path.join(GOLD, f"steps_order{order}{tag}.npz"))
     gd = gpu_domain_from_golden(g, order, strict=True)
     ns = len(g["q"])
     for k in range(gd.nchunk):
