@@ -171,9 +171,15 @@ def cpu_reference_run(w, steps, warmup, budget_s=None):
             break
     dt = time.perf_counter() - t0
     kind = "reference" if name.startswith("ref") else "port"
+    # the reference's scalar templates on the same sample, one step (both paths reported)
+    scalar = None
+    if simd:
+        t1 = time.perf_counter()
+        dom.step(0.5, 1.0, False)
+        scalar = npart / (time.perf_counter() - t1)
     return {
         "value": npart * done / dt, "unit": "particle-updates/s", "cores": nthreads, "kind": kind,
-        "backend": name, "simd_lanes": lib.nixo_simd_lanes() if simd else 1,
+        "backend": name, "simd_lanes": lib.nixo_simd_lanes() if simd else 1, "scalar_path_value": scalar,
         "sample": f"{cd[0]}x{cd[1]}x{cd[2]} chunks of 16^3 cells, {w['ppc']} ppc x {w['ns']} species "
                   f"({npart} particles), order {w['order']}, {done} steps after {warmup} warm-up",
         "ms_per_step": 1e3 * dt / done, "steps": done,
@@ -192,7 +198,8 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "128^3 cells, 128 ppc (2 species x 64), order 2, fp64, 8^3 chunks of 16^3 "
                                "(bounded CPU sample: " + r["sample"] + ")"},
-        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes")},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes",
+                                           "scalar_path_value")},
         "e2e": {"value": r["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -403,7 +410,7 @@ def run_gpu(args):
         }
         if world == 1 and not args.no_cpu:
             r = cpu_reference_run(w, steps=3, warmup=1, budget_s=25.0)
-            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes")}
+            out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes", "scalar_path_value")}
         emit(out)
     dom.close()
     if world > 1:
