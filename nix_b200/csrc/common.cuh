@@ -207,7 +207,7 @@ struct PushArgs {
 int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st,
                         cudaEvent_t* ev = nullptr);
 size_t push_smem_bytes(const Geo& g);
-void   push_tile_box(int order, int& tz, int& ty, int& tx);
+void   push_tile_box(int order, int& ez, int& ey, int& ex); // nodes per axis of the staged E/B tile
 int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits
 
 int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);

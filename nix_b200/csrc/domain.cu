@@ -41,13 +41,12 @@ static int make_tensor_map(Domain* d)
     return 1;
   }
   const Geo&  g       = d->geo;
-  const int   NW      = g.order + 2;
   cuuint64_t  dims[5] = {6, (cuuint64_t)g.M[2], (cuuint64_t)g.M[1], (cuuint64_t)g.M[0], (cuuint64_t)g.nchunk};
   cuuint64_t  strides[4] = {48, (cuuint64_t)g.M[2] * 48, (cuuint64_t)g.M[1] * g.M[2] * 48,
                             (cuuint64_t)g.M[0] * g.M[1] * g.M[2] * 48};
-  int bz, by, bx;
-  push_tile_box(g.order, bz, by, bx); // compile-time box of the push kernel (>= g.tile)
-  cuuint32_t  box[5]  = {6, (cuuint32_t)(bx + NW - 1), (cuuint32_t)(by + NW - 1), (cuuint32_t)(bz + NW - 1), 1};
+  int ez, ey, ex;
+  push_tile_box(g.order, ez, ey, ex); // compile-time box of the push kernel (stencil box + bank padding)
+  cuuint32_t  box[5]  = {6, (cuuint32_t)ex, (cuuint32_t)ey, (cuuint32_t)ez, 1};
   cuuint32_t  estr[5] = {1, 1, 1, 1, 1};
   CUresult    r = ((encode_fn)fn)(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, d->uf, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,

@@ -93,7 +93,14 @@ struct Cfg {
   // bins per CTA (compile-time, so that every shared-memory offset of the gather is an immediate);
   // smaller chunks simply use part of the box
   static constexpr int TZ = 4, TY = 4, TX = 9;
-  static constexpr int EZ = TZ + NW - 1, EY = TY + NW - 1, EX = TX + NW - 1; // staged E/B tile
+  // staged E/B tile: the stencil box plus dummy rows / columns (the TMA box is simply larger) chosen so
+  // that the row and plane strides, modulo the 128 bytes of the banks, keep the four half-grid base
+  // offsets of every component in different bank pairs (unpadded, both strides are 64 B for order 2)
+#ifndef NIX_TILE_PAD
+#define NIX_TILE_PAD 1
+#endif
+  static constexpr int PADX = !NIX_TILE_PAD ? 0 : (O == 2 ? 1 : 0), PADY = !NIX_TILE_PAD ? 0 : (O == 2 ? 3 : (O == 3 ? 2 : 0));
+  static constexpr int EZ = TZ + NW - 1, EY = TY + NW - 1 + PADY, EX = TX + NW - 1 + PADX;
   static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
   static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
   // J tile, component-major: s_j[comp * JC + node] -- lanes that add the same component of neighbouring
@@ -1190,12 +1197,14 @@ size_t push_smem_bytes(const Geo& g)
   }
 }
 
-void push_tile_box(int order, int& tz, int& ty, int& tx)
+// box of the E/B tile the push kernel stages (nodes per axis z, y, x; dummy rows / columns included)
+void push_tile_box(int order, int& ez, int& ey, int& ex)
 {
-  (void)order;
-  tz = Cfg<2>::TZ;
-  ty = Cfg<2>::TY;
-  tx = Cfg<2>::TX;
+  switch (order) {
+  case 1: ez = Cfg<1>::EZ, ey = Cfg<1>::EY, ex = Cfg<1>::EX; break;
+  case 2: ez = Cfg<2>::EZ, ey = Cfg<2>::EY, ex = Cfg<2>::EX; break;
+  default: ez = Cfg<3>::EZ, ey = Cfg<3>::EY, ex = Cfg<3>::EX; break;
+  }
 }
 
 // The bins-per-CTA box is a compile-time constant of the kernel (Cfg<O>::TZ/TY/TX); small chunks use
