@@ -85,9 +85,12 @@ struct Cfg {
   // per-warp weight scratch (doubles).  Axis record of y and x: S0[N1] DS[N1] CP[1..N1-1] as NPR
   // 16-byte pairs, [axis][pair][particle][2]; z: [plane][particle][2] = (S0z, DSz); [plane-1][particle] = CPz
   static constexpr int NPR   = (3 * N1) / 2;
+  // (plane stride ZP = 33 particles: the lanes of a slot read different planes of the same particle,
+  // which a stride of 32 would put into the same banks)
+  static constexpr int ZP    = 33;
   static constexpr int WQ_Z  = 2 * NPR * 64;
-  static constexpr int WQ_ZC = WQ_Z + N1 * 64;
-  static constexpr int WQ_DOUBLES = WQ_ZC + (N1 - 1) * 32;
+  static constexpr int WQ_ZC = WQ_Z + N1 * 2 * ZP;
+  static constexpr int WQ_DOUBLES = WQ_ZC + (N1 - 1) * ZP;
   // the scratch also holds the expanded mover records of flush_movers
   static constexpr int SCR = ((WQ_DOUBLES > XGROUP * REC ? WQ_DOUBLES : XGROUP * REC) + 15) / 16 * 16;
   // bins per CTA (compile-time, so that every shared-memory offset of the gather is an immediate);
@@ -289,8 +292,8 @@ __device__ __forceinline__ void deposit_round(const double* wq, int p, int plc, 
     ty[2 * pr] = a.x, ty[2 * pr + 1] = a.y;
     tx[2 * pr] = b.x, tx[2 * pr + 1] = b.y;
   }
-  const double2 z2 = q2[C::WQ_Z / 2 + plc * 32 + p];
-  const double  zc = wq[C::WQ_ZC + (plc >= 1 ? plc - 1 : 0) * 32 + p];
+  const double2 z2 = q2[C::WQ_Z / 2 + plc * C::ZP + p];
+  const double  zc = wq[C::WQ_ZC + (plc >= 1 ? plc - 1 : 0) * C::ZP + p];
   const double  s0z = pl_on ? z2.x : 0.0, dsz = pl_on ? z2.y : 0.0, cpz = (pl_on && plc >= 1) ? zc : 0.0;
   plane_accumulate<O>(s0z, dsz, cpz, ty, tx, q, qd, acc);
 }
@@ -1109,8 +1112,8 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
           if (a == 0) {
 #pragma unroll
             for (int z = 0; z < N1; z++) {
-              q2[C::WQ_Z / 2 + z * 32 + lane] = make_double2(s0[z], ds[z]);
-              if (z >= 1) my_red[C::WQ_ZC + (z - 1) * 32 + lane] = cp[z];
+              q2[C::WQ_Z / 2 + z * C::ZP + lane] = make_double2(s0[z], ds[z]);
+              if (z >= 1) my_red[C::WQ_ZC + (z - 1) * C::ZP + lane] = cp[z];
             }
           } else {
             constexpr int NPR = C::NPR;
