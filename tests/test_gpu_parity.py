@@ -161,3 +161,21 @@ def test_other_pushers_fast(oracle_port, gpu_lib, pusher):
             assert (np.abs(got[:, :6] - ref[:, :6]) / scale).max() < 1e-12
         assert rel_err(gd.get_current(k), c.uj) < JTOL
     gd.close()
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_anisotropic_cells_and_c(oracle_port, gpu_lib, order):
+    """delz != dely != delx and c != 1 (chunk.cpp:210-237): full steps with migration, strict."""
+    prob = Problem((2, 2, 1), (8, 6, 10), order, ppc=6, seed=95 + order, vth=(0.5, 0.1), delh=(0.5, 1.25, 2.0))
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True, cc=2.0)
+    for step in range(3):
+        od.step(0.2, 2.0)
+        gd.step(0.2)
+        assert gd.check() == 0
+        for k, c in enumerate(od.chunks):
+            assert rel_err(gd.get_current(k), c.uj) < JTOL, f"step {step} J chunk {k}"
+            for s in range(prob.ns):
+                assert np.array_equal(gd.get_pindex(k, s), c.pindex(s))
+        assert_particles_equal(od, gd, f"anisotropic step {step}")
+    gd.close()

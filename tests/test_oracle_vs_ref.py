@@ -142,3 +142,19 @@ def test_full_steps_other_pushers_bit_exact(oracle_port, oracle_ref, order, push
     finally:
         oracle_port.nixo_set_pusher(0)
         oracle_ref.nixo_set_pusher(0)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_anisotropic_cells_and_c_bit_exact(oracle_port, oracle_ref, order):
+    """delz != dely != delx and c != 1: every place where a cell size or the speed of light enters."""
+    prob = Problem((2, 2, 1), (6, 5, 7), order, ppc=5, seed=90 + order, vth=(0.5, 0.1), delh=(0.5, 1.25, 2.0))
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    for step in range(3):
+        a.step(0.2, 2.0)
+        b.step(0.2, 2.0)
+        for ca, cb in zip(a.chunks, b.chunks):
+            assert np.array_equal(bits(ca.uj), bits(cb.uj)), f"step {step}: J"
+            for s in range(prob.ns):
+                assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s))), f"step {step}: particles"
+                assert np.array_equal(ca.pindex(s), cb.pindex(s))
