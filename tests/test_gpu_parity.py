@@ -179,3 +179,21 @@ def test_anisotropic_cells_and_c(oracle_port, gpu_lib, order):
                 assert np.array_equal(gd.get_pindex(k, s), c.pindex(s))
         assert_particles_equal(od, gd, f"anisotropic step {step}")
     gd.close()
+
+
+@pytest.mark.parametrize("ns", [1, 3])
+def test_one_and_three_species(oracle_port, gpu_lib, ns):
+    """Species count other than two (the J of all species accumulates into one array), nb larger than the
+    stencil needs."""
+    prob = Problem((2, 1, 2), (8, 8, 8), 2, ppc=6, ns=ns, seed=77 + ns, vth=(0.3, 0.05, 0.02)[:ns],
+                   q=(-1.0, 1.0, 2.0)[:ns], m=(1.0, 25.0, 100.0)[:ns], nb=3)
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True)
+    for step in range(3):
+        od.step(0.5, 1.0)
+        gd.step(0.5)
+        assert gd.check() == 0
+        for k, c in enumerate(od.chunks):
+            assert rel_err(gd.get_current(k), c.uj) < JTOL, f"step {step} J chunk {k}"
+        assert_particles_equal(od, gd, f"ns={ns} step {step}")
+    gd.close()
