@@ -57,7 +57,8 @@ public:
 
   GpuDomain(nix::ChunkMap& chunkmap, const int cdims[3], const int dims[3], int nb, int order,
             const std::vector<SpeciesSpec>& species, float64 delz, float64 dely, float64 delx, float64 cc,
-            int id_begin_, int id_end_, int device, bool strict_fp = false, double capacity_factor = 1.25)
+            int id_begin_, int id_end_, int device, bool strict_fp = false, double capacity_factor = 1.25,
+            int pusher = NIXB200_PUSH_BORIS)
       : id_begin(id_begin_), id_end(id_end_)
   {
     const int        ncid = cdims[0] * cdims[1] * cdims[2];
@@ -85,6 +86,7 @@ public:
     desc.device          = device;
     desc.strict_fp       = strict_fp ? 1 : 0;
     desc.capacity_factor = capacity_factor;
+    desc.pusher          = pusher; // push_boris / push_vay / push_higuera_cary (primitives.hpp:165-253)
     std::vector<double> q, m;
     for (auto& s : species) {
       q.push_back(s.q);
@@ -245,7 +247,7 @@ public:
 template <typename ChunkVec>
 std::shared_ptr<GpuDomain> make_domain(ChunkVec& chunks, nix::ChunkMap& chunkmap, const int cdims[3], int nb, int order,
                                        const std::vector<SpeciesSpec>& species, float64 cc, int device, bool strict_fp,
-                                       double capacity_factor = 1.25)
+                                       double capacity_factor = 1.25, int pusher = NIXB200_PUSH_BORIS)
 {
   if (chunks.size() == 0) return nullptr;
   auto* first = static_cast<GpuChunk*>(chunks.front().get());
@@ -254,7 +256,7 @@ std::shared_ptr<GpuDomain> make_domain(ChunkVec& chunks, nix::ChunkMap& chunkmap
   int dims[3]         = {nd[0], nd[1], nd[2]};
   auto dom = std::make_shared<GpuDomain>(chunkmap, cdims, dims, nb, order, species, first->get_delz(), first->get_dely(),
                                          first->get_delx(), cc, first->get_id(), last->get_id() + 1, device, strict_fp,
-                                         capacity_factor);
+                                         capacity_factor, pusher);
   const int ns = (int)species.size();
   for (int k = 0; k < (int)chunks.size(); k++) {
     auto* c = static_cast<GpuChunk*>(chunks[k].get());
@@ -293,6 +295,7 @@ protected:
   int                        order = 2, nb = 2, device = 0;
   float64                    cc    = 1.0;
   bool                       strict_fp = false;
+  int                        pusher    = NIXB200_PUSH_BORIS;
 
 public:
   GpuApplication(int argc, char** argv, PtrInterface interface = std::make_shared<GpuInterface>())
@@ -306,7 +309,7 @@ public:
     bool stale = !domain;
     for (auto& c : chunkvec) stale = stale || static_cast<GpuChunk*>(c.get())->domain != domain;
     if (stale) {
-      domain = make_domain(chunkvec, *chunkmap, cdims, nb, order, species, cc, device, strict_fp);
+      domain = make_domain(chunkvec, *chunkmap, cdims, nb, order, species, cc, device, strict_fp, 1.25, pusher);
       if (domain && nprocess > 1) {
         unsigned char id[128] = {0};
         if (thisrank == 0) check(nixb200_comm_unique_id(id), "comm_unique_id");
