@@ -39,7 +39,8 @@ extern "C" {
 /* error bits accumulated on the device, see nixb200_domain_check() */
 #define NIXB200_ERR_UNSORTED 1 /* push found a particle outside the cell it is binned in */
 #define NIXB200_ERR_CFL 2      /* a particle moved more than one cell (c*dt > dx)          */
-#define NIXB200_ERR_CAPACITY 4 /* a particle / message buffer overflowed                   */
+#define NIXB200_ERR_CAPACITY 4 /* a particle / message buffer overflowed: particles were lost; the
+                                  domain refuses further steps until particles are set again     */
 
 /* momentum update of the push: the reference's three interchangeable primitives */
 #define NIXB200_PUSH_BORIS 0        /* push_boris         primitives.hpp:165-189 */
@@ -64,7 +65,8 @@ typedef struct {
   int    device;     /* CUDA device ordinal                                                         */
   int    strict_fp;  /* 1: push arithmetic without FMA contraction, bit-identical to the reference's
                         scalar templates; 0: contracted (<=1e-12 relative)                           */
-  double capacity_factor; /* particle storage = factor * initial count (>=1; 0 -> 1.25)            */
+  double capacity_factor; /* initial particle storage = factor * initial count (>=1; 0 -> 1.25); the
+                             stores regrow on their own while a run drifts (see nixb200_domain_reserve) */
   int    pusher;     /* NIXB200_PUSH_BORIS / _VAY / _HIGUERA_CARY               primitives.hpp:165-253 */
 } nixb200_domain_desc;
 
@@ -116,6 +118,15 @@ int nixb200_chunk_get_particles(nixb200_domain* d, int k, int is, double* xu_aos
  * the state count() leaves (before sort() turns it into cursors); pindex the state sort() leaves */
 int nixb200_chunk_get_pindex(nixb200_domain* d, int k, int is, int32_t* pindex);
 int nixb200_chunk_get_pcount(nixb200_domain* d, int k, int is, int32_t* pcount);
+
+/* Particle storage.  The reference's containers grow on demand (XtensorParticle::resize called from
+ * XtensorHaloParticle3D::pre_unpack, xtensor_halo3d.hpp:464-476).  Here each species has one store of `np`
+ * particles for all chunks of the domain and migration buffers for `nmove` particles per step; after every
+ * sort the device reports its fill level and the next push_deposit regrows the stores BEFORE they are full
+ * (what moved in the last step must fit twice on top of what is there).  A jump that outruns this in a single
+ * step raises NIXB200_ERR_CAPACITY -- never an out-of-bounds access -- and is avoided by reserving up front. */
+int nixb200_domain_reserve(nixb200_domain* d, int is, int64_t np, int64_t nmove);
+int nixb200_domain_get_capacity(nixb200_domain* d, int is, int64_t* np, int64_t* nmove);
 
 /* ---- the per-step hot path, batched over every chunk of the domain ---- */
 /* XtensorParticle::count + sort for every chunk/species (xtensor_particle.hpp:260-357); drops

@@ -32,7 +32,8 @@ SYMBOLS = [
     "nixb200_domain_interior_download_overlapped", "nixb200_domain_copy_synchronize", "nixb200_domain_set_profiling", "nixb200_domain_get_phase_ms",
     "nixb200_plan_create", "nixb200_plan_destroy", "nixb200_plan_npeer", "nixb200_plan_peer",
     "nixb200_plan_entries", "nixb200_domain_set_ranks", "nixb200_comm_unique_id", "nixb200_domain_comm_init",
-    "nixb200_domain_set_comm", "nixb200_domain_peer_traffic",
+    "nixb200_domain_set_comm", "nixb200_domain_peer_traffic", "nixb200_domain_reserve",
+    "nixb200_domain_get_capacity",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit")
@@ -127,6 +128,8 @@ def load_library():
     sig("nixb200_domain_comm_init", I, P, P)
     sig("nixb200_domain_set_comm", I, P, P)
     sig("nixb200_domain_peer_traffic", I, P, PL, PL, PL)
+    sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
+    sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib
     return lib
 
@@ -169,6 +172,9 @@ class Plan:
             self.peers.append(dict(rank=r.value, send=[tuple(int(v) for v in e) for e in snd],
                                    recv=[tuple(int(v) for v in e) for e in rcv]))
         lib.nixb200_plan_destroy(h)
+
+
+from .sfc import chunk_coords  # noqa: E402  (the reference's chunk order; re-exported)
 
 
 def uniform_boundary(nchunk, nrank):
@@ -306,6 +312,15 @@ class Domain:
         npc = np.ascontiguousarray(npc, dtype=np.int64)
         self._ck(self.lib.nixb200_domain_set_particles(
             self.h, s, flat.ctypes.data_as(C.POINTER(C.c_double)), npc.ctypes.data_as(C.POINTER(C.c_int64))))
+
+    def reserve(self, s, np_=0, nmove=0):
+        """Room for np_ particles of species s (all chunks) and nmove migrating particles per step."""
+        self._ck(self.lib.nixb200_domain_reserve(self.h, s, int(np_), int(nmove)))
+
+    def capacity(self, s):
+        a, b = C.c_int64(0), C.c_int64(0)
+        self._ck(self.lib.nixb200_domain_get_capacity(self.h, s, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def get_np(self, s):
         a = np.zeros(self.nchunk, dtype=np.int64)

@@ -4,6 +4,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -171,7 +172,7 @@ __host__ __device__ inline int slab_entry(const Geo& g, int d, const int* b)
 // host-side error plumbing
 // ---------------------------------------------------------------------------------------------
 void        set_error(const std::string& msg);
-extern int64_t g_launches;
+extern std::atomic<int64_t> g_launches;
 
 #define NIX_CUDA(call)                                                                           \
   do {                                                                                           \
@@ -199,13 +200,14 @@ struct PushArgs {
   double*          uj; // [nchunk][Mz][My][Mx][4]
   SpeciesDev       sp;
   double           delt;
-  int*             err;
+  int*             err;    // err[0]: NIXB200_ERR_* bits; err[1]: sticky "store overflowed" flag (kernels exit)
   int              pusher; // NIXB200_PUSH_*
 };
 
 // ev: null, or four events recorded around the two kernels: ev[0] k_push ev[1] | ev[2] k_deposit ev[3]
 int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st,
                         cudaEvent_t* ev = nullptr);
+int push_deposit_prepare(int order); // per-device kernel attributes (call with the device current)
 size_t push_smem_bytes(const Geo& g);
 void   push_tile_box(int order, int& ez, int& ey, int& ex); // nodes per axis of the staged E/B tile
 int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits
@@ -216,6 +218,7 @@ int launch_peer_counts(const Geo& g, const SpeciesDev& sp, const PeerTabs& pt, i
                        cudaStream_t st);
 int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int* err,
                      cudaStream_t st);
+int launch_stats(const Geo& g, const SpeciesDev& sp, int32_t* out4, cudaStream_t st);
 int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int nrecv_particles,
                     int* err, cudaStream_t st);
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,

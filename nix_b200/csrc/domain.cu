@@ -15,7 +15,7 @@
 namespace nixb200
 {
 static thread_local std::string g_error;
-int64_t                         g_launches = 0;
+std::atomic<int64_t>            g_launches{0};
 
 void set_error(const std::string& msg)
 {
@@ -95,35 +95,48 @@ static int alloc_species_fixed(Domain* d, SpeciesDev& s)
   return 0;
 }
 
+static int64_t round_cap(int64_t n)
+{
+  return (n + 127) / 128 * 128;
+}
+
+static int alloc_leavers(Domain* d, SpeciesDev& s, int64_t lcap)
+{
+  s.lcap = lcap;
+  NIX_CUDA(cudaMalloc(&s.lrec, sizeof(int4) * lcap));
+  NIX_CUDA(cudaMalloc(&s.msg, sizeof(double) * NC * lcap));
+  NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
+  NIX_CUDA(cudaMemset(s.msgkey, 0xff, sizeof(int32_t) * lcap));
+  if (d->peer && peer_alloc_species(d, s)) return 1;
+  return 0;
+}
+
 static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
 {
   void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.paysend, s.payrecv};
   for (void* p : old)
     if (p) cudaFree(p);
+  s.xu = s.xv = nullptr;
+  s.key = s.ordl = nullptr;
+  s.lrec = nullptr;
+  s.msg = nullptr;
+  s.msgkey = nullptr;
   s.paysend = s.payrecv = nullptr;
   double f = d->desc.capacity_factor > 0 ? d->desc.capacity_factor : 1.25;
   if (f < 1.0) f = 1.0;
-  int64_t cap = (int64_t)((double)ntot * f) + 1024;
-  cap         = (cap + 127) / 128 * 128;
+  int64_t cap = round_cap((int64_t)((double)ntot * f) + 1024);
   if (cap >= (int64_t)1 << 31) {
     set_error("more than 2^31 particles of one species on one device");
     return 1;
   }
-  int64_t lcap = std::max<int64_t>(4096, cap / 4);
-  lcap         = (lcap + 127) / 128 * 128;
-  s.cap        = cap;
-  s.lcap       = lcap;
+  s.cap = cap;
   NIX_CUDA(cudaMalloc(&s.xu, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMalloc(&s.xv, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * cap));
   NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * cap));
-  NIX_CUDA(cudaMalloc(&s.lrec, sizeof(int4) * lcap));
-  NIX_CUDA(cudaMalloc(&s.msg, sizeof(double) * NC * lcap));
-  NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
   NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
-  if (d->peer && peer_alloc_species(d, s)) return 1;
-  return 0;
+  return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, cap / 4)));
 }
 
 static int check_chunk(Domain* d, int k)
@@ -159,6 +172,91 @@ int do_sort_species(Domain* d, SpeciesDev& s)
   std::swap(s.cbase, s.cbase_new); // Np = pindex(Ng), xtensor_particle.hpp:320
   return 0;
 }
+
+// The reference's containers grow on demand (XtensorParticle::resize from pre_unpack,
+// xtensor_halo3d.hpp:464-476).  Here the stores are sized once and regrown from the host BEFORE they fill
+// up: only xu carries state between steps (xv, key, ordl are scratch), and the move runs on the domain's
+// stream.
+int grow_particles(Domain* d, SpeciesDev& s, int64_t newcap)
+{
+  newcap = round_cap(newcap);
+  if (newcap <= s.cap) return 0;
+  if (newcap >= (int64_t)1 << 31) {
+    set_error("more than 2^31 particles of one species on one device");
+    return 1;
+  }
+  double*  nxu = nullptr;
+  double*  nxv = nullptr;
+  int32_t *nkey = nullptr, *nordl = nullptr;
+  NIX_CUDA(cudaMalloc(&nxu, sizeof(double) * NC * newcap));
+  NIX_CUDA(cudaMalloc(&nxv, sizeof(double) * NC * newcap));
+  NIX_CUDA(cudaMalloc(&nkey, sizeof(int32_t) * newcap));
+  NIX_CUDA(cudaMalloc(&nordl, sizeof(int32_t) * newcap));
+  NIX_CUDA(cudaMemsetAsync(nxu, 0, sizeof(double) * NC * newcap, d->stream));
+  NIX_CUDA(cudaMemsetAsync(nxv, 0, sizeof(double) * NC * newcap, d->stream));
+  for (int c = 0; c < NC; c++)
+    NIX_CUDA(cudaMemcpyAsync(nxu + (size_t)c * newcap, s.xu + (size_t)c * s.cap, sizeof(double) * s.cap,
+                             cudaMemcpyDeviceToDevice, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  cudaFree(s.xu);
+  cudaFree(s.xv);
+  cudaFree(s.key);
+  cudaFree(s.ordl);
+  s.xu = nxu, s.xv = nxv, s.key = nkey, s.ordl = nordl;
+  s.cap = newcap;
+  return 0;
+}
+
+int grow_leavers(Domain* d, SpeciesDev& s, int64_t newlcap, bool keep)
+{
+  newlcap = round_cap(newlcap);
+  if (newlcap <= s.lcap) return 0;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  int4*         olrec = s.lrec;
+  const int64_t olcap = s.lcap;
+  cudaFree(s.msg);
+  cudaFree(s.msgkey);
+  s.lrec = nullptr, s.msg = nullptr, s.msgkey = nullptr;
+  if (alloc_leavers(d, s, newlcap)) return 1; // (the peer payload buffers follow s.lcap)
+  if (keep) NIX_CUDA(cudaMemcpy(s.lrec, olrec, sizeof(int4) * olcap, cudaMemcpyDeviceToDevice));
+  cudaFree(olrec);
+  return 0;
+}
+
+// after a sort: (particles, leaver records, message particles) of every species -> pinned host memory
+int record_stats(Domain* d)
+{
+  const int ns = (int)d->sp.size();
+  for (int is = 0; is < ns; is++)
+    if (launch_stats(d->geo, d->sp[is], d->stat_dev + 4 * is, d->stream)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(d->stat_host, d->stat_dev, sizeof(int32_t) * 4 * ns, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaEventRecord(d->ev_stat, d->stream));
+  d->stat_pending = true;
+  return 0;
+}
+
+// before a push: look at what the last sort reported and make room.  The wait is for work that was
+// enqueued a whole step ago.
+static int ensure_capacity(Domain* d)
+{
+  if (!d->stat_pending) return 0;
+  NIX_CUDA(cudaEventSynchronize(d->ev_stat));
+  d->stat_pending = false;
+  for (size_t is = 0; is < d->sp.size(); is++) {
+    SpeciesDev&    s  = d->sp[is];
+    const int32_t* st = d->stat_host + 4 * is;
+    const int64_t  total = st[0], moving = std::max(st[1], st[2]);
+    if (total > s.cap || moving > s.lcap) {
+      set_error("particle store overflowed during the last step (raise capacity_factor or call nixb200_domain_reserve): "
+                "the particles of this domain are lost");
+      return 1;
+    }
+    // headroom for one more step: what moved last step may arrive on top
+    if (total + 2 * moving + 1024 > s.cap && grow_particles(d, s, (int64_t)(1.25 * (double)(total + 2 * moving)) + 4096)) return 1;
+    if (2 * moving > s.lcap && grow_leavers(d, s, 4 * moving, false)) return 1;
+  }
+  return 0;
+}
 } // namespace nixb200
 
 using namespace nixb200;
@@ -166,6 +264,25 @@ using namespace nixb200;
 static Domain* D(nixb200_domain* d)
 {
   return reinterpret_cast<Domain*>(d);
+}
+
+// every entry point that takes a domain runs with the domain's device current and restores the
+// caller's device on return (several domains on several devices may live in one process / thread)
+#define NIX_ENTER(dd)                                                                            \
+  Domain* d = D(dd);                                                                             \
+  if (!d) {                                                                                      \
+    set_error("null domain");                                                                    \
+    return 1;                                                                                    \
+  }                                                                                              \
+  DeviceGuard dev_guard__(d->desc.device)
+
+static int need_peers(Domain* d)
+{
+  if (d->has_remote && !d->peer) {
+    set_error("a neighbour chunk lives on another rank: call nixb200_domain_set_ranks (and comm_init) first");
+    return 1;
+  }
+  return 0;
 }
 
 extern "C" {
@@ -198,7 +315,12 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
     set_error("no CUDA device: libnixb200 has no CPU fallback");
     return 1;
   }
-  NIX_CUDA(cudaSetDevice(desc->device));
+  DeviceGuard dev_guard(desc->device);
+  int         cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != desc->device) {
+    set_error("cannot select CUDA device " + std::to_string(desc->device));
+    return 1;
+  }
   cudaDeviceProp prop;
   NIX_CUDA(cudaGetDeviceProperties(&prop, desc->device));
   if (prop.major != 10) {
@@ -312,7 +434,10 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
       int id = grid2id[(n[0] * cd[1] + n[1]) * cd[2] + n[2]];
       if (id < 0) cg.nbr[s] = -1;
       else if (id >= desc->id_begin && id < desc->id_end) cg.nbr[s] = id - desc->id_begin;
-      else cg.nbr[s] = -2; // lives on another rank
+      else {
+        cg.nbr[s]     = -2; // lives on another rank
+        d->has_remote = true;
+      }
     }
   }
 
@@ -323,6 +448,13 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
     return 1;
   };
   if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
+  d->owns_stream = true;
+  if (push_deposit_prepare(g.order)) {
+    std::string e = g_error;
+    nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(d));
+    set_error(e);
+    return 1;
+  }
   if (cudaMalloc(&d->cg_dev, sizeof(ChunkGeo) * g.nchunk) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMemcpy(d->cg_dev, d->cg_host.data(), sizeof(ChunkGeo) * g.nchunk, cudaMemcpyHostToDevice) != cudaSuccess)
     return fail("cudaMemcpy");
@@ -331,8 +463,11 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
   cudaMemset(d->uf, 0, sizeof(double) * 6 * d->cells_per_chunk * g.nchunk);
   cudaMemset(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * g.nchunk);
   if (cudaMalloc(&d->scan_tmp, scan_tmp_bytes((size_t)g.nchunk * g.ncell * LANES)) != cudaSuccess) return fail("cudaMalloc scan");
-  if (cudaMalloc(&d->err_dev, sizeof(int)) != cudaSuccess) return fail("cudaMalloc err");
-  cudaMemset(d->err_dev, 0, sizeof(int));
+  if (cudaMalloc(&d->err_dev, 2 * sizeof(int)) != cudaSuccess) return fail("cudaMalloc err");
+  cudaMemset(d->err_dev, 0, 2 * sizeof(int));
+  if (cudaMalloc(&d->stat_dev, sizeof(int32_t) * 4 * desc->ns) != cudaSuccess) return fail("cudaMalloc stat");
+  if (cudaMallocHost(&d->stat_host, sizeof(int32_t) * 4 * desc->ns) != cudaSuccess) return fail("cudaMallocHost stat");
+  cudaEventCreateWithFlags(&d->ev_stat, cudaEventDisableTiming);
   if (cudaMalloc(&d->nbvalid_dev, sizeof(int) * 27) != cudaSuccess) return fail("cudaMalloc");
   d->halo_buf_bytes = sizeof(double) * 6 * d->cells_per_chunk;
   if (cudaMalloc(&d->halo_buf, d->halo_buf_bytes) != cudaSuccess) return fail("cudaMalloc halo");
@@ -370,6 +505,7 @@ int nixb200_domain_destroy(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return 0;
+  DeviceGuard dev_guard(d->desc.device);
   cudaDeviceSynchronize();
   peer_destroy(d);
   for (auto& s : d->sp) free_species(s);
@@ -378,6 +514,9 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->uj) cudaFree(d->uj);
   if (d->scan_tmp) cudaFree(d->scan_tmp);
   if (d->err_dev) cudaFree(d->err_dev);
+  if (d->stat_dev) cudaFree(d->stat_dev);
+  if (d->stat_host) cudaFreeHost(d->stat_host);
+  if (d->ev_stat) cudaEventDestroy(d->ev_stat);
   if (d->nbvalid_dev) cudaFree(d->nbvalid_dev);
   if (d->halo_buf) cudaFree(d->halo_buf);
   if (d->ev0) cudaEventDestroy(d->ev0);
@@ -389,24 +528,24 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   for (int w = 0; w < 2; w++)
     if (d->dense[w]) cudaFree(d->dense[w]);
   if (d->copy_stream) cudaStreamDestroy(d->copy_stream);
-  if (d->stream) cudaStreamDestroy(d->stream);
+  if (d->stream && d->owns_stream) cudaStreamDestroy(d->stream); // never a stream the caller handed over
   delete d;
   return 0;
 }
 
 int nixb200_domain_set_stream(nixb200_domain* dd, void* cuda_stream)
 {
-  Domain* d = D(dd);
-  if (!d) return 1;
+  NIX_ENTER(dd);
   NIX_CUDA(cudaStreamSynchronize(d->stream));
-  // the previously owned stream (if any) is leaked on purpose: it may be the caller's
-  d->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  if (d->owns_stream) cudaStreamDestroy(d->stream); // the library's own stream; a caller's stream is never destroyed
+  d->stream      = reinterpret_cast<cudaStream_t>(cuda_stream);
+  d->owns_stream = false;
   return 0;
 }
 
 int nixb200_domain_synchronize(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   return 0;
@@ -414,17 +553,19 @@ int nixb200_domain_synchronize(nixb200_domain* dd)
 
 int nixb200_domain_check(nixb200_domain* dd, int* errbits)
 {
-  Domain* d = D(dd);
-  if (!d || !errbits) return 1;
-  NIX_CUDA(cudaMemcpyAsync(errbits, d->err_dev, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
-  NIX_CUDA(cudaMemsetAsync(d->err_dev, 0, sizeof(int), d->stream));
+  NIX_ENTER(dd);
+  if (!errbits) return 1;
+  int e[2] = {0, 0};
+  NIX_CUDA(cudaMemcpyAsync(e, d->err_dev, 2 * sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaMemsetAsync(d->err_dev, 0, sizeof(int), d->stream)); // the overflow flag e[1] stays until new particles are set
   NIX_CUDA(cudaStreamSynchronize(d->stream));
+  *errbits = e[0] | (e[1] ? NIXB200_ERR_CAPACITY : 0);
   return 0;
 }
 
 int nixb200_chunk_field_upload(nixb200_domain* dd, int k, int which, const double* host)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || !host) return 1;
   int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
   double* dst = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
@@ -435,7 +576,7 @@ int nixb200_chunk_field_upload(nixb200_domain* dd, int k, int which, const doubl
 
 int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* host)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || !host) return 1;
   int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
   const double* src = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
@@ -446,7 +587,7 @@ int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* h
 
 int nixb200_domain_field_upload_async(nixb200_domain* dd, int which, const double* host)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d || !host) return 1;
   int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
   double* dst = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
@@ -456,7 +597,7 @@ int nixb200_domain_field_upload_async(nixb200_domain* dd, int which, const doubl
 
 int nixb200_domain_field_download_async(nixb200_domain* dd, int which, double* host)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d || !host) return 1;
   int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
   const double* src = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
@@ -489,6 +630,7 @@ static int mark_main_done(Domain* d, int w)
 static int field_copy_overlapped(Domain* d, int which, double* host, bool upload, bool interior)
 {
   if (!d || !host) return 1;
+  DeviceGuard  dev_guard(d->desc.device);
   const int    w     = field_index(which);
   const int    nc    = (w == 0) ? 6 : 4;
   const Geo&   g     = d->geo;
@@ -535,7 +677,7 @@ int nixb200_domain_field_download_overlapped(nixb200_domain* dd, int which, doub
 
 int nixb200_domain_copy_synchronize(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
   NIX_CUDA(cudaStreamSynchronize(d->copy_stream));
   return 0;
@@ -543,7 +685,7 @@ int nixb200_domain_copy_synchronize(nixb200_domain* dd)
 
 int nixb200_domain_set_profiling(nixb200_domain* dd, int on)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
   d->profiling = on != 0;
   return 0;
@@ -551,7 +693,7 @@ int nixb200_domain_set_profiling(nixb200_domain* dd, int on)
 
 int nixb200_domain_get_phase_ms(nixb200_domain* dd, int phase, double* ms_sum, int* calls)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d || phase < 0 || phase >= NIXB200_NPHASE || !ms_sum || !calls) return 1;
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   for (auto& pr : d->pending[phase]) {
@@ -573,7 +715,7 @@ int nixb200_domain_get_phase_ms(nixb200_domain* dd, int phase, double* ms_sum, i
 
 int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_aos, const int64_t* np_chunk)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_species(d, is) || !np_chunk) return 1;
   const Geo&           g = d->geo;
   std::vector<int32_t> cbase(g.nchunk + 1, 0);
@@ -592,6 +734,8 @@ int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_ao
   }
   SpeciesDev& s = d->sp[is];
   NIX_CUDA(cudaStreamSynchronize(d->stream));
+  d->stat_pending = false;
+  NIX_CUDA(cudaMemsetAsync(d->err_dev + 1, 0, sizeof(int), d->stream)); // fresh particles: the overflow flag goes
   if (alloc_species_particles(d, s, ntot)) return 1;
   NIX_CUDA(cudaMemcpyAsync(s.cbase, cbase.data(), sizeof(int32_t) * (g.nchunk + 1), cudaMemcpyHostToDevice, d->stream));
   if (ntot > 0) {
@@ -611,7 +755,7 @@ int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_ao
 
 int nixb200_domain_get_np(nixb200_domain* dd, int is, int64_t* np_chunk)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_species(d, is) || !np_chunk) return 1;
   const Geo&           g = d->geo;
   std::vector<int32_t> cbase(g.nchunk + 1);
@@ -623,7 +767,7 @@ int nixb200_domain_get_np(nixb200_domain* dd, int is, int64_t* np_chunk)
 
 int nixb200_chunk_get_particles(nixb200_domain* dd, int k, int is, double* xu_aos, int64_t max_np, int64_t* np)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || check_species(d, is) || !np) return 1;
   SpeciesDev& s = d->sp[is];
   int32_t     cb[2];
@@ -646,7 +790,7 @@ int nixb200_chunk_get_particles(nixb200_domain* dd, int k, int is, double* xu_ao
 // expand the device's compact rows [0, ncell) (+ out-of-bounds row) to the reference's [Ng+1] layout
 int nixb200_chunk_get_pindex(nixb200_domain* dd, int k, int is, int32_t* pindex)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || check_species(d, is) || !pindex) return 1;
   const Geo&           g = d->geo;
   SpeciesDev&          s = d->sp[is];
@@ -663,7 +807,7 @@ int nixb200_chunk_get_pindex(nixb200_domain* dd, int k, int is, int32_t* pindex)
 
 int nixb200_chunk_get_pcount(nixb200_domain* dd, int k, int is, int32_t* pcount)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || check_species(d, is) || !pcount) return 1;
   const Geo&           g = d->geo;
   SpeciesDev&          s = d->sp[is];
@@ -682,19 +826,19 @@ int nixb200_chunk_get_pcount(nixb200_domain* dd, int k, int is, int32_t* pcount)
 
 int nixb200_domain_sort(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
   PhaseTimer pt(d, 4);
   for (auto& s : d->sp) {
     if (launch_count_only(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
     if (do_sort_species(d, s)) return 1;
   }
-  return 0;
+  return record_stats(d);
 }
 
 int nixb200_domain_clear_current(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
   if (wait_copy(d, 1)) return 1;
   NIX_CUDA(cudaMemsetAsync(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * d->geo.nchunk, d->stream));
@@ -703,8 +847,9 @@ int nixb200_domain_clear_current(nixb200_domain* dd)
 
 int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
+  if (ensure_capacity(d)) return 1;
   if (wait_copy(d, 0) || wait_copy(d, 1)) return 1;
   PhaseTimer pt(d, 0);
   NIX_CUDA(cudaEventRecord(d->ev0, d->stream));
@@ -733,9 +878,9 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
 
 int nixb200_domain_exchange_current(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
-  if (wait_copy(d, 1)) return 1;
+  if (need_peers(d) || wait_copy(d, 1)) return 1;
   {
     PhaseTimer pt(d, 1);
     if (peer_exchange_halo(d, NIXB200_MODE_CURRENT)) return 1;
@@ -746,9 +891,9 @@ int nixb200_domain_exchange_current(nixb200_domain* dd)
 
 int nixb200_domain_exchange_field(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
-  if (wait_copy(d, 0)) return 1;
+  if (need_peers(d) || wait_copy(d, 0)) return 1;
   {
     PhaseTimer pt(d, 2);
     if (peer_exchange_halo(d, NIXB200_MODE_FIELD)) return 1;
@@ -759,17 +904,18 @@ int nixb200_domain_exchange_field(nixb200_domain* dd)
 
 int nixb200_domain_migrate_sort(nixb200_domain* dd)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d) return 1;
+  if (need_peers(d)) return 1;
   PhaseTimer pt(d, 3);
-  if (d->peer) return peer_migrate(d);
+  if (d->peer) return peer_migrate(d) || record_stats(d);
   const PeerTabs none = peer_tabs(d);
   for (auto& s : d->sp) {
     if (launch_mig_scan(d->geo, s, d->stream)) return 1;
     if (launch_mig_route(d->geo, d->cg_dev, s, none, d->err_dev, d->stream)) return 1;
     if (do_sort_species(d, s)) return 1;
   }
-  return 0;
+  return record_stats(d);
 }
 
 int nixb200_domain_step(nixb200_domain* dd, double delt)
@@ -784,7 +930,7 @@ int nixb200_domain_step(nixb200_domain* dd, double delt)
 
 int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufaddr27)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d || !bufsize27 || !bufaddr27) return 1;
   if (mode != NIXB200_MODE_FIELD && mode != NIXB200_MODE_CURRENT) {
     set_error("halo_layout: fixed layouts exist for field and current only");
@@ -811,7 +957,7 @@ int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufad
 
 int nixb200_chunk_halo_pack(nixb200_domain* dd, int k, int mode, void* host_sendbuf)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || !host_sendbuf) return 1;
   int bs[27], ba[27];
   if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
@@ -825,7 +971,7 @@ int nixb200_chunk_halo_pack(nixb200_domain* dd, int k, int mode, void* host_send
 
 int nixb200_chunk_halo_unpack(nixb200_domain* dd, int k, int mode, const void* host_recvbuf, const int* nbvalid27)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (check_chunk(d, k) || !host_recvbuf) return 1;
   int bs[27], ba[27];
   if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
@@ -840,9 +986,27 @@ int nixb200_chunk_halo_unpack(nixb200_domain* dd, int k, int mode, const void* h
   return 0;
 }
 
+int nixb200_domain_reserve(nixb200_domain* dd, int is, int64_t np, int64_t nmove)
+{
+  NIX_ENTER(dd);
+  if (check_species(d, is)) return 1;
+  if (np > d->sp[is].cap && grow_particles(d, d->sp[is], np)) return 1;
+  if (nmove > d->sp[is].lcap && grow_leavers(d, d->sp[is], nmove, false)) return 1;
+  return 0;
+}
+
+int nixb200_domain_get_capacity(nixb200_domain* dd, int is, int64_t* np, int64_t* nmove)
+{
+  NIX_ENTER(dd);
+  if (check_species(d, is)) return 1;
+  if (np) *np = d->sp[is].cap;
+  if (nmove) *nmove = d->sp[is].lcap;
+  return 0;
+}
+
 int nixb200_domain_get_load(nixb200_domain* dd, double* ms)
 {
-  Domain* d = D(dd);
+  NIX_ENTER(dd);
   if (!d || !ms) return 1;
   *ms = 0.0;
   if (!d->timed) return 0;
@@ -857,6 +1021,7 @@ int64_t nixb200_domain_total_particles(nixb200_domain* dd)
 {
   Domain* d = D(dd);
   if (!d) return -1;
+  DeviceGuard dev_guard(d->desc.device);
   int64_t tot = 0;
   for (auto& s : d->sp) {
     int32_t n = 0;

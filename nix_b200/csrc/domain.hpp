@@ -19,6 +19,14 @@ struct Domain {
   double*                 uj     = nullptr;
   std::vector<SpeciesDev> sp;
   cudaStream_t            stream = nullptr;
+  bool                    owns_stream = false; // false once the caller has handed over its own stream
+  bool                    has_remote  = false; // a neighbour chunk lives on another rank (needs set_ranks + comm)
+  // capacity bookkeeping: after every sort the device reports, per species, (total particles, leaver
+  // records, message particles) to pinned host memory; the next step grows the stores before they fill up
+  int32_t*                stat_host    = nullptr; // pinned [ns][4]
+  int32_t*                stat_dev     = nullptr; // device [ns][4]
+  cudaEvent_t             ev_stat      = nullptr;
+  bool                    stat_pending = false;
   CUtensorMap             tmap;
   void*                   scan_tmp = nullptr;
   int*                    err_dev  = nullptr;
@@ -64,6 +72,25 @@ struct PhaseTimer {
   }
 };
 
+
+// restores the caller's current device on scope exit (every entry point runs on the domain's device)
+struct DeviceGuard {
+  int  prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int dev)
+  {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard()
+  {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
+// domain.cu
+int grow_particles(Domain* d, SpeciesDev& s, int64_t newcap);           // keeps xu
+int grow_leavers(Domain* d, SpeciesDev& s, int64_t newlcap, bool keep); // keep: lrec survives
+int record_stats(Domain* d);
 
 // peer.cu
 PeerTabs peer_tabs(const Domain* d);

@@ -354,9 +354,10 @@ int peer_migrate(Domain* d)
     }
     rpoff[c->nrecv] = (int32_t)run;
     nrecvd[is]      = run;
+    // every rank must reach the payload group below with the sizes both sides agreed on: a buffer that
+    // is too small is regrown here (the host knows the exact counts), never a reason to leave early
     if (nsent[is] > d->sp[is].lcap || nrecvd[is] > d->sp[is].lcap) {
-      set_error("migration buffer too small for the particles crossing rank boundaries (raise capacity_factor)");
-      return 1;
+      if (grow_leavers(d, d->sp[is], 2 * std::max(nsent[is], nrecvd[is]), true)) return 1;
     }
     c->last_sent += nsent[is];
     c->last_received += nrecvd[is];
@@ -526,7 +527,7 @@ int nixb200_domain_set_ranks(nixb200_domain* dd, int nrank, const int* boundary,
     set_error("set_ranks: boundary[rank], boundary[rank+1] must equal the domain's id range");
     return 1;
   }
-  NIX_CUDA(cudaSetDevice(d->desc.device));
+  DeviceGuard dev_guard(d->desc.device);
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   Plan* p = plan_build(d->desc.cdims, d->desc.dims, d->desc.nb, d->coord_all.data(), nrank, boundary, rank);
   if (!p) return 1;
@@ -553,7 +554,7 @@ int nixb200_domain_comm_init(nixb200_domain* dd, const void* id128)
   }
   Nccl* n = nccl();
   if (!n) return 1;
-  NIX_CUDA(cudaSetDevice(d->desc.device));
+  DeviceGuard dev_guard(d->desc.device);
   ncclUniqueId id;
   std::memcpy(&id, id128, sizeof(id));
   NIX_NCCL(n->CommInitRank(&d->peer->comm, d->peer->plan->nrank, id, d->peer->plan->rank));

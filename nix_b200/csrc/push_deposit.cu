@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   constexpr int EY = C::EY, EX = C::EX;
   constexpr int esy = EX * 6, esz = EY * EX * 6;
 
+  if (P.err[1]) return; // a particle store overflowed earlier: the cell ranges no longer describe memory
   extern __shared__ __align__(1024) double smem_d[];
   double*   s_eb   = smem_d;
   double*   s_pf   = smem_d + C::EB_DOUBLES;
@@ -856,6 +857,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   constexpr int JZ = C::JZ, JY = C::JY, JX = C::JX;
   constexpr int REC_D = (DWARPS * MAXMOV * CREC + 15) / 16 * 16;
 
+  if (P.err[1]) return;
   extern __shared__ __align__(1024) double smem_d[];
   double*   s_j    = smem_d;
   double*   s_rec  = s_j + C::J_DOUBLES;
@@ -1169,12 +1171,6 @@ int launch_split_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st, 
   for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
   P.err = a.err;
   P.pusher = a.pusher;
-  static bool attr_set = false;
-  if (!attr_set) {
-    NIX_CUDA(cudaFuncSetAttribute(k_push<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    NIX_CUDA(cudaFuncSetAttribute(k_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-    attr_set = true;
-  }
   int nblocks = a.geo.nchunk * a.geo.ntile;
   if (ev) cudaEventRecord(ev[0], st);
   k_push<O, S><<<nblocks, PTHREADS, push_smem<O>(), st>>>(*tmap, P);
@@ -1189,7 +1185,26 @@ int launch_split_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st, 
   return 0;
 }
 
+template <int O, bool S>
+int prepare_t()
+{
+  NIX_CUDA(cudaFuncSetAttribute(k_push<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  NIX_CUDA(cudaFuncSetAttribute(k_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  return 0;
+}
 } // namespace
+
+// The dynamic shared-memory limit is a per-DEVICE attribute of a kernel: set for the current device by
+// every nixb200_domain_create (cheap; several domains on several devices may live in one process).
+int push_deposit_prepare(int order)
+{
+  switch (order) {
+  case 1: return prepare_t<1, true>() || prepare_t<1, false>();
+  case 2: return prepare_t<2, true>() || prepare_t<2, false>();
+  case 3: return prepare_t<3, true>() || prepare_t<3, false>();
+  default: set_error("order must be 1, 2 or 3"); return 1;
+  }
+}
 
 size_t push_smem_bytes(const Geo& g)
 {

@@ -198,6 +198,27 @@ __device__ __forceinline__ void deliver(const Geo& g, const ChunkGeo* __restrict
   sp.msgkey[m] = key;
 }
 
+// The leaver list or the message buffer overflowed (k_push dropped records, or more particles arrive
+// than fit): message slots that nobody fills must not be consumed with last step's content.  Normally
+// exits at once.
+__global__ void k_mig_guard(SpeciesDev sp, int* err)
+{
+  if (*sp.nleave <= sp.lcap && *sp.nmsg <= sp.lcap) return;
+  if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(err, NIXB200_ERR_CAPACITY);
+  for (int64_t m = blockIdx.x * blockDim.x + threadIdx.x; m < sp.lcap; m += (int64_t)gridDim.x * blockDim.x)
+    sp.msgkey[m] = -1;
+}
+
+// what the host needs to grow the stores in time: particles after the sort, leaver records, messages
+__global__ void k_stats(Geo g, SpeciesDev sp, int32_t* __restrict__ out4)
+{
+  const size_t nkey = (size_t)g.nchunk * g.ncell * LANES;
+  out4[0] = sp.start[nkey];
+  out4[1] = *sp.nleave;
+  out4[2] = *sp.nmsg;
+  out4[3] = 0;
+}
+
 // one thread per leaver: destination chunk, pre-sort index there, periodic wrap, count
 // (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
 __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt, int* err)
@@ -402,7 +423,10 @@ __global__ void k_chunk_bases(Geo g, SpeciesDev sp, const int32_t* __restrict__ 
   int          c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c == 0) {
     sp.start[n] = *total;
-    if (*total > sp.cap) atomicOr(err, NIXB200_ERR_CAPACITY);
+    if (*total > sp.cap) { // the sorted array would not fit: place / gather and every later kernel stand down
+      atomicOr(err, NIXB200_ERR_CAPACITY);
+      err[1] = 1;
+    }
   }
   if (c < g.nchunk) sp.cbase_new[c] = sp.start[(size_t)c * g.ncell * LANES];
   if (c == g.nchunk) sp.cbase_new[c] = *total;
@@ -411,8 +435,9 @@ __global__ void k_chunk_bases(Geo g, SpeciesDev sp, const int32_t* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 // place: drop each particle's pre-sort index into its bin (any order)
 // ---------------------------------------------------------------------------------------------
-__global__ void k_place(Geo g, SpeciesDev sp)
+__global__ void k_place(Geo g, SpeciesDev sp, const int* __restrict__ err)
 {
+  if (err[1]) return;
   const int ntot = sp.cbase[g.nchunk];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
     int k = sp.key[i];
@@ -422,8 +447,9 @@ __global__ void k_place(Geo g, SpeciesDev sp)
   }
 }
 
-__global__ void k_place_msg(Geo g, SpeciesDev sp)
+__global__ void k_place_msg(Geo g, SpeciesDev sp, const int* __restrict__ err)
 {
+  if (err[1]) return;
   const int nm = min(*sp.nmsg, (int)sp.lcap);
   for (int m = blockIdx.x * blockDim.x + threadIdx.x; m < nm; m += gridDim.x * blockDim.x) {
     int k = sp.msgkey[m];
@@ -439,8 +465,9 @@ __global__ void k_place_msg(Geo g, SpeciesDev sp)
 // (xtensor_particle.hpp:303-313).  Unsigned compare: received particles (top bit set) follow the
 // residents.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_gather(Geo g, SpeciesDev sp)
+__global__ void __launch_bounds__(256) k_gather(Geo g, SpeciesDev sp, const int* __restrict__ err)
 {
+  if (err[1]) return;
   const size_t nkey = (size_t)g.nchunk * g.ncell * LANES;
   const int    ntot = min(sp.start[nkey], (int)sp.cap);
   const int32_t* __restrict__ ordl = sp.ordl;
@@ -513,7 +540,16 @@ int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const Pee
 {
   k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp, pt);
   NIX_LAUNCHED();
+  k_mig_guard<<<148, 256, 0, st>>>(sp, err);
+  NIX_LAUNCHED();
   k_mig_key<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, err);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+int launch_stats(const Geo& g, const SpeciesDev& sp, int32_t* out4, cudaStream_t st)
+{
+  k_stats<<<1, 1, 0, st>>>(g, sp, out4);
   NIX_LAUNCHED();
   return 0;
 }
@@ -545,11 +581,11 @@ int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void
   NIX_LAUNCHED();
   k_chunk_bases<<<(g.nchunk + 1 + 255) / 256, 256, 0, st>>>(g, sp, total, err);
   NIX_LAUNCHED();
-  k_place<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp);
+  k_place<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp, err);
   NIX_LAUNCHED();
-  k_place_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp);
+  k_place_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp, err);
   NIX_LAUNCHED();
-  k_gather<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp);
+  k_gather<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp, err);
   NIX_LAUNCHED();
   return 0;
 }

@@ -7,14 +7,12 @@ the GPU run the same arrays.
 """
 import numpy as np
 
+from .sfc import chunk_coords
 
-def gilbert_like_order(cdims):
-    """Boustrophedon (snake) chunk order: consecutive ids are always face neighbours.
 
-    The reference orders chunks along a generalised Hilbert curve (sfc.cpp); the hot path only
-    needs *some* id -> coordinate table (nixb200_domain_create takes it as an argument), and the
-    snake order shares the locality property that matters for rank partitioning.
-    """
+def snake_order(cdims):
+    """Boustrophedon chunk order (consecutive ids are face neighbours).  NOT the reference's curve: kept
+    only as a second, different id -> coordinate table for tests (the hot path takes any table)."""
     cz, cy, cx = cdims
     out = []
     for z in range(cz):
@@ -41,7 +39,7 @@ class Problem:
         self.m = np.array(m[:ns], dtype=np.float64)
         self.delh = tuple(delh)
         self.nchunk = int(np.prod(self.cdims))
-        self.coord = np.asarray(coord, dtype=np.int32) if coord is not None else gilbert_like_order(self.cdims)
+        self.coord = np.asarray(coord, dtype=np.int32) if coord is not None else chunk_coords(self.cdims)
         self.M = tuple(d + 2 * self.nb for d in self.dims)
         self.seed = seed
         self.vth = vth

@@ -7,6 +7,7 @@ import os
 import numpy as np
 import pytest
 
+from nix_b200 import core
 from nix_b200.synth import Problem
 from oracle import nixoracle as no
 
@@ -354,4 +355,63 @@ def test_interior_transfers(gpu_lib):
     assert gd.check() == 0
     for k in range(gd.nchunk):
         assert np.array_equal(bits(uji.numpy()[k]), bits(gd.get_current(k)[inner])), f"J chunk {k}"
+    gd.close()
+
+
+# ---- particle storage: growth and overflow (sort.cu:405, push_deposit.cu:814) ----------
+def _stream_problem(n=40000):
+    """Two chunks of (8, 8, 2) cells side by side in x; every particle flies in +x at ~c, so c*dt/dx of a
+    chunk's particles cross into the neighbour every step."""
+    prob = Problem((1, 1, 2), (8, 8, 2), 2, ppc=1, ns=1, seed=5, vth=(0.0,), amp=0.0, b0=0.0)
+
+    def particles(k, s, prob=prob):
+        rng = np.random.default_rng([99, k])
+        xu = np.zeros((n, 7))
+        xu[:, 0] = 2.0 * k + rng.uniform(0.0, 2.0, n) * (1 - 1e-12)
+        xu[:, 1] = rng.uniform(0.0, 8.0, n) * (1 - 1e-12)
+        xu[:, 2] = rng.uniform(0.0, 8.0, n) * (1 - 1e-12)
+        xu[:, 3] = 50.0  # u_x: v = 0.9998 c
+        xu[:, 6] = (np.arange(n, dtype=np.int64) + (np.int64(k) << 32)).view(np.float64)
+        return xu
+    prob.particles = particles
+    return prob
+
+
+def test_migration_buffers_regrow_before_they_fill(oracle_port, gpu_lib):
+    """15 % of the particles leave in step 1 (buffers hold 25 %): the next step regrows the buffers, so the
+    45 % that leave in step 2 fit.  Particles stay bit-exact with the oracle throughout."""
+    prob = _stream_problem()
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True, capacity_factor=1.0)
+    cap0, lcap0 = gd.capacity(0)
+    assert lcap0 < 0.3 * 2 * 40000
+    for dt in (0.3, 0.9, 0.9):
+        od.step(dt, 1.0)
+        gd.step(dt)
+        assert gd.check() == 0
+        assert_particles_equal(od, gd, f"dt {dt}")
+    cap1, lcap1 = gd.capacity(0)
+    assert lcap1 > lcap0, "the migration buffers did not grow"
+    gd.close()
+
+
+def test_migration_overflow_is_an_error_not_a_memory_fault(oracle_port, gpu_lib):
+    """45 % leave in the very first step, more than the buffers hold and with nothing to warn the host:
+    ERR_CAPACITY, no out-of-bounds access, and the next step refuses to run; with room reserved up front
+    the same run is bit-exact."""
+    prob = _stream_problem()
+    gd = gpu_domain(prob, strict=True, capacity_factor=1.0)
+    gd.step(0.9)
+    assert gd.check() & core.ERR_CAPACITY
+    with pytest.raises(core.NixB200Error, match="overflowed"):
+        gd.step(0.9)
+    gd.close()
+    od = oracle_domain(oracle_port, prob)
+    gd = gpu_domain(prob, strict=True, capacity_factor=1.0)
+    gd.reserve(0, nmove=60000)
+    for _ in range(2):
+        od.step(0.9, 1.0)
+        gd.step(0.9)
+        assert gd.check() == 0
+        assert_particles_equal(od, gd, "reserved")
     gd.close()

@@ -2,8 +2,9 @@
 migration across ranks over NCCL (csrc/peer.cu), against the single-process CPU oracle of the whole
 box.  Strict mode => particles, counts and E/B bit-exact; J <= 1e-12 of its maximum.
 
-The 2-rank tests need 2 GPUs (`gpurun --gpus 2`); on a 1-GPU box they skip and only the
-single-rank pass through the multi-rank code path runs."""
+The N-rank tests need N GPUs (`gpurun --gpus N`); on a 1-GPU box they skip and only the single-rank
+pass through the multi-rank code path runs.  The logs of the 2/4/8-GPU runs of this file are kept
+under profiles/ (r02_multirank_n*.log)."""
 import os
 import socket
 import sys
@@ -131,19 +132,111 @@ def _worker(rank, world, port, cdims, dims, order, steps, q):
         q.put((rank, "fail: " + "".join(traceback.format_exception(exc))))
 
 
-@pytest.mark.parametrize("cdims,dims,order", [((2, 2, 2), (8, 8, 8), 2), ((1, 2, 3), (6, 8, 10), 1),
-                                              ((2, 2, 4), (8, 8, 8), 3), ((1, 1, 2), (8, 8, 8), 2)])
-def test_two_ranks_equal_single_process_oracle(oracle_port, gpu_lib, cdims, dims, order):
+def _run_ranks(world, target, args, timeout=420):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs (gpurun --gpus {world})")
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, cdims, dims, order, 3, q)) for r in range(2)]
+    procs = [ctx.Process(target=target, args=(r, world, port) + tuple(args) + (q,)) for r in range(world)]
     for p in procs:
         p.start()
-    res = _collect(q, procs, 240)
+    res = _collect(q, procs, timeout)
     for rank, status in res:
         assert status == "ok", f"rank {rank}: {status}"
+
+
+@pytest.mark.parametrize("cdims,dims,order", [((2, 2, 2), (8, 8, 8), 2), ((1, 2, 3), (6, 8, 10), 1),
+                                              ((2, 2, 4), (8, 8, 8), 3), ((1, 1, 2), (8, 8, 8), 2)])
+def test_two_ranks_equal_single_process_oracle(oracle_port, gpu_lib, cdims, dims, order):
+    _run_ranks(2, _worker, (cdims, dims, order, 3))
+
+
+# 4 and 8 ranks: contiguous segments of the reference's Gilbert curve (nix_b200/sfc.py) -- a rank's
+# chunks touch several other ranks through faces, edges and corners, and some ranks are not neighbours
+@pytest.mark.parametrize("cdims,dims,order", [((4, 4, 2), (8, 8, 8), 2), ((4, 4, 2), (8, 8, 8), 3),
+                                              ((2, 3, 4), (6, 8, 10), 1)])
+def test_four_ranks_equal_single_process_oracle(oracle_port, gpu_lib, cdims, dims, order):
+    _run_ranks(4, _worker, (cdims, dims, order, 3))
+
+
+@pytest.mark.parametrize("cdims,dims,order", [((4, 4, 2), (8, 8, 8), 2), ((4, 4, 2), (8, 8, 8), 3),
+                                              ((4, 4, 4), (8, 8, 8), 2), ((2, 2, 2), (16, 16, 16), 2)])
+def test_eight_ranks_equal_single_process_oracle(oracle_port, gpu_lib, cdims, dims, order):
+    _run_ranks(8, _worker, (cdims, dims, order, 3))
+
+
+def _growth_worker(rank, world, port, reserve, q):
+    """Rank 0 owns a chunk full of particles that all fly in +x, rank 1 an empty one sized for nothing:
+    rank 1's store must grow as they arrive (the reference resizes in pre_unpack,
+    xtensor_halo3d.hpp:464-476)."""
+    try:
+        import torch
+        import torch.distributed as dist
+        from nix_b200 import core
+        from oracle import nixoracle as no
+        from helpers import oracle_domain
+        torch.cuda.set_device(rank)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        n = 30000
+        prob = Problem((1, 1, 2), (8, 8, 8), 2, ppc=1, ns=1, seed=5, vth=(0.0,), amp=0.0, b0=0.0)
+
+        def particles(k, s):
+            m = n if k == 0 else 0
+            rng = np.random.default_rng([77, k])
+            xu = np.zeros((m, 7))
+            xu[:, 0] = rng.uniform(0.0, 8.0, m) * (1 - 1e-12)
+            xu[:, 1] = rng.uniform(0.0, 8.0, m) * (1 - 1e-12)
+            xu[:, 2] = rng.uniform(0.0, 8.0, m) * (1 - 1e-12)
+            xu[:, 3] = 50.0
+            xu[:, 6] = np.arange(m, dtype=np.int64).view(np.float64)
+            return xu
+        prob.particles = particles
+        bd = core.uniform_boundary(prob.nchunk, world)
+        ids = [rank]
+        gd = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord,
+                         id_range=(rank, rank + 1), device=rank, strict_fp=True, capacity_factor=1.0)
+        gd.set_ranks(bd, rank)
+        gd.comm_init_torch()
+        _load(gd, prob, ids)
+        od = oracle_domain(no.load("port"), prob)
+        cap0 = gd.capacity(0)
+        if reserve:
+            # 6 % of 30000 arrive per step: the first arrival has no history to warn the host
+            gd.reserve(0, np_=4096)
+        status = "ok"
+        # without room reserved only ONE step is taken: a rank that refuses the next step would leave its
+        # peer alone in the exchange (the caller's job is to check the error bits every step)
+        for step in range(6 if reserve else 1):
+            od.step(0.5, 1.0)
+            gd.step(0.5)
+            err = gd.check()
+            if err:
+                status = f"errbits {err}"
+                continue
+            _compare(rank, prob, od, gd, ids, f"growth step {step}")
+        cap1 = gd.capacity(0)
+        flag = torch.tensor([0 if status == "ok" else 1, int(cap1[0] > cap0[0])], dtype=torch.int64)
+        gather = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+        dist.all_gather(gather, flag)
+        gd.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        if reserve:
+            assert status == "ok", status
+            assert int(gather[1][1]) == 1, "rank 1's particle store did not grow"
+        else:
+            # rank 1 (sized for 1024 particles) receives 1800 at once: error bits, later steps refused,
+            # no crash and no hang of the peer
+            assert int(gather[1][0]) == 1, "the overflow went unnoticed"
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: " + "".join(traceback.format_exception(exc))))
+
+
+@pytest.mark.parametrize("reserve", [True, False])
+def test_two_ranks_particle_store_growth(oracle_port, gpu_lib, reserve):
+    _run_ranks(2, _growth_worker, (reserve,))
