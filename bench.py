@@ -43,26 +43,51 @@ METRIC = "particle-updates/s (push+deposit+sort)"
 ALGO_BYTES = {"k_push": 124.0, "k_deposit": 48.0}
 
 
+CONFIGS = {
+    # BASELINE.json configs[1] -- the contract line
+    "cfg2": dict(cdims=(8, 8, 8), dims=(16, 16, 16), order=2, ppc=64, ns=2, vth=(0.1, 0.02), drift=None,
+                 label="128^3 cells per GPU, 128 ppc (electrons+ions, 64 each), order 2, fp64, periodic thermal plasma"),
+    # configs[2]: 256^3 on one GPU as 512 chunks of 32^3 in the reference's Gilbert order (ppc is not given by
+    # BASELINE.json; SURVEY.md 8d: 16 per species, 2 species)
+    "cfg3": dict(cdims=(8, 8, 8), dims=(32, 32, 32), order=2, ppc=16, ns=2, vth=(0.1, 0.02), drift=None,
+                 label="256^3 cells per GPU as 512 chunks of 32^3 (Gilbert order), 32 ppc (2 species x 16), order 2, fp64"),
+    # configs[3]: Weibel set-up, two counter-streaming electron species u_z = +-0.5 c, order 3, nb 3; 512^3 over
+    # 8 GPUs = 256^3 per GPU.  24 per species instead of 32: 32 needs 186 GB with the double-buffered store
+    "cfg4": dict(cdims=(8, 8, 8), dims=(32, 32, 32), order=3, ppc=24, ns=2, vth=(0.03, 0.03), drift=(0.5, -0.5),
+                 q=(-1.0, -1.0), m=(1.0, 1.0),
+                 label="Weibel: 256^3 cells per GPU as 512 chunks of 32^3, two counter-streaming electron species "
+                       "u_z = +-0.5 c, 48 ppc (2 x 24), order 3, nb 3, fp64"),
+}
+
+
 def workload(args):
+    w = dict(CONFIGS[args.config])
     small = os.environ.get("NIXB200_BENCH_SMALL", "") == "1" or args.small
-    cd = (2, 2, 2) if small else (8, 8, 8)
+    if small:
+        w["cdims"] = (2, 2, 2)
     if args.cdims:
-        cd = tuple(int(v) for v in args.cdims.split(","))
-    dims = tuple(int(v) for v in args.chunk.split(",")) if args.chunk else (16, 16, 16)
-    return dict(cdims=cd, dims=dims, order=args.order, ppc=args.ppc, ns=2)
+        w["cdims"] = tuple(int(v) for v in args.cdims.split(","))
+    if args.chunk:
+        w["dims"] = tuple(int(v) for v in args.chunk.split(","))
+    if args.order:
+        w["order"] = args.order
+    if args.ppc:
+        w["ppc"] = args.ppc
+    w["name"] = args.config
+    return w
 
 
 def make_problem(w, seed=2024, cdims=None, coord=None):
     from nix_b200.synth import Problem
     return Problem(cdims or w["cdims"], w["dims"], w["order"], ppc=w["ppc"], ns=w["ns"], seed=seed,
-                   vth=(0.1, 0.02), coord=coord)
+                   vth=w["vth"], coord=coord, q=w.get("q", (-1.0, 1.0)), m=w.get("m", (1.0, 25.0)))
 
 
 def global_box(cd, world):
-    """Weak scaling: the per-GPU block of cd chunks is repeated world times (z first, then y, then x),
-    and the chunk order visits block after block (snake order inside a block), so that the uniform
-    rank boundaries of Balancer::assign_initial give every rank one compact block."""
-    from nix_b200.synth import gilbert_like_order
+    """Weak scaling: the per-GPU block of cd chunks is repeated world times (z first, then y, then x).  Chunk
+    ids follow the reference's Gilbert curve over the WHOLE box (sfc.cpp:97-169 via nix_b200/sfc.py) and every
+    rank owns one contiguous segment of it (Balancer::assign_initial with uniform loads, balancer.cpp:101-124)."""
+    from nix_b200.sfc import chunk_coords
     rep = [1, 1, 1]
     a, n = 0, world
     while n > 1:
@@ -71,13 +96,31 @@ def global_box(cd, world):
         rep[a % 3] *= 2
         n //= 2
         a += 1
-    inner = gilbert_like_order(cd)
-    coord = []
-    for bz in range(rep[0]):
-        for by in range(rep[1]):
-            for bx in range(rep[2]):
-                coord.append(inner + np.array([bz * cd[0], by * cd[1], bx * cd[2]], dtype=np.int32))
-    return tuple(cd[i] * rep[i] for i in range(3)), np.concatenate(coord).astype(np.int32)
+    gcd = tuple(cd[i] * rep[i] for i in range(3))
+    return gcd, chunk_coords(gcd)
+
+
+def device_particles(torch, prob, w, ids, s, seed):
+    """Synthetic particles of species s for the chunks `ids`, generated on the device (the large configs would
+    spend minutes in numpy): uniform positions inside each chunk, Gaussian momenta, optional drift along z."""
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(seed * 1000 + s)
+    n = prob.ncell() * prob.ppc
+    dims = torch.tensor(prob.dims, dtype=torch.float64, device="cuda")
+    out = torch.empty((len(ids) * n, 7), dtype=torch.float64, device="cuda")
+    for j, k in enumerate(ids):
+        o = out[j * n:(j + 1) * n]
+        lo = torch.tensor([float(prob.coord[k][a] * prob.dims[a]) for a in range(3)], dtype=torch.float64, device="cuda")
+        u = torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=gen) * (1.0 - 1e-12)
+        o[:, 0] = lo[2] + u[:, 0] * dims[2]
+        o[:, 1] = lo[1] + u[:, 1] * dims[1]
+        o[:, 2] = lo[0] + u[:, 2] * dims[0]
+        o[:, 3:6] = torch.randn((n, 3), dtype=torch.float64, device="cuda", generator=gen) * w["vth"][s]
+        if w.get("drift"):
+            o[:, 5] += w["drift"][s]
+        idv = torch.arange(n, dtype=torch.int64, device="cuda") + (int(k) << 32) + (s << 56)
+        o[:, 6] = idv.view(torch.float64)
+    return out
 
 
 class ClockSampler:
@@ -180,7 +223,7 @@ def cpu_reference_run(w, steps, warmup, budget_s=None):
     return {
         "value": npart * done / dt, "unit": "particle-updates/s", "cores": nthreads, "kind": kind,
         "backend": name, "simd_lanes": lib.nixo_simd_lanes() if simd else 1, "scalar_path_value": scalar,
-        "sample": f"{cd[0]}x{cd[1]}x{cd[2]} chunks of 16^3 cells, {w['ppc']} ppc x {w['ns']} species "
+        "sample": f"{cd[0]}x{cd[1]}x{cd[2]} chunks of {'x'.join(map(str, w['dims']))} cells, {w['ppc']} ppc x {w['ns']} species "
                   f"({npart} particles), order {w['order']}, {done} steps after {warmup} warm-up",
         "ms_per_step": 1e3 * dt / done, "steps": done,
     }
@@ -196,8 +239,8 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": r["value"], "unit": "particle-updates/s",
         "n_gpus": args.gpus, "steps": r["steps"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "128^3 cells, 128 ppc (2 species x 64), order 2, fp64, 8^3 chunks of 16^3 "
-                               "(bounded CPU sample: " + r["sample"] + ")"},
+        "config": {"workload": "%s: %s (bounded CPU sample of the same chunk shape, ppc and order: %s)"
+                               % (w["name"], w["label"], r["sample"])},
         "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes",
                                            "scalar_path_value")},
         "e2e": {"value": r["value"], "unit": "particle-updates/s", "h2d_bytes_per_step": 0,
@@ -205,6 +248,18 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     emit(out)
+
+
+def fp64_peak():
+    """Measured fp64 FMA peak of this GPU (tools/micro/dfma_peak, a register-resident DFMA kernel)."""
+    exe = os.path.join(ROOT, "tools", "micro", "dfma_peak")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception:
+        return None
 
 
 def run_gpu(args):
@@ -223,20 +278,21 @@ def run_gpu(args):
     from nix_b200 import core
 
     w = workload(args)
+    peak64 = fp64_peak() if rank == 0 else None  # before the timed regions, GPU otherwise idle
     gcd, gcoord = global_box(w["cdims"], world)
     prob = make_problem(w, seed=2024, cdims=gcd, coord=gcoord)
     bd = core.uniform_boundary(prob.nchunk, world)
     ids = list(range(int(bd[rank]), int(bd[rank + 1])))
     stream = torch.cuda.current_stream()
     dom = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, device=local,
-                      id_range=(ids[0], ids[-1] + 1), strict_fp=bool(args.strict), capacity_factor=1.15,
+                      id_range=(ids[0], ids[-1] + 1), strict_fp=bool(args.strict), capacity_factor=1.12,
                       stream=stream.cuda_stream)
     if world > 1:
         dom.set_ranks(bd, rank)
         dom.comm_init_torch()
     nchunk = dom.nchunk
     cells = int(np.prod(dom.M))
-    # pinned host mirrors of the grid arrays (the host-side field solver's view)
+    # pinned host mirrors of the grid arrays (initial condition in, diagnostic snapshots out)
     uf_host = torch.empty((nchunk, cells, 6), dtype=torch.float64, pin_memory=True)
     icells = prob.ncell()
     ufi_host = torch.empty((nchunk, icells, 6), dtype=torch.float64, pin_memory=True)  # interior cells only
@@ -253,11 +309,18 @@ def run_gpu(args):
         :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
     npc = prob.ncell() * prob.ppc
     for s in range(prob.ns):
-        flat = np.empty((nchunk * npc, 7), dtype=np.float64)
-        for k in range(nchunk):
-            flat[k * npc:(k + 1) * npc] = prob.particles(ids[k], s)
-        dom.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
-        del flat
+        if w["name"] == "cfg2":  # the contract line keeps the numpy inputs the parity tests use
+            flat = np.empty((nchunk * npc, 7), dtype=np.float64)
+            for k in range(nchunk):
+                flat[k * npc:(k + 1) * npc] = prob.particles(ids[k], s)
+            dom.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
+            del flat
+        else:
+            t = device_particles(torch, prob, w, ids, s, seed=2024)
+            torch.cuda.synchronize()
+            dom.set_particles_ptr(s, t.data_ptr(), np.full(nchunk, npc, dtype=np.int64))
+            del t
+            torch.cuda.empty_cache()
     dom.sort()
     dom.synchronize()
     ntot = dom.total_particles()
@@ -268,12 +331,25 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     dt = 0.5
+    # coupling constant of the device-side field update: E -= cfj dt J.  With unit charges and ppc particles per
+    # cell the electron plasma frequency is sqrt(cfj ppc); cfj = 0.16 / ppc puts it at 0.4 (wpe dt = 0.2)
+    cfj = 0.16 / w["ppc"]
     for _ in range(max(args.warmup, 3)):
         dom.step(dt)
     barrier()
     err = dom.check()
     if err:
         raise SystemExit(f"bench.py: device error bits {err} during warm-up")
+
+    def timed_steps(nsteps, fn):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(nsteps):
+            fn()
+        e1.record(stream)
+        barrier()
+        return e0.elapsed_time(e1)
 
     # ---- timed region: K device-resident steps ----
     try:
@@ -285,27 +361,53 @@ def run_gpu(args):
     dom.set_profiling(True)
     dom.phase_ms()
     l0 = core.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        dom.step(dt)
-    e1.record(stream)
-    barrier()
-    ms = e0.elapsed_time(e1)
+    ms = timed_steps(args.steps, lambda: dom.step(dt))
     launches = core.launch_count() - l0
     phases = dom.phase_ms()
     dom.set_profiling(False)
     clocks = sampler.stop()
 
-    # ---- end to end: host E/B in, J + particle counts out, every step (host-side field solver) ----
+    # ---- the same K steps in the OTHER arithmetic mode (strict = no FMA contraction = bit-exact with the
+    #      reference's scalar templates; the headline is the contracted mode unless --strict) ----
+    dom.set_strict_fp(not args.strict)
+    dom.step(dt)
+    ms_other = timed_steps(args.steps, lambda: dom.step(dt))
+    dom.set_strict_fp(bool(args.strict))
+
+    # ---- end to end through the C ABI with HOST buffers: one diagnostic interval of a nix application whose
+    #      fields live on the device (field solver = nixb200_domain_step_em): the initial E/B of every chunk comes
+    #      up from pinned host memory, every step reads back the history diagnostics (field energies and particle
+    #      counts per chunk -- what HistoryDiag and the balancer consume), and at the end of the interval the
+    #      interior J and E/B of every chunk go down as a snapshot.  Bytes are counted from what is copied. ----
+    energies = np.zeros((args.steps, nchunk, 2))
     barrier()
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
-    # The host-side field solver of a nix application works on the interior cells: every step the interior
-    # J of every chunk goes down after the J halo and the interior E/B of every chunk comes up for the next
-    # step (its ghost cells are filled by the E/B halo on the device).  The copies run on the domain's
-    # second stream while the device migrates and sorts particles.
+    dom.interior_upload_overlapped(core.FIELD_UF, ufi_host.data_ptr())
+    dom.exchange_field()
+    for k in range(args.steps):
+        dom.step_em(dt, cfj)
+        energies[k] = dom.field_energy()
+        dom.get_np(0)  # Chunk::get_total_load-style read back (synchronises the step)
+    dom.interior_download_overlapped(core.FIELD_UJ, uji_host.data_ptr())
+    dom.interior_download_overlapped(core.FIELD_UF, ufi_host.data_ptr())
+    dom.copy_synchronize()
+    e3.record(stream)
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    h2d_step = ufi_host.numel() * 8 / args.steps
+    d2h_step = (ufi_host.numel() + uji_host.numel()) * 8 / args.steps + nchunk * (16 + 8)
+    err = dom.check()
+    if err:
+        raise SystemExit(f"bench.py: device error bits {err} during the timed region")
+
+    # ---- the round-1 flavour for comparison: HOST-side field solver, interior E/B up and interior J down
+    #      every step on a second stream (what the device-side solver removes) ----
+    ufi_host.numpy()[...] = ufn.reshape((nchunk,) + tuple(prob.M) + (6,))[
+        :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
+    barrier()
+    e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e4.record(stream)
     dom.interior_upload_overlapped(core.FIELD_UF, ufi_host.data_ptr())
     for k in range(args.steps):
         dom.exchange_field()  # ghosts of the E/B that has just arrived
@@ -317,27 +419,26 @@ def run_gpu(args):
         dom.copy_synchronize()  # J is on the host: the field solver would run here
         if k + 1 < args.steps:
             dom.interior_upload_overlapped(core.FIELD_UF, ufi_host.data_ptr())  # its result, for the next step
-        dom.get_np(0)  # Chunk::get_total_load-style read back (synchronises the step)
-    e3.record(stream)
+        dom.get_np(0)
+    e5.record(stream)
     barrier()
-    ms_e2e = e2.elapsed_time(e3)
+    ms_e2e_host = e4.elapsed_time(e5)
     err = dom.check()
     if err:
         raise SystemExit(f"bench.py: device error bits {err} during the timed region")
     ntot_end = dom.total_particles()
     traffic = dom.peer_traffic()
 
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms, ms_e2e, ms_other, ms_e2e_host], dtype=torch.float64, device="cuda")
     n = torch.tensor([float(ntot), float(ntot_end), float(traffic["particles_sent"]),
                       float(traffic["halo_cells_sent"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e, ms_other, ms_e2e_host = (float(v) for v in t)
     nglobal = float(n[0])
 
     if rank == 0:
-        push_ms, push_calls = phases["push_deposit"]
         peaks = {}
         try:
             with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -347,14 +448,17 @@ def run_gpu(args):
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         # per kernel: CUDA events recorded by the library around every launch on the domain's stream
-        traffic_by_kernel = {}
+        prof = {}
         tpath = os.path.join(ROOT, "profiles", "push_deposit_traffic.json")
         if os.path.exists(tpath):
             try:
                 with open(tpath) as f:
-                    traffic_by_kernel = json.load(f).get("dram_bytes_per_particle", {})
+                    prof = json.load(f)
             except (OSError, ValueError):
-                traffic_by_kernel = {}
+                prof = {}
+        traffic_by_kernel = prof.get("dram_bytes_per_particle", {}) if w["name"] == "cfg2" else {}
+        fp64_by_kernel = prof.get("fp64_warp_inst_per_particle", {}) if w["name"] == "cfg2" else {}
+        peak_fma = peak64["fp64_gfma_per_s"] * 1e9 if peak64 and "fp64_gfma_per_s" in peak64 else None
         kern = []
         for name in ("k_push", "k_deposit"):
             k_ms, k_calls = phases[name]
@@ -362,51 +466,67 @@ def run_gpu(args):
             part = ntot / prob.ns
             ach = ALGO_BYTES[name] * part / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
             tr = traffic_by_kernel.get(name)
+            wi = fp64_by_kernel.get(name)
             kern.append({"kernel": name + "<%d>" % w["order"], "launch_ms": launch_ms, "launches": k_calls,
                          "algorithmic_bytes_per_particle": ALGO_BYTES[name], "particles_per_launch": part,
                          "achieved": ach, "frac": ach / peak if peak else None,
-                         "traffic": tr * part if tr else None})
+                         "traffic": tr * part if tr else None,
+                         # fp64 pipe: warp instructions (ncu) x 32 lanes / launch time / measured DFMA peak
+                         "fp64_frac": (wi * 32 * part / (launch_ms * 1e-3) / peak_fma) if (wi and peak_fma and launch_ms > 0) else None})
         dom_k = max(kern, key=lambda k: k["launch_ms"])
-        cells = int(np.prod(w["cdims"])) * int(np.prod(w["dims"]))
-        side = round(cells ** (1.0 / 3.0))
-        workload_name = ("%s cells per GPU, %d ppc (electrons+ions, %d each), order %d, fp64, periodic thermal "
-                         "plasma, %dx%dx%d chunks of %s per GPU"
-                         % ("%d^3" % side if side ** 3 == cells else str(cells), 2 * w["ppc"], w["ppc"], w["order"],
-                            w["cdims"][0], w["cdims"][1], w["cdims"][2],
-                            "%d^3" % w["dims"][0] if len(set(w["dims"])) == 1 else "x".join(map(str, w["dims"]))))
+        # whole step against SURVEY 8(d)'s 232 B per particle-update (push+deposit+count 116 B, sort 116 B)
+        step_gbs = 232.0 * ntot / (ms / args.steps * 1e-3) / 1e9
+        value = nglobal * args.steps / (ms * 1e-3)
+        other = nglobal * args.steps / (ms_other * 1e-3)
         out = {
-            "metric": METRIC, "value": nglobal * args.steps / (ms * 1e-3), "unit": "particle-updates/s",
+            "metric": METRIC, "value": value, "unit": "particle-updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
-                "workload": workload_name,
+                "workload": "%s: %s; %dx%dx%d chunks of %s per GPU in the reference's Gilbert order"
+                            % (w["name"], w["label"], w["cdims"][0], w["cdims"][1], w["cdims"][2],
+                               "x".join(map(str, w["dims"]))),
                 "particles_per_gpu": ntot, "particles_end_all_ranks": int(n[1]),
                 "fp_contract": "off" if args.strict else "fma",
                 "l2": "inputs (%.1f GB of particles per GPU) larger than L2" % (ntot * 56 / 1e9),
-                "multi_gpu": ("one periodic box of %dx%dx%d chunks partitioned over %d ranks along the chunk order "
-                              "(one compact block per rank); J / E/B halo and particle migration between ranks "
-                              "over NCCL send/recv, one message per peer and mode; last step: %d particles and "
-                              "%d ghost cells per exchange crossed rank boundaries"
+                "multi_gpu": ("one periodic box of %dx%dx%d chunks, ids along the reference's Gilbert curve, one "
+                              "contiguous curve segment per rank (%d ranks); J / E/B halo and particle migration "
+                              "between ranks over NCCL send/recv, one message per peer and mode; last step: %d "
+                              "particles and %d ghost cells per exchange crossed rank boundaries"
                               % (prob.cdims + (world, int(n[2]), int(n[3])))) if world > 1 else "single GPU",
             },
             "clocks": clocks,
+            # the bit-exact (no FMA contraction) mode next to the contracted one, same steps, same data
+            "strict_value": value if args.strict else other,
+            "strict_ms_per_step": (ms if args.strict else ms_other) / args.steps,
+            "fma_value": other if args.strict else value,
             "e2e": {"value": nglobal * args.steps / (ms_e2e * 1e-3), "unit": "particle-updates/s",
-                    "h2d_bytes_per_step": int(ufi_host.numel() * 8),
-                    "d2h_bytes_per_step": int(uji_host.numel() * 8 + nchunk * 4 + 4),
-                    "what": "per step: interior E/B of every chunk from pinned host memory, E/B halo, one full "
-                            "step, interior J of every chunk + per-chunk particle counts back to the host (what "
-                            "a host-side field solver exchanges); the copies run on a second stream while the "
-                            "device migrates and sorts"},
+                    "h2d_bytes_per_step": int(h2d_step), "d2h_bytes_per_step": int(d2h_step),
+                    "ms_per_step": ms_e2e / args.steps,
+                    "what": "one diagnostic interval of %d steps through the C ABI with host buffers: interior E/B of "
+                            "every chunk up from pinned host memory at the start, then per step "
+                            "nixb200_domain_step_em (the PIC step + Yee field update on the device) and the read-back "
+                            "of per-chunk field energies and particle counts, and the interior J + E/B snapshot of "
+                            "every chunk down to pinned host memory at the end; bytes are totals / steps" % args.steps},
+            "e2e_host_fields": {"value": nglobal * args.steps / (ms_e2e_host * 1e-3), "unit": "particle-updates/s",
+                                "h2d_bytes_per_step": int(ufi_host.numel() * 8),
+                                "d2h_bytes_per_step": int(uji_host.numel() * 8 + nchunk * 8),
+                                "what": "round-1 flavour: HOST-side field solver, interior E/B up and interior J down "
+                                        "every step on a second stream"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": dom_k["kernel"], "achieved": dom_k["achieved"], "peak": peak,
                          "unit": "GB/s", "frac": dom_k["frac"], "traffic": dom_k["traffic"],
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_particle": dom_k["algorithmic_bytes_per_particle"],
                          "launch_ms": dom_k["launch_ms"], "kernels": kern,
-                         "note": "dominant kernel by time; at order 2 / fp64 k_deposit is bound by the fp64 pipe "
-                                 "and issue latency and k_push by the shared-memory data pipe (the 2-wavefront "
-                                 "64-bit gathers), not by HBM (DESIGN.md 3.2, SURVEY.md 8d)"},
-            "phases_ms_per_step": {k: (v[0] / v[1] if v[1] else 0.0) for k, v in phases.items()},
+                         "step": {"algorithmic_bytes_per_update": 232.0, "achieved": step_gbs, "frac": step_gbs / peak},
+                         "fp64_peak": peak64,
+                         "note": "dominant kernel by time; at order >= 2 / fp64 k_deposit is bound by the fp64 pipe "
+                                 "and issue latency and k_push by the shared-memory data pipe, not by HBM "
+                                 "(DESIGN.md 3.2, SURVEY.md 8d): fp64_frac = fp64 warp instructions x 32 / time / "
+                                 "measured DFMA peak"},
+            "phases_ms_per_step": {k: (v[0] / args.steps) for k, v in phases.items()},
+            "field_energy_last": [float(energies[-1, :, 0].sum()), float(energies[-1, :, 1].sum())],
         }
         if world == 1 and not args.no_cpu:
             r = cpu_reference_run(w, steps=3, warmup=1, budget_s=25.0)
@@ -428,9 +548,10 @@ def main():
     ap.add_argument("--cdims", default="", help="override chunks per axis, e.g. 4,4,4")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     # exploration only (the contract line is the default: order 2, 16^3-cell chunks, 64 ppc per species)
-    ap.add_argument("--order", type=int, default=2, help="shape order 1/2/3 (default 2 = BASELINE configs[1])")
-    ap.add_argument("--chunk", default="", help="cells per chunk, e.g. 32,32,32")
-    ap.add_argument("--ppc", type=int, default=64, help="particles per cell and species")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json config (default cfg2 = configs[1])")
+    ap.add_argument("--order", type=int, default=0, help="override the shape order 1/2/3")
+    ap.add_argument("--chunk", default="", help="override cells per chunk, e.g. 32,32,32")
+    ap.add_argument("--ppc", type=int, default=0, help="override particles per cell and species")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -108,7 +108,8 @@ int nixb200_domain_field_download_overlapped(nixb200_domain* d, int which, doubl
 int nixb200_domain_interior_upload_overlapped(nixb200_domain* d, int which, const double* host);
 int nixb200_domain_interior_download_overlapped(nixb200_domain* d, int which, double* host);
 int nixb200_domain_copy_synchronize(nixb200_domain* d);
-/* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each */
+/* all chunks of one species at once: xu_aos = concatenation over local chunks, np_chunk[k] each (host or
+ * device memory) */
 int nixb200_domain_set_particles(nixb200_domain* d, int is, const double* xu_aos,
                                  const int64_t* np_chunk);
 int nixb200_domain_get_np(nixb200_domain* d, int is, int64_t* np_chunk /* [nchunk] */);
@@ -143,6 +144,22 @@ int nixb200_domain_exchange_field(nixb200_domain* d);
 int nixb200_domain_migrate_sort(nixb200_domain* d);
 /* clear J, push+deposit, J halo, E/B halo, migrate+sort: one Application::push() worth of work */
 int nixb200_domain_step(nixb200_domain* d, double delt);
+
+/* ---- field solver on the device.  The reference has none -- Application::push() is an
+ *      empty virtual (application.hpp:343-346), the Maxwell update belongs to the downstream application --
+ *      but it fixes the Yee staggering of uf (xtensor_packer3d.hpp:279-302) and of J (esirkepov.hpp:177-237).
+ *      With these calls E, B and J never leave the device between steps.
+ *        push_bfd   B -= c dt curl E on the interior plus `ext` (< nb) ghost layers
+ *        push_efd   E += c dt curl B - cfj dt J on the interior (cfj: 1 in Heaviside-Lorentz units, 4 pi in Gaussian)
+ *        step_em    clear J, push+deposit, J halo, B half step (ext = 1: no exchange of B needed), E step,
+ *                   E/B halo, B half step, E/B halo, migrate+sort  -- a time-centred leapfrog
+ *        field_energy   [nchunk][2] = sum E^2, sum B^2 over the interior cells of every chunk (history diagnostic) ---- */
+int nixb200_domain_push_bfd(nixb200_domain* d, double delt, int ext);
+int nixb200_domain_push_efd(nixb200_domain* d, double delt, double cfj);
+int nixb200_domain_step_em(nixb200_domain* d, double delt, double cfj);
+int nixb200_domain_field_energy(nixb200_domain* d, double* host_e2b2);
+/* 1: push arithmetic without FMA contraction (bit-identical to the reference's scalar templates), 0: contracted */
+int nixb200_domain_set_strict_fp(nixb200_domain* d, int on);
 
 /* ---- per-chunk halo buffers in the reference's MpiBuffer layout (chunk.cpp:257-286), for
  *      neighbours that live on another rank and for drop-in use behind Chunk::set_boundary_* ---- */
@@ -185,10 +202,11 @@ int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int
 
 /* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
  * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only),
- * 5 the k_push launches of phase 0 alone, 6 its k_deposit launches alone (one call = one launch = one species).
+ * 5 the k_push launches of phase 0 alone, 6 its k_deposit launches alone (one call = one launch = one species),
+ * 7 field solver (push_bfd + push_efd).
  * With profiling on, every phase call is bracketed by CUDA events on the domain's stream;
  * get_phase_ms synchronises, then returns and resets the accumulated milliseconds and call count. */
-#define NIXB200_NPHASE 7
+#define NIXB200_NPHASE 8
 int nixb200_domain_set_profiling(nixb200_domain* d, int on);
 int nixb200_domain_get_phase_ms(nixb200_domain* d, int phase, double* ms_sum, int* calls);
 

@@ -33,10 +33,12 @@ SYMBOLS = [
     "nixb200_plan_create", "nixb200_plan_destroy", "nixb200_plan_npeer", "nixb200_plan_peer",
     "nixb200_plan_entries", "nixb200_domain_set_ranks", "nixb200_comm_unique_id", "nixb200_domain_comm_init",
     "nixb200_domain_set_comm", "nixb200_domain_peer_traffic", "nixb200_domain_reserve",
-    "nixb200_domain_get_capacity",
+    "nixb200_domain_get_capacity", "nixb200_domain_push_bfd", "nixb200_domain_push_efd", "nixb200_domain_step_em",
+    "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp",
 ]
 
-PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit")
+PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
+          "field_solve")
 
 
 PUSH_BORIS, PUSH_VAY, PUSH_HIGUERA_CARY = 0, 1, 2  # primitives.hpp:165-253
@@ -128,6 +130,11 @@ def load_library():
     sig("nixb200_domain_comm_init", I, P, P)
     sig("nixb200_domain_set_comm", I, P, P)
     sig("nixb200_domain_peer_traffic", I, P, PL, PL, PL)
+    sig("nixb200_domain_push_bfd", I, P, D, I)
+    sig("nixb200_domain_push_efd", I, P, D, D)
+    sig("nixb200_domain_step_em", I, P, D, D)
+    sig("nixb200_domain_field_energy", I, P, PD)
+    sig("nixb200_domain_set_strict_fp", I, P, I)
     sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
     sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib
@@ -322,6 +329,12 @@ class Domain:
         self._ck(self.lib.nixb200_domain_get_capacity(self.h, s, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def set_particles_ptr(self, s, ptr, npc):
+        """ptr: address of an [n][7] float64 AoS array in host OR device memory."""
+        npc = np.ascontiguousarray(npc, dtype=np.int64)
+        self._ck(self.lib.nixb200_domain_set_particles(
+            self.h, s, C.cast(C.c_void_p(int(ptr)), C.POINTER(C.c_double)), npc.ctypes.data_as(C.POINTER(C.c_int64))))
+
     def get_np(self, s):
         a = np.zeros(self.nchunk, dtype=np.int64)
         self._ck(self.lib.nixb200_domain_get_np(self.h, s, a.ctypes.data_as(C.POINTER(C.c_int64))))
@@ -367,6 +380,24 @@ class Domain:
 
     def step(self, delt):
         self._ck(self.lib.nixb200_domain_step(self.h, float(delt)))
+
+    # ---- Yee field update on the device (row N1; the reference ships none) ----
+    def push_bfd(self, delt, ext=0):
+        self._ck(self.lib.nixb200_domain_push_bfd(self.h, float(delt), int(ext)))
+
+    def push_efd(self, delt, cfj=1.0):
+        self._ck(self.lib.nixb200_domain_push_efd(self.h, float(delt), float(cfj)))
+
+    def step_em(self, delt, cfj=1.0):
+        self._ck(self.lib.nixb200_domain_step_em(self.h, float(delt), float(cfj)))
+
+    def field_energy(self):
+        out = np.zeros((self.nchunk, 2), dtype=np.float64)
+        self._ck(self.lib.nixb200_domain_field_energy(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def set_strict_fp(self, on):
+        self._ck(self.lib.nixb200_domain_set_strict_fp(self.h, int(bool(on))))
 
     # ---- per-chunk halo buffers in the reference's MpiBuffer layout ----
     def halo_layout(self, mode):

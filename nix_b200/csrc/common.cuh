@@ -235,6 +235,11 @@ int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* 
 int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
                        const int* nbvalid_dev, cudaStream_t st);
 
+// Yee FDTD on the device-resident grid (fdtd.cu)
+int launch_push_bfd(const Geo& g, double* uf, double delt, int ext, cudaStream_t st);
+int launch_push_efd(const Geo& g, double* uf, const double* uj, double delt, double cfj, cudaStream_t st);
+int launch_field_energy(const Geo& g, const double* uf, double* out, cudaStream_t st);
+
 // interior cells of all chunks <-> dense [chunk][Nz][Ny][Nx][ncomp] (pack: full -> dense)
 int launch_interior(bool pack, double* full, double* dense, const Geo& g, int ncomp, cudaStream_t st);
 int launch_aos_to_soa(const double* aos, double* soa_base, size_t cap, size_t first, size_t n,

@@ -136,7 +136,7 @@ static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
   NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * cap));
   NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
   NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
-  return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, cap / 4)));
+  return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, cap / 16))); // regrown on demand (ensure_capacity)
 }
 
 static int check_chunk(Domain* d, int k)
@@ -515,6 +515,7 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->scan_tmp) cudaFree(d->scan_tmp);
   if (d->err_dev) cudaFree(d->err_dev);
   if (d->stat_dev) cudaFree(d->stat_dev);
+  if (d->energy_dev) cudaFree(d->energy_dev);
   if (d->stat_host) cudaFreeHost(d->stat_host);
   if (d->ev_stat) cudaEventDestroy(d->ev_stat);
   if (d->nbvalid_dev) cudaFree(d->nbvalid_dev);
@@ -743,8 +744,8 @@ int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_ao
       set_error("null particle array");
       return 1;
     }
-    // AoS staged in the xv buffer (same byte size), transposed into xu
-    NIX_CUDA(cudaMemcpyAsync(s.xv, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyHostToDevice, d->stream));
+    // AoS staged in the xv buffer (same byte size), transposed into xu; the source may be host or device memory
+    NIX_CUDA(cudaMemcpyAsync(s.xv, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyDefault, d->stream));
     if (launch_aos_to_soa(s.xv, s.xu, s.cap, 0, (size_t)ntot, d->stream)) return 1;
   }
   // start[] of an unsorted container: only the chunk bases are meaningful until domain_sort()
@@ -925,6 +926,61 @@ int nixb200_domain_step(nixb200_domain* dd, double delt)
   if (nixb200_domain_exchange_current(dd)) return 1;
   if (nixb200_domain_exchange_field(dd)) return 1;
   if (nixb200_domain_migrate_sort(dd)) return 1;
+  return 0;
+}
+
+int nixb200_domain_push_bfd(nixb200_domain* dd, double delt, int ext)
+{
+  NIX_ENTER(dd);
+  if (wait_copy(d, 0)) return 1;
+  {
+    PhaseTimer pt(d, 7);
+    if (launch_push_bfd(d->geo, d->uf, delt, ext, d->stream)) return 1;
+  }
+  return mark_main_done(d, 0);
+}
+
+int nixb200_domain_push_efd(nixb200_domain* dd, double delt, double cfj)
+{
+  NIX_ENTER(dd);
+  if (wait_copy(d, 0) || wait_copy(d, 1)) return 1;
+  {
+    PhaseTimer pt(d, 7);
+    if (launch_push_efd(d->geo, d->uf, d->uj, delt, cfj, d->stream)) return 1;
+  }
+  return mark_main_done(d, 0) || mark_main_done(d, 1);
+}
+
+int nixb200_domain_step_em(nixb200_domain* dd, double delt, double cfj)
+{
+  if (nixb200_domain_clear_current(dd)) return 1;
+  if (nixb200_domain_push_deposit(dd, delt)) return 1;
+  if (nixb200_domain_exchange_current(dd)) return 1;
+  if (nixb200_domain_push_bfd(dd, 0.5 * delt, 1)) return 1;
+  if (nixb200_domain_push_efd(dd, delt, cfj)) return 1;
+  if (nixb200_domain_exchange_field(dd)) return 1;
+  if (nixb200_domain_push_bfd(dd, 0.5 * delt, 0)) return 1;
+  if (nixb200_domain_exchange_field(dd)) return 1;
+  if (nixb200_domain_migrate_sort(dd)) return 1;
+  return 0;
+}
+
+int nixb200_domain_field_energy(nixb200_domain* dd, double* host_e2b2)
+{
+  NIX_ENTER(dd);
+  if (!host_e2b2) return 1;
+  if (wait_copy(d, 0)) return 1;
+  if (!d->energy_dev) NIX_CUDA(cudaMalloc(&d->energy_dev, sizeof(double) * 2 * d->geo.nchunk));
+  if (launch_field_energy(d->geo, d->uf, d->energy_dev, d->stream)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(host_e2b2, d->energy_dev, sizeof(double) * 2 * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_domain_set_strict_fp(nixb200_domain* dd, int on)
+{
+  NIX_ENTER(dd);
+  d->desc.strict_fp = on ? 1 : 0;
   return 0;
 }
 

@@ -25,6 +25,7 @@ struct Domain {
   // records, message particles) to pinned host memory; the next step grows the stores before they fill up
   int32_t*                stat_host    = nullptr; // pinned [ns][4]
   int32_t*                stat_dev     = nullptr; // device [ns][4]
+  double*                 energy_dev   = nullptr; // device [nchunk][2]
   cudaEvent_t             ev_stat      = nullptr;
   bool                    stat_pending = false;
   CUtensorMap             tmap;

@@ -29,6 +29,8 @@ struct nixo_domain {
   int          nchunk;
   int          ns;
   int          order;
+  int          dims[3], nb;
+  double       del[3];
   int*         coord;    /* [nchunk][3] */
   int*         grid2id;  /* [Cz][Cy][Cx] -> chunk index */
   int*         nbr;      /* [nchunk][27] */
@@ -51,6 +53,9 @@ nixo_domain* nixo_domain_create(const int* cdims, const int* dims, int nb, int o
   d->ns          = ns;
   d->order       = order;
   memcpy(d->cdims, cdims, 3 * sizeof(int));
+  memcpy(d->dims, dims, 3 * sizeof(int));
+  memcpy(d->del, del, 3 * sizeof(double));
+  d->nb = nb;
   d->coord    = (int*)malloc(sizeof(int) * 3 * d->nchunk);
   d->grid2id  = (int*)malloc(sizeof(int) * d->nchunk);
   d->nbr      = (int*)malloc(sizeof(int) * 27 * d->nchunk);
@@ -209,6 +214,38 @@ void nixo_domain_step(nixo_domain* d, double delt, double cc, int simd)
   nixo_domain_push_deposit(d, delt, cc, simd);
   nixo_domain_exchange(d, NIXO_MODE_CURRENT);
   /* [field solver would run here -- downstream of nix, not on this path] */
+  nixo_domain_exchange(d, NIXO_MODE_FIELD);
+  nixo_domain_exchange(d, NIXO_MODE_PARTICLE);
+}
+
+/* ---- the same step with the Yee field update on the grid (oracle/field_solver.c; NOT in the reference
+ *      tree -- parity unpinned by the reference).  Time-centred leapfrog:
+ *        push with E^n, B^n -> J^{n+1/2};  B^n -> B^{n+1/2} (on the cells one ghost layer out as well,
+ *        from the ghost E of the last exchange, so that E needs no exchange of B);  E^n -> E^{n+1};
+ *        E/B halo;  B^{n+1/2} -> B^{n+1};  E/B halo;  particle migration + sort ---- */
+void nixo_domain_push_bfd(nixo_domain* d, double delt, double cc, int ext)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < d->nchunk; k++)
+    nixo_fdtd_push_bfd(nixo_chunk_uf(d->chunk[k]), d->dims, d->nb, d->del, cc, delt, ext);
+}
+
+void nixo_domain_push_efd(nixo_domain* d, double delt, double cc, double cfj)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < d->nchunk; k++)
+    nixo_fdtd_push_efd(nixo_chunk_uf(d->chunk[k]), nixo_chunk_uj(d->chunk[k]), d->dims, d->nb, d->del, cc, delt, cfj);
+}
+
+void nixo_domain_step_em(nixo_domain* d, double delt, double cc, double cfj, int simd)
+{
+  nixo_domain_clear_current(d);
+  nixo_domain_push_deposit(d, delt, cc, simd);
+  nixo_domain_exchange(d, NIXO_MODE_CURRENT);
+  nixo_domain_push_bfd(d, 0.5 * delt, cc, 1);
+  nixo_domain_push_efd(d, delt, cc, cfj);
+  nixo_domain_exchange(d, NIXO_MODE_FIELD);
+  nixo_domain_push_bfd(d, 0.5 * delt, cc, 0);
   nixo_domain_exchange(d, NIXO_MODE_FIELD);
   nixo_domain_exchange(d, NIXO_MODE_PARTICLE);
 }

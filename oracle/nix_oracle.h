@@ -117,6 +117,18 @@ void         nixo_domain_sort_only(nixo_domain* d);          /* count(reset) + s
 /* one full step: clear J, push+deposit, J halo, E/B halo, particle migration (count+pack+unpack+sort) */
 void    nixo_domain_step(nixo_domain* d, double delt, double cc, int simd);
 int64_t nixo_domain_total_particles(nixo_domain* d);
+
+/* ---- Yee FDTD field update (oracle/field_solver.c).  NOT part of the reference tree: parity unpinned by
+ *      the reference, pinned by known answers (tests/test_field_solver.py).  uf [Mz][My][Mx][6],
+ *      uj [Mz][My][Mx][4]; ext = extra cell layers around the interior that are updated too ---- */
+void nixo_fdtd_push_bfd(double* uf, const int* dims, int nb, const double* del, double cc, double delt, int ext);
+void nixo_fdtd_push_efd(double* uf, const double* uj, const int* dims, int nb, const double* del, double cc,
+                        double delt, double cfj);
+void nixo_fdtd_energy(const double* uf, const int* dims, int nb, double* e2b2);
+void nixo_domain_push_bfd(nixo_domain* d, double delt, double cc, int ext);
+void nixo_domain_push_efd(nixo_domain* d, double delt, double cc, double cfj);
+/* clear J, push+deposit, J halo, B half step, E step, E/B halo, B half step, E/B halo, migration */
+void nixo_domain_step_em(nixo_domain* d, double delt, double cc, double cfj, int simd);
 void    nixo_set_num_threads(int n);
 int     nixo_get_num_threads(void);
 

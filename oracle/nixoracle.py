@@ -140,6 +140,12 @@ def load(name="port"):
     sig("nixo_domain_sort_only", None, P)
     sig("nixo_domain_step", None, P, D, D, I)
     sig("nixo_domain_total_particles", C.c_int64, P)
+    sig("nixo_fdtd_push_bfd", None, PD, PI, I, PD, D, D, I)
+    sig("nixo_fdtd_push_efd", None, PD, PD, PI, I, PD, D, D, D)
+    sig("nixo_fdtd_energy", None, PD, PI, I, PD)
+    sig("nixo_domain_push_bfd", None, P, D, D, I)
+    sig("nixo_domain_push_efd", None, P, D, D, D)
+    sig("nixo_domain_step_em", None, P, D, D, D, I)
     sig("nixo_set_num_threads", None, I)
     sig("nixo_get_num_threads", I)
     _cache[name] = lib
@@ -325,6 +331,27 @@ class Domain:
 
     def step(self, delt, cc, simd=False):
         self.lib.nixo_domain_step(self.h, delt, cc, int(simd))
+
+    # Yee field update between the J halo and the E/B halo (oracle/field_solver.c; not in the reference tree)
+    def push_bfd(self, delt, cc, ext=0):
+        self.lib.nixo_domain_push_bfd(self.h, delt, cc, int(ext))
+
+    def push_efd(self, delt, cc, cfj=1.0):
+        self.lib.nixo_domain_push_efd(self.h, delt, cc, cfj)
+
+    def step_em(self, delt, cc, cfj=1.0, simd=False):
+        self.lib.nixo_domain_step_em(self.h, delt, cc, cfj, int(simd))
+
+    def field_energy(self):
+        """[nchunk][2]: sum E^2, sum B^2 over the interior cells of every chunk"""
+        out = np.zeros((self.nchunk, 2))
+        a_d, p_d = _iarr(self.dims)
+        for k, c in enumerate(self.chunks):
+            e = np.zeros(2)
+            self.lib.nixo_fdtd_energy(c.uf.ctypes.data_as(C.POINTER(C.c_double)), p_d, self.nb,
+                                      e.ctypes.data_as(C.POINTER(C.c_double)))
+            out[k] = e
+        return out
 
     def total_particles(self):
         return int(self.lib.nixo_domain_total_particles(self.h))
