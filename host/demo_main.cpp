@@ -86,6 +86,8 @@ int main(int argc, char** argv)
       chunks.push_back(std::move(c));
     }
     auto dom = make_domain(chunks, chunkmap, cdims, nb, order, species, 1.0, 0, /*strict_fp=*/true, 2.0);
+    check(nixb200_domain_exchange_field(dom->h), "exchange_field");
+    check(nixb200_domain_sort(dom->h), "sort");
     for (int s = 0; s < steps; s++) check(nixb200_domain_step(dom->h, 0.5), "step");
     int err = 0;
     check(nixb200_domain_check(dom->h, &err), "check");
@@ -94,6 +96,7 @@ int main(int argc, char** argv)
     for (int id = 0; id < nchunk; id++) {
       auto* g          = static_cast<GpuChunk*>(chunks[id].get());
       g->host_is_newer = false;
+      g->host_synced   = false;
       g->sync_host();
       write_bin(dir + "/out_uj_" + std::to_string(id) + ".bin", g->uj.data(), g->uj.size());
       for (int is = 0; is < ns; is++) {

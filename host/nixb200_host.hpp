@@ -123,7 +123,8 @@ public:
   std::vector<ParticlePtr>     up; ///< host staging of the species (reference container)
   std::shared_ptr<GpuDomain>   domain;
   int                          local = -1; ///< index inside the domain
-  bool                         host_is_newer = true;
+  bool                         host_is_newer = true;  ///< staging holds data the device has not seen
+  bool                         host_synced   = false; ///< staging equals the device state (no step since the last download)
 
   GpuChunk(nix::Dims3D dims, nix::Bool3D has_dim, int id = 0) : nix::Chunk(dims, has_dim, id)
   {
@@ -165,7 +166,7 @@ public:
   /// device -> host staging (before pack, diagnostics, rebalance)
   void sync_host()
   {
-    if (!domain || local < 0 || host_is_newer) return;
+    if (!domain || local < 0 || host_is_newer || host_synced) return;
     check(nixb200_chunk_field_download(domain->h, local, NIXB200_FIELD_UF, uf.data()), "field_download");
     check(nixb200_chunk_field_download(domain->h, local, NIXB200_FIELD_UJ, uj.data()), "field_download");
     for (size_t is = 0; is < up.size(); is++) {
@@ -176,6 +177,7 @@ public:
       up[is]->Np = (int)np;
       check(nixb200_chunk_get_pindex(domain->h, local, (int)is, up[is]->pindex.data()), "get_pindex");
     }
+    host_synced = true;
   }
 
   // Chunk::pack / unpack (chunk.cpp:18-116): base header first, then this chunk's arrays in the
@@ -243,13 +245,16 @@ public:
 };
 
 /// Build (or rebuild) the rank's domain from its chunk vector and upload every chunk's staging.
-/// `chunks` are the rank-local chunks in ascending id order (ChunkVector keeps them sorted).
+/// `chunks` are the rank-local chunks in ascending id order (ChunkVector keeps them sorted).  Chunks that
+/// still live in a previous domain are brought down to their staging first (lazily: only here and in
+/// GpuChunk::pack, never per step).
 template <typename ChunkVec>
 std::shared_ptr<GpuDomain> make_domain(ChunkVec& chunks, nix::ChunkMap& chunkmap, const int cdims[3], int nb, int order,
                                        const std::vector<SpeciesSpec>& species, float64 cc, int device, bool strict_fp,
                                        double capacity_factor = 1.25, int pusher = NIXB200_PUSH_BORIS)
 {
   if (chunks.size() == 0) return nullptr;
+  for (auto& c : chunks) static_cast<GpuChunk*>(c.get())->sync_host();
   auto* first = static_cast<GpuChunk*>(chunks.front().get());
   auto* last  = static_cast<GpuChunk*>(chunks.back().get());
   std::vector<int> nd = first->get_dims();
@@ -278,24 +283,29 @@ std::shared_ptr<GpuDomain> make_domain(ChunkVec& chunks, nix::ChunkMap& chunkmap
     }
     check(nixb200_domain_set_particles(dom->h, is, flat.data(), np.data()), "set_particles");
   }
-  check(nixb200_domain_exchange_field(dom->h), "exchange_field");
-  check(nixb200_domain_sort(dom->h), "sort");
-  for (auto& c : chunks) static_cast<GpuChunk*>(c.get())->host_is_newer = false;
+  for (auto& c : chunks) {
+    static_cast<GpuChunk*>(c.get())->host_is_newer = false;
+    static_cast<GpuChunk*>(c.get())->host_synced   = false; // (sort may drop / reorder particles)
+  }
   return dom;
 }
 
 /// nix::Application with the PIC step on the GPU.  A downstream application derives from this
-/// instead of nix::Application, fills the staging of its GpuChunks in setup_chunks(), and keeps
+/// instead of nix::Application, fills the staging of its GpuChunks in Chunk::setup(), and keeps
 /// everything else (config, diagnostics, checkpoints, balancer) unchanged.
 class GpuApplication : public nix::Application
 {
 protected:
   std::shared_ptr<GpuDomain> domain;
   std::vector<SpeciesSpec>   species;
-  int                        order = 2, nb = 2, device = 0;
+  int                        order = 2, nb = 2, device = -1; ///< device < 0: node-local rank modulo the device count
   float64                    cc    = 1.0;
-  bool                       strict_fp = false;
-  int                        pusher    = NIXB200_PUSH_BORIS;
+  bool                       strict_fp    = true;  ///< bit-exact with the reference's scalar templates (1.8 % slower)
+  bool                       field_solver = false; ///< true: nixb200_domain_step_em (E/B never leave the device)
+  float64                    cfj          = 1.0;
+  int                        pusher       = NIXB200_PUSH_BORIS;
+  void*                      nccl_comm    = nullptr; ///< created once, handed to every rebuilt domain
+  long                       npush = 0, nrebuild = 0;
 
 public:
   GpuApplication(int argc, char** argv, PtrInterface interface = std::make_shared<GpuInterface>())
@@ -303,22 +313,68 @@ public:
   {
   }
 
+  ~GpuApplication() override
+  {
+    domain.reset();
+    if (nccl_comm) nixb200_comm_destroy(nccl_comm);
+  }
+
+  /// node-local rank -> device (one rank per GPU)
+  virtual int select_device()
+  {
+    if (device >= 0) return device;
+    int ndev = 0;
+    check(nixb200_device_count(&ndev), "nixb200_device_count");
+    MPI_Comm node;
+    int      local = 0;
+    MPI_Comm_split_type(MPI_COMM_WORLD, MPI_COMM_TYPE_SHARED, thisrank, MPI_INFO_NULL, &node);
+    MPI_Comm_rank(node, &local);
+    MPI_Comm_free(&node);
+    return device = local % ndev;
+  }
+
+  /// (Re)build the device-resident domain when the chunk set of ANY rank changed.  Every decision that
+  /// leads to a collective call is itself collective: the staleness flag is all-reduced and the NCCL
+  /// bootstrap runs on every rank, whether or not it owns chunks.
+  virtual void ensure_domain()
+  {
+    int stale = !domain && chunkvec.size() > 0;
+    for (auto& c : chunkvec) stale = stale || static_cast<GpuChunk*>(c.get())->domain != domain;
+    MPI_Allreduce(MPI_IN_PLACE, &stale, 1, MPI_INT, MPI_MAX, MPI_COMM_WORLD);
+    if (!stale) return;
+    const int dev = select_device();
+    if (nprocess > 1 && nccl_comm == nullptr) {
+      unsigned char id[128] = {0};
+      if (thisrank == 0) check(nixb200_comm_unique_id(id), "comm_unique_id");
+      MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
+      check(nixb200_comm_create(nprocess, thisrank, id, dev, &nccl_comm), "nixb200_comm_create");
+    }
+    int cd[3] = {cdims[0], cdims[1], cdims[2]};
+    domain    = make_domain(chunkvec, *chunkmap, cd, nb, order, species, cc, dev, strict_fp, 1.25, pusher);
+    nrebuild++;
+    if (domain) {
+      auto boundary = chunkmap->get_rank_boundary();
+      check(nixb200_domain_set_ranks(domain->h, nprocess, boundary.data(), thisrank), "nixb200_domain_set_ranks");
+      if (nprocess > 1) check(nixb200_domain_set_comm(domain->h, nccl_comm), "nixb200_domain_set_comm");
+      check(nixb200_domain_exchange_field(domain->h), "exchange_field");
+      check(nixb200_domain_sort(domain->h), "sort");
+    }
+  }
+
   /// Application::push() (application.hpp:343-346): one step of every local chunk
   void push() override
   {
-    bool stale = !domain;
-    for (auto& c : chunkvec) stale = stale || static_cast<GpuChunk*>(c.get())->domain != domain;
-    if (stale) {
-      domain = make_domain(chunkvec, *chunkmap, cdims, nb, order, species, cc, device, strict_fp, 1.25, pusher);
-      if (domain && nprocess > 1) {
-        unsigned char id[128] = {0};
-        if (thisrank == 0) check(nixb200_comm_unique_id(id), "comm_unique_id");
-        MPI_Bcast(id, 128, MPI_BYTE, 0, MPI_COMM_WORLD);
-        domain->set_ranks(chunkmap->get_rank_boundary(), thisrank, id);
-      }
-    }
+    ensure_domain();
+    npush++;
     if (!domain) return;
-    check(nixb200_domain_step(domain->h, cfgparser->get_delt()), "nixb200_domain_step");
+    const float64 delt = cfgparser->get_delt();
+    if (field_solver) check(nixb200_domain_step_em(domain->h, delt, cfj), "nixb200_domain_step_em");
+    else check(nixb200_domain_step(domain->h, delt), "nixb200_domain_step");
+    int err = 0;
+    check(nixb200_domain_check(domain->h, &err), "nixb200_domain_check");
+    if (err & NIXB200_ERR_CFL) ERROR << tfm::format("step[%d] a particle moved more than one cell (c*delt > delh)", curstep);
+    if (err & NIXB200_ERR_UNSORTED) ERROR << tfm::format("step[%d] particle container was not cell-sorted", curstep);
+    assert_mpi((err & NIXB200_ERR_CAPACITY) == 0, "particle storage overflowed on the device (raise capacity_factor)");
     // Chunk::load feeds the balancer (chunk.hpp:177-192): device time of the push, shared among
     // the chunks in proportion to their particle counts
     double ms = 0;
@@ -336,17 +392,36 @@ public:
     for (size_t k = 0; k < chunkvec.size(); k++) {
       auto* c          = static_cast<GpuChunk*>(chunkvec[k].get());
       c->host_is_newer = false;
+      c->host_synced   = false;
       c->set_load_value(total > 0 ? ms * w[k] / total : ms / chunkvec.size());
     }
   }
 
-  /// chunks are about to be shipped by Balancer::sendrecv_chunk through Chunk::pack (balancer.hpp:161-222)
+  /// Application::rebalance() (application.cpp:337-381) ships chunks through Chunk::pack / unpack
+  /// (Balancer::sendrecv_chunk, balancer.hpp:161-222).  GpuChunk::pack brings ITS chunk down from the device
+  /// on demand, so nothing is downloaded on the steps -- or for the chunks -- that do not move; the domain is
+  /// rebuilt by the next push() only if the rank boundaries actually changed.
   bool rebalance() override
   {
+    const auto before = chunkmap->get_rank_boundary();
+    const bool ran    = nix::Application::rebalance();
+    if (ran && chunkmap->get_rank_boundary() != before) {
+      for (auto& c : chunkvec) static_cast<GpuChunk*>(c.get())->sync_host(); // those that stay: staged for the re-upload
+      for (auto& c : chunkvec) {
+        auto* g   = static_cast<GpuChunk*>(c.get());
+        g->host_is_newer = true;
+        g->domain.reset();
+        g->local = -1;
+      }
+      domain.reset();
+    }
+    return ran;
+  }
+
+  /// everything back in the staging containers (before diagnostics that read Chunk data, before save)
+  void sync_host_all()
+  {
     for (auto& c : chunkvec) static_cast<GpuChunk*>(c.get())->sync_host();
-    bool moved = nix::Application::rebalance();
-    if (moved) domain.reset(); // push() rebuilds it from the new chunk vector
-    return moved;
   }
 };
 } // namespace nixb200host

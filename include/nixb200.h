@@ -195,6 +195,11 @@ int nixb200_domain_set_ranks(nixb200_domain* d, int nrank, const int* boundary, 
 int nixb200_comm_unique_id(void* id128);
 int nixb200_domain_comm_init(nixb200_domain* d, const void* id128);
 int nixb200_domain_set_comm(nixb200_domain* d, void* nccl_comm);
+/* a communicator the APPLICATION owns (one per run; handed to every domain it rebuilds after a rebalance with
+ * nixb200_domain_set_comm, which never destroys it) */
+int nixb200_comm_create(int nrank, int rank, const void* id128, int device, void** nccl_comm);
+int nixb200_comm_destroy(void* nccl_comm);
+int nixb200_device_count(int* n);
 /* per step: ghost cells sent to other ranks per halo exchange; particles sent / received by the
  * last migrate */
 int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int64_t* particles_sent,

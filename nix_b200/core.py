@@ -34,7 +34,8 @@ SYMBOLS = [
     "nixb200_plan_entries", "nixb200_domain_set_ranks", "nixb200_comm_unique_id", "nixb200_domain_comm_init",
     "nixb200_domain_set_comm", "nixb200_domain_peer_traffic", "nixb200_domain_reserve",
     "nixb200_domain_get_capacity", "nixb200_domain_push_bfd", "nixb200_domain_push_efd", "nixb200_domain_step_em",
-    "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp",
+    "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp", "nixb200_comm_create", "nixb200_comm_destroy",
+    "nixb200_device_count",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",

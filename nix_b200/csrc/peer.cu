@@ -562,6 +562,38 @@ int nixb200_domain_comm_init(nixb200_domain* dd, const void* id128)
   return 0;
 }
 
+int nixb200_comm_create(int nrank, int rank, const void* id128, int device, void** comm_out)
+{
+  if (!id128 || !comm_out) {
+    set_error("comm_create: null argument");
+    return 1;
+  }
+  Nccl* n = nccl();
+  if (!n) return 1;
+  DeviceGuard  dev_guard(device);
+  ncclUniqueId id;
+  std::memcpy(&id, id128, sizeof(id));
+  ncclComm_t comm = nullptr;
+  NIX_NCCL(n->CommInitRank(&comm, nrank, id, rank));
+  *comm_out = comm;
+  return 0;
+}
+
+int nixb200_comm_destroy(void* comm)
+{
+  Nccl* n = nccl();
+  if (!n || !comm) return 1;
+  NIX_NCCL(n->CommDestroy(reinterpret_cast<ncclComm_t>(comm)));
+  return 0;
+}
+
+int nixb200_device_count(int* n)
+{
+  if (!n) return 1;
+  NIX_CUDA(cudaGetDeviceCount(n));
+  return 0;
+}
+
 int nixb200_domain_set_comm(nixb200_domain* dd, void* nccl_comm)
 {
   Domain* d = reinterpret_cast<Domain*>(dd);
