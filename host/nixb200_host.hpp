@@ -87,6 +87,7 @@ public:
     desc.strict_fp       = strict_fp ? 1 : 0;
     desc.capacity_factor = capacity_factor;
     desc.pusher          = pusher; // push_boris / push_vay / push_higuera_cary (primitives.hpp:165-253)
+    desc.fp32            = 0;      // the host mirror keeps the reference's real type
     std::vector<double> q, m;
     for (auto& s : species) {
       q.push_back(s.q);

@@ -68,6 +68,12 @@ typedef struct {
   double capacity_factor; /* initial particle storage = factor * initial count (>=1; 0 -> 1.25); the
                              stores regrow on their own while a run drifts (see nixb200_domain_reserve) */
   int    pusher;     /* NIXB200_PUSH_BORIS / _VAY / _HIGUERA_CARY               primitives.hpp:165-253 */
+  int    fp32;       /* 0: fp64 on the device (the reference's real type, nix.hpp:76-78); 1: fp32 mode -- particles,
+                        E/B and J are kept as floats on the device (particle positions relative to their chunk's
+                        origin), all kernels compute in fp32; this C ABI stays fp64 (converted at the boundary).
+                        No reference exists for it: results agree with the fp64 path to ~1e-6 (tests: 1e-5);
+                        strict_fp is ignored; the MpiBuffer-layout halo calls and the full-array overlapped
+                        transfers are fp64 only */
 } nixb200_domain_desc;
 
 const char* nixb200_last_error(void);

@@ -60,6 +60,7 @@ class DomainDesc(C.Structure):
         ("strict_fp", C.c_int),
         ("capacity_factor", C.c_double),
         ("pusher", C.c_int),
+        ("fp32", C.c_int),
     ]
 
 
@@ -196,7 +197,7 @@ class Domain:
     nix::Application, application.hpp:114, behind the Chunk API)."""
 
     def __init__(self, cdims, dims, nb, order, q, m, delh=(1.0, 1.0, 1.0), cc=1.0, coord=None,
-                 id_range=None, device=0, strict_fp=True, capacity_factor=1.25, stream=None, pusher=0):
+                 id_range=None, device=0, strict_fp=True, capacity_factor=1.25, stream=None, pusher=0, fp32=False):
         self.lib = load_library()
         self.cdims = tuple(int(v) for v in cdims)
         self.dims = tuple(int(v) for v in dims)
@@ -222,6 +223,8 @@ class Domain:
         desc.strict_fp = int(bool(strict_fp))
         desc.capacity_factor = float(capacity_factor)
         desc.pusher = int(pusher)  # PUSH_BORIS / PUSH_VAY / PUSH_HIGUERA_CARY
+        desc.fp32 = int(bool(fp32))  # fp32 on the device (the C ABI stays fp64)
+        self.fp32 = bool(fp32)
         self.h = C.c_void_p()
         self._ck(self.lib.nixb200_domain_create(
             C.byref(desc), self.coord.ctypes.data_as(C.POINTER(C.c_int)),

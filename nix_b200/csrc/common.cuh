@@ -107,48 +107,99 @@ inline __host__ __device__ size_t soa(int comp, size_t cap, size_t i)
 // arithmetic helpers.  STRICT = evaluate exactly as written (no FMA contraction) so that push
 // results are bit-identical to the reference's scalar templates compiled without contraction.
 // ---------------------------------------------------------------------------------------------
-template <bool S>
-__device__ __forceinline__ double mul(double a, double b)
+// (double: __d*_rn, float: __f*_rn; T is deduced, so mixing a float with a double operand does not compile --
+// the fp32 instantiations must not be promoted to fp64 behind our back)
+template <bool S, typename T>
+__device__ __forceinline__ T mul(T a, T b)
 {
-  if constexpr (S) return __dmul_rn(a, b);
-  else return a * b;
+  if constexpr (!S) return a * b;
+  else if constexpr (sizeof(T) == 8) return __dmul_rn(a, b);
+  else return __fmul_rn(a, b);
 }
-template <bool S>
-__device__ __forceinline__ double add(double a, double b)
+template <bool S, typename T>
+__device__ __forceinline__ T add(T a, T b)
 {
-  if constexpr (S) return __dadd_rn(a, b);
-  else return a + b;
+  if constexpr (!S) return a + b;
+  else if constexpr (sizeof(T) == 8) return __dadd_rn(a, b);
+  else return __fadd_rn(a, b);
 }
-template <bool S>
-__device__ __forceinline__ double sub(double a, double b)
+template <bool S, typename T>
+__device__ __forceinline__ T sub(T a, T b)
 {
-  if constexpr (S) return __dsub_rn(a, b);
-  else return a - b;
+  if constexpr (!S) return a - b;
+  else if constexpr (sizeof(T) == 8) return __dsub_rn(a, b);
+  else return __fsub_rn(a, b);
 }
 // a*b + c
-template <bool S>
-__device__ __forceinline__ double mad(double a, double b, double c)
+template <bool S, typename T>
+__device__ __forceinline__ T mad(T a, T b, T c)
 {
-  if constexpr (S) return __dadd_rn(__dmul_rn(a, b), c);
-  else return fma(a, b, c);
+  if constexpr (!S) {
+    if constexpr (sizeof(T) == 8) return fma(a, b, c);
+    else return fmaf(a, b, c);
+  } else return add<true>(mul<true>(a, b), c);
 }
-template <bool S>
-__device__ __forceinline__ double div_(double a, double b)
+template <bool S, typename T>
+__device__ __forceinline__ T div_(T a, T b)
 {
-  if constexpr (S) return __ddiv_rn(a, b);
-  else return a / b;
+  if constexpr (!S) return a / b;
+  else if constexpr (sizeof(T) == 8) return __ddiv_rn(a, b);
+  else return __fdiv_rn(a, b);
 }
-template <bool S>
-__device__ __forceinline__ double sqrt_(double a)
+template <bool S, typename T>
+__device__ __forceinline__ T sqrt_(T a)
 {
-  if constexpr (S) return __dsqrt_rn(a);
-  else return sqrt(a);
+  if constexpr (sizeof(T) == 8) return S ? __dsqrt_rn(a) : sqrt(a);
+  else return S ? __fsqrt_rn(a) : sqrtf(a);
 }
 
 // primitives.hpp:46-58 -- always exact (counts and permutations must be bit-exact)
 __device__ __forceinline__ int digitize(double x, double xmin, double rdx)
 {
   return (int)floor(__dmul_rn(__dsub_rn(x, xmin), rdx));
+}
+__device__ __forceinline__ int digitize(float x, float xmin, float rdx)
+{
+  return (int)floorf(__fmul_rn(__fsub_rn(x, xmin), rdx));
+}
+
+// The real type of a domain: fp64 is the reference's (nix.hpp:76-78 has real = float64 only); fp32 is the
+// north star's second mode.  NCT = words of T per particle in the SoA store: x y z ux uy uz + the 64-bit id.
+template <typename T>
+struct Real;
+template <>
+struct Real<double> {
+  using vec2 = double2;
+  static constexpr int NCT = 7;
+  static __device__ __forceinline__ double2 make2(double a, double b) { return make_double2(a, b); }
+};
+template <>
+struct Real<float> {
+  using vec2 = float2;
+  static constexpr int NCT = 8; // the id occupies two words
+  static __device__ __forceinline__ float2 make2(float a, float b) { return make_float2(a, b); }
+};
+
+// words per cell of the E/B array on the device: the reference's 6 doubles (48 B), or 8 floats (32 B, two
+// of them padding) because TMA strides must be multiples of 16 bytes
+template <typename T>
+__host__ __device__ constexpr int field_stride()
+{
+  return sizeof(T) == 8 ? 6 : 8;
+}
+
+// per-chunk constants in the real type of the kernel (staged in shared memory from ChunkGeo)
+template <typename T>
+struct ChunkGeoT {
+  T   lo[3], hi[3], off[3], hoff[3], imin[3];
+  int nbr[27];
+};
+template <typename T>
+__device__ __forceinline__ void stage_chunk_geo(ChunkGeoT<T>* dst, const ChunkGeo* src, int tid, int nthreads)
+{
+  const double* sd = reinterpret_cast<const double*>(src);
+  for (int t = tid; t < 15; t += nthreads) reinterpret_cast<T*>(dst)[t] = (T)sd[t];
+  for (int t = tid; t < 27; t += nthreads) dst->nbr[t] = src->nbr[t];
 }
 
 // entry of bin (b[0],b[1],b[2]) in the slab of direction d = 9*ez+3*ey+ex (0/1/2 = -/centre/+);
@@ -196,8 +247,9 @@ extern std::atomic<int64_t> g_launches;
 struct PushArgs {
   Geo              geo;
   const ChunkGeo*  cg;
-  const double*    uf; // [nchunk][Mz][My][Mx][6]
-  double*          uj; // [nchunk][Mz][My][Mx][4]
+  const void*      uf; // [nchunk][Mz][My][Mx][6]  (real type of the domain)
+  void*            uj; // [nchunk][Mz][My][Mx][4]
+  bool             fp32 = false;
   SpeciesDev       sp;
   double           delt;
   int*             err;    // err[0]: NIXB200_ERR_* bits; err[1]: sticky "store overflowed" flag (kernels exit)
@@ -207,41 +259,48 @@ struct PushArgs {
 // ev: null, or four events recorded around the two kernels: ev[0] k_push ev[1] | ev[2] k_deposit ev[3]
 int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict, cudaStream_t st,
                         cudaEvent_t* ev = nullptr);
-int push_deposit_prepare(int order); // per-device kernel attributes (call with the device current)
+int push_deposit_prepare(int order, bool fp32); // per-device kernel attributes (call with the device current)
 size_t push_smem_bytes(const Geo& g);
 void   push_tile_box(int order, int& ez, int& ey, int& ex); // nodes per axis of the staged E/B tile
 int    choose_push_tile(Geo& g); // fills tile / ntl / ntile; non-zero if nothing fits
 
-int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st);
+int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st, bool fp32);
 int launch_mig_scan(const Geo& g, SpeciesDev& sp, cudaStream_t st);
 int launch_peer_counts(const Geo& g, const SpeciesDev& sp, const PeerTabs& pt, int is, int32_t* cnt_send,
                        cudaStream_t st);
 int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int* err,
-                     cudaStream_t st);
+                     cudaStream_t st, bool fp32);
 int launch_stats(const Geo& g, const SpeciesDev& sp, int32_t* out4, cudaStream_t st);
 int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int nrecv_particles,
-                    int* err, cudaStream_t st);
+                    int* err, cudaStream_t st, bool fp32);
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
-                cudaStream_t st);
+                cudaStream_t st, bool fp32);
 size_t scan_tmp_bytes(size_t n);
 
-int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, const PeerTabs& pt, const double* recvbuf,
-                      cudaStream_t st);
-int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, const PeerTabs& pt, const double* recvbuf,
-                        cudaStream_t st);
-int launch_peer_pack(const Geo& g, int mode, const double* data, const PeerTabs& pt, double* sendbuf,
-                     cudaStream_t st);
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, void* uf, const PeerTabs& pt, const void* recvbuf,
+                      cudaStream_t st, bool fp32);
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, void* uj, const PeerTabs& pt, const void* recvbuf,
+                        cudaStream_t st, bool fp32);
+int launch_peer_pack(const Geo& g, int mode, const void* data, const PeerTabs& pt, void* sendbuf,
+                     cudaStream_t st, bool fp32);
 int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* buf, cudaStream_t st);
 int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
                        const int* nbvalid_dev, cudaStream_t st);
 
 // Yee FDTD on the device-resident grid (fdtd.cu)
-int launch_push_bfd(const Geo& g, double* uf, double delt, int ext, cudaStream_t st);
-int launch_push_efd(const Geo& g, double* uf, const double* uj, double delt, double cfj, cudaStream_t st);
-int launch_field_energy(const Geo& g, const double* uf, double* out, cudaStream_t st);
+int launch_push_bfd(const Geo& g, void* uf, double delt, int ext, cudaStream_t st, bool fp32);
+int launch_push_efd(const Geo& g, void* uf, const void* uj, double delt, double cfj, cudaStream_t st, bool fp32);
+int launch_field_energy(const Geo& g, const void* uf, double* out, cudaStream_t st, bool fp32);
 
 // interior cells of all chunks <-> dense [chunk][Nz][Ny][Nx][ncomp] (pack: full -> dense)
 int launch_interior(bool pack, double* full, double* dense, const Geo& g, int ncomp, cudaStream_t st);
+// fp32 mode: conversions at the (fp64) C-ABI boundary
+int launch_aos_to_soa_f32(const double* aos, float* soa_base, size_t cap, size_t first, size_t n, const int32_t* cbase,
+                          int nchunk, const double* origin, const double* extent /* z,y,x */, cudaStream_t st);
+int launch_soa_to_aos_f32(const float* soa_base, double* aos, size_t cap, size_t first, size_t n, const double* origin3,
+                          cudaStream_t st);
+int launch_cells_convert(bool to_dev, double* host_layout, float* dev_layout, size_t ncell, int nc, int fc, cudaStream_t st);
+int launch_interior_f32(bool pack, float* full, double* dense, const Geo& g, int ncomp, int fc, cudaStream_t st);
 int launch_aos_to_soa(const double* aos, double* soa_base, size_t cap, size_t first, size_t n,
                       cudaStream_t st);
 int launch_soa_to_aos(const double* soa_base, double* aos, size_t cap, size_t first, size_t n,

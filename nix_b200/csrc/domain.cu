@@ -41,14 +41,16 @@ static int make_tensor_map(Domain* d)
     return 1;
   }
   const Geo&  g       = d->geo;
-  cuuint64_t  dims[5] = {6, (cuuint64_t)g.M[2], (cuuint64_t)g.M[1], (cuuint64_t)g.M[0], (cuuint64_t)g.nchunk};
-  cuuint64_t  strides[4] = {48, (cuuint64_t)g.M[2] * 48, (cuuint64_t)g.M[1] * g.M[2] * 48,
-                            (cuuint64_t)g.M[0] * g.M[1] * g.M[2] * 48};
+  // one cell = 6 doubles = 48 bytes, or 8 floats = 32 bytes (global strides must be multiples of 16 bytes)
+  const cuuint64_t fc = (cuuint64_t)d->fcs, cb = fc * d->esz;
+  cuuint64_t  dims[5] = {fc, (cuuint64_t)g.M[2], (cuuint64_t)g.M[1], (cuuint64_t)g.M[0], (cuuint64_t)g.nchunk};
+  cuuint64_t  strides[4] = {cb, (cuuint64_t)g.M[2] * cb, (cuuint64_t)g.M[1] * g.M[2] * cb,
+                            (cuuint64_t)g.M[0] * g.M[1] * g.M[2] * cb};
   int ez, ey, ex;
   push_tile_box(g.order, ez, ey, ex); // compile-time box of the push kernel (stencil box + bank padding)
-  cuuint32_t  box[5]  = {6, (cuuint32_t)ex, (cuuint32_t)ey, (cuuint32_t)ez, 1};
+  cuuint32_t  box[5]  = {(cuuint32_t)fc, (cuuint32_t)ex, (cuuint32_t)ey, (cuuint32_t)ez, 1};
   cuuint32_t  estr[5] = {1, 1, 1, 1, 1};
-  CUresult    r = ((encode_fn)fn)(&d->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, d->uf, dims, strides, box, estr,
+  CUresult    r = ((encode_fn)fn)(&d->tmap, d->fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, d->uf, dims, strides, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -104,7 +106,7 @@ static int alloc_leavers(Domain* d, SpeciesDev& s, int64_t lcap)
 {
   s.lcap = lcap;
   NIX_CUDA(cudaMalloc(&s.lrec, sizeof(int4) * lcap));
-  NIX_CUDA(cudaMalloc(&s.msg, sizeof(double) * NC * lcap));
+  NIX_CUDA(cudaMalloc(&s.msg, d->esz * d->nct * lcap));
   NIX_CUDA(cudaMalloc(&s.msgkey, sizeof(int32_t) * lcap));
   NIX_CUDA(cudaMemset(s.msgkey, 0xff, sizeof(int32_t) * lcap));
   if (d->peer && peer_alloc_species(d, s)) return 1;
@@ -130,13 +132,25 @@ static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
     return 1;
   }
   s.cap = cap;
-  NIX_CUDA(cudaMalloc(&s.xu, sizeof(double) * NC * cap));
-  NIX_CUDA(cudaMalloc(&s.xv, sizeof(double) * NC * cap));
+  NIX_CUDA(cudaMalloc(&s.xu, d->esz * d->nct * cap));
+  NIX_CUDA(cudaMalloc(&s.xv, d->esz * d->nct * cap));
   NIX_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * cap));
   NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * cap));
-  NIX_CUDA(cudaMemset(s.xu, 0, sizeof(double) * NC * cap));
-  NIX_CUDA(cudaMemset(s.xv, 0, sizeof(double) * NC * cap));
+  NIX_CUDA(cudaMemset(s.xu, 0, d->esz * d->nct * cap));
+  NIX_CUDA(cudaMemset(s.xv, 0, d->esz * d->nct * cap));
   return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, cap / 16))); // regrown on demand (ensure_capacity)
+}
+
+// fp32 mode: fp64 AoS scratch for the particle boundary
+static int aos_scratch(Domain* d, size_t bytes)
+{
+  if (bytes <= d->aos_tmp_bytes) return 0;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  if (d->aos_tmp) cudaFree(d->aos_tmp);
+  d->aos_tmp = nullptr, d->aos_tmp_bytes = 0;
+  NIX_CUDA(cudaMalloc(&d->aos_tmp, bytes));
+  d->aos_tmp_bytes = bytes;
+  return 0;
 }
 
 static int check_chunk(Domain* d, int k)
@@ -167,7 +181,7 @@ static int check_species(Domain* d, int is)
 
 int do_sort_species(Domain* d, SpeciesDev& s)
 {
-  if (launch_sort(d->geo, d->cg_dev, s, d->err_dev, d->scan_tmp, d->stream)) return 1;
+  if (launch_sort(d->geo, d->cg_dev, s, d->err_dev, d->scan_tmp, d->stream, d->fp32)) return 1;
   std::swap(s.xu, s.xv);           // XtensorParticle::swap, xtensor_particle.hpp:120-123
   std::swap(s.cbase, s.cbase_new); // Np = pindex(Ng), xtensor_particle.hpp:320
   return 0;
@@ -188,14 +202,15 @@ int grow_particles(Domain* d, SpeciesDev& s, int64_t newcap)
   double*  nxu = nullptr;
   double*  nxv = nullptr;
   int32_t *nkey = nullptr, *nordl = nullptr;
-  NIX_CUDA(cudaMalloc(&nxu, sizeof(double) * NC * newcap));
-  NIX_CUDA(cudaMalloc(&nxv, sizeof(double) * NC * newcap));
+  NIX_CUDA(cudaMalloc(&nxu, d->esz * d->nct * newcap));
+  NIX_CUDA(cudaMalloc(&nxv, d->esz * d->nct * newcap));
   NIX_CUDA(cudaMalloc(&nkey, sizeof(int32_t) * newcap));
   NIX_CUDA(cudaMalloc(&nordl, sizeof(int32_t) * newcap));
-  NIX_CUDA(cudaMemsetAsync(nxu, 0, sizeof(double) * NC * newcap, d->stream));
-  NIX_CUDA(cudaMemsetAsync(nxv, 0, sizeof(double) * NC * newcap, d->stream));
-  for (int c = 0; c < NC; c++)
-    NIX_CUDA(cudaMemcpyAsync(nxu + (size_t)c * newcap, s.xu + (size_t)c * s.cap, sizeof(double) * s.cap,
+  NIX_CUDA(cudaMemsetAsync(nxu, 0, d->esz * d->nct * newcap, d->stream));
+  NIX_CUDA(cudaMemsetAsync(nxv, 0, d->esz * d->nct * newcap, d->stream));
+  for (int c = 0; c < d->nct; c++)
+    NIX_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(nxu) + (size_t)c * newcap * d->esz,
+                             reinterpret_cast<char*>(s.xu) + (size_t)c * s.cap * d->esz, d->esz * s.cap,
                              cudaMemcpyDeviceToDevice, d->stream));
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   cudaFree(s.xu);
@@ -353,6 +368,10 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
 
   Domain* d = new Domain();
   d->desc   = *desc;
+  d->fp32   = desc->fp32 != 0;
+  d->esz    = d->fp32 ? 4 : 8;
+  d->nct    = d->fp32 ? 8 : 7;
+  d->fcs    = d->fp32 ? 8 : 6;
   Geo& g    = d->geo;
   std::memset(&g, 0, sizeof(g));
   g.nb     = desc->nb;
@@ -421,6 +440,8 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
     for (int a = 0; a < 3; a++) {
       int    off = c[a] * g.N[a];
       double del = g.del[a];
+      d->origin_host.push_back(off * del);
+      if (d->fp32) off = 0;                    // fp32 mode: positions are relative to the chunk's origin
       cg.lo[a]   = off * del;                  // chunk.cpp:217,224,231
       cg.hi[a]   = off * del + g.N[a] * del;   // chunk.cpp:218,225,232
       cg.off[a]  = cg.lo[a] - 0.5 * del * g.is_odd;       // xtensor_particle.hpp:332-334
@@ -449,7 +470,7 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
   };
   if (cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess) return fail("stream");
   d->owns_stream = true;
-  if (push_deposit_prepare(g.order)) {
+  if (push_deposit_prepare(g.order, d->fp32)) {
     std::string e = g_error;
     nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(d));
     set_error(e);
@@ -458,10 +479,12 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
   if (cudaMalloc(&d->cg_dev, sizeof(ChunkGeo) * g.nchunk) != cudaSuccess) return fail("cudaMalloc");
   if (cudaMemcpy(d->cg_dev, d->cg_host.data(), sizeof(ChunkGeo) * g.nchunk, cudaMemcpyHostToDevice) != cudaSuccess)
     return fail("cudaMemcpy");
-  if (cudaMalloc(&d->uf, sizeof(double) * 6 * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uf");
-  if (cudaMalloc(&d->uj, sizeof(double) * 4 * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uj");
-  cudaMemset(d->uf, 0, sizeof(double) * 6 * d->cells_per_chunk * g.nchunk);
-  cudaMemset(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * g.nchunk);
+  if (cudaMalloc(&d->uf, d->esz * d->fcs * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uf");
+  if (cudaMalloc(&d->uj, d->esz * 4 * d->cells_per_chunk * g.nchunk) != cudaSuccess) return fail("cudaMalloc uj");
+  cudaMemset(d->uf, 0, d->esz * d->fcs * d->cells_per_chunk * g.nchunk);
+  cudaMemset(d->uj, 0, d->esz * 4 * d->cells_per_chunk * g.nchunk);
+  if (cudaMalloc(&d->origin_dev, sizeof(double) * 3 * g.nchunk) != cudaSuccess) return fail("cudaMalloc origin");
+  cudaMemcpy(d->origin_dev, d->origin_host.data(), sizeof(double) * 3 * g.nchunk, cudaMemcpyHostToDevice);
   if (cudaMalloc(&d->scan_tmp, scan_tmp_bytes((size_t)g.nchunk * g.ncell * LANES)) != cudaSuccess) return fail("cudaMalloc scan");
   if (cudaMalloc(&d->err_dev, 2 * sizeof(int)) != cudaSuccess) return fail("cudaMalloc err");
   cudaMemset(d->err_dev, 0, 2 * sizeof(int));
@@ -516,6 +539,8 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->err_dev) cudaFree(d->err_dev);
   if (d->stat_dev) cudaFree(d->stat_dev);
   if (d->energy_dev) cudaFree(d->energy_dev);
+  if (d->origin_dev) cudaFree(d->origin_dev);
+  if (d->aos_tmp) cudaFree(d->aos_tmp);
   if (d->stat_host) cudaFreeHost(d->stat_host);
   if (d->ev_stat) cudaEventDestroy(d->ev_stat);
   if (d->nbvalid_dev) cudaFree(d->nbvalid_dev);
@@ -564,13 +589,34 @@ int nixb200_domain_check(nixb200_domain* dd, int* errbits)
   return 0;
 }
 
+// address of chunk k inside uf / uj (bytes: the device arrays hold the domain's real type)
+static char* chunk_array(Domain* d, int which, int k)
+{
+  const int fc = (which == NIXB200_FIELD_UF) ? d->fcs : 4;
+  char*     b  = reinterpret_cast<char*>((which == NIXB200_FIELD_UF) ? d->uf : d->uj);
+  return b + (size_t)k * d->cells_per_chunk * fc * d->esz;
+}
+
+// fp32 mode: one chunk's fp64 array <-> the device floats, through the fp64 staging buffer of the domain
+static int chunk_convert(Domain* d, int which, int k, bool to_dev)
+{
+  const int nc = (which == NIXB200_FIELD_UF) ? 6 : 4, fc = (which == NIXB200_FIELD_UF) ? d->fcs : 4;
+  return launch_cells_convert(to_dev, d->halo_buf, reinterpret_cast<float*>(chunk_array(d, which, k)), d->cells_per_chunk, nc,
+                              fc, d->stream);
+}
+
 int nixb200_chunk_field_upload(nixb200_domain* dd, int k, int which, const double* host)
 {
   NIX_ENTER(dd);
   if (check_chunk(d, k) || !host) return 1;
-  int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
-  double* dst = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
-  NIX_CUDA(cudaMemcpyAsync(dst, host, sizeof(double) * nc * d->cells_per_chunk, cudaMemcpyHostToDevice, d->stream));
+  const int    nc    = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const size_t bytes = sizeof(double) * nc * d->cells_per_chunk;
+  if (d->fp32) {
+    NIX_CUDA(cudaMemcpyAsync(d->halo_buf, host, bytes, cudaMemcpyHostToDevice, d->stream));
+    if (chunk_convert(d, which, k, true)) return 1;
+  } else {
+    NIX_CUDA(cudaMemcpyAsync(chunk_array(d, which, k), host, bytes, cudaMemcpyHostToDevice, d->stream));
+  }
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   return 0;
 }
@@ -579,9 +625,14 @@ int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* h
 {
   NIX_ENTER(dd);
   if (check_chunk(d, k) || !host) return 1;
-  int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
-  const double* src = ((which == NIXB200_FIELD_UF) ? d->uf : d->uj) + (size_t)k * d->cells_per_chunk * nc;
-  NIX_CUDA(cudaMemcpyAsync(host, src, sizeof(double) * nc * d->cells_per_chunk, cudaMemcpyDeviceToHost, d->stream));
+  const int    nc    = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const size_t bytes = sizeof(double) * nc * d->cells_per_chunk;
+  if (d->fp32) {
+    if (chunk_convert(d, which, k, false)) return 1;
+    NIX_CUDA(cudaMemcpyAsync(host, d->halo_buf, bytes, cudaMemcpyDeviceToHost, d->stream));
+  } else {
+    NIX_CUDA(cudaMemcpyAsync(host, chunk_array(d, which, k), bytes, cudaMemcpyDeviceToHost, d->stream));
+  }
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   return 0;
 }
@@ -589,20 +640,34 @@ int nixb200_chunk_field_download(nixb200_domain* dd, int k, int which, double* h
 int nixb200_domain_field_upload_async(nixb200_domain* dd, int which, const double* host)
 {
   NIX_ENTER(dd);
-  if (!d || !host) return 1;
-  int     nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
-  double* dst = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
-  NIX_CUDA(cudaMemcpyAsync(dst, host, sizeof(double) * nc * d->cells_per_chunk * d->geo.nchunk, cudaMemcpyHostToDevice, d->stream));
+  if (!host) return 1;
+  const int    nc    = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const size_t bytes = sizeof(double) * nc * d->cells_per_chunk;
+  if (d->fp32) { // chunk by chunk through the staging buffer (stream order keeps it consistent)
+    for (int k = 0; k < d->geo.nchunk; k++) {
+      NIX_CUDA(cudaMemcpyAsync(d->halo_buf, reinterpret_cast<const char*>(host) + (size_t)k * bytes, bytes, cudaMemcpyHostToDevice, d->stream));
+      if (chunk_convert(d, which, k, true)) return 1;
+    }
+    return 0;
+  }
+  NIX_CUDA(cudaMemcpyAsync(chunk_array(d, which, 0), host, bytes * d->geo.nchunk, cudaMemcpyHostToDevice, d->stream));
   return 0;
 }
 
 int nixb200_domain_field_download_async(nixb200_domain* dd, int which, double* host)
 {
   NIX_ENTER(dd);
-  if (!d || !host) return 1;
-  int           nc  = (which == NIXB200_FIELD_UF) ? 6 : 4;
-  const double* src = (which == NIXB200_FIELD_UF) ? d->uf : d->uj;
-  NIX_CUDA(cudaMemcpyAsync(host, src, sizeof(double) * nc * d->cells_per_chunk * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
+  if (!host) return 1;
+  const int    nc    = (which == NIXB200_FIELD_UF) ? 6 : 4;
+  const size_t bytes = sizeof(double) * nc * d->cells_per_chunk;
+  if (d->fp32) {
+    for (int k = 0; k < d->geo.nchunk; k++) {
+      if (chunk_convert(d, which, k, false)) return 1;
+      NIX_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(host) + (size_t)k * bytes, d->halo_buf, bytes, cudaMemcpyDeviceToHost, d->stream));
+    }
+    return 0;
+  }
+  NIX_CUDA(cudaMemcpyAsync(host, chunk_array(d, which, 0), bytes * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
   return 0;
 }
 
@@ -637,18 +702,26 @@ static int field_copy_overlapped(Domain* d, int which, double* host, bool upload
   const Geo&   g     = d->geo;
   const size_t cells = interior ? (size_t)g.N[0] * g.N[1] * g.N[2] : d->cells_per_chunk;
   const size_t bytes = sizeof(double) * nc * cells * g.nchunk;
-  double*      full  = (w == 0) ? d->uf : d->uj;
+  double*      full  = reinterpret_cast<double*>((w == 0) ? d->uf : d->uj);
   double*      dev   = full;
+  if (d->fp32 && !interior) {
+    set_error("fp32 mode: the full-array overlapped transfers are fp64 only (use the interior variants or the per-chunk calls)");
+    return 1;
+  }
   if (interior) {
     if (!d->dense[w]) NIX_CUDA(cudaMalloc(&d->dense[w], bytes));
     dev = d->dense[w];
   }
+  auto interior_kernel = [&](bool pack) {
+    if (d->fp32) return launch_interior_f32(pack, reinterpret_cast<float*>(full), dev, g, nc, (w == 0) ? d->fcs : 4, d->copy_stream);
+    return launch_interior(pack, full, dev, g, nc, d->copy_stream);
+  };
   NIX_CUDA(cudaStreamWaitEvent(d->copy_stream, d->ev_main_done[w], 0)); // no-op before the first phase
   if (upload) {
     NIX_CUDA(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, d->copy_stream));
-    if (interior && launch_interior(false, full, dev, g, nc, d->copy_stream)) return 1;
+    if (interior && interior_kernel(false)) return 1;
   } else {
-    if (interior && launch_interior(true, full, dev, g, nc, d->copy_stream)) return 1;
+    if (interior && interior_kernel(true)) return 1;
     NIX_CUDA(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, d->copy_stream));
   }
   NIX_CUDA(cudaEventRecord(d->ev_copy_done[w], d->copy_stream));
@@ -744,9 +817,19 @@ int nixb200_domain_set_particles(nixb200_domain* dd, int is, const double* xu_ao
       set_error("null particle array");
       return 1;
     }
-    // AoS staged in the xv buffer (same byte size), transposed into xu; the source may be host or device memory
-    NIX_CUDA(cudaMemcpyAsync(s.xv, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyDefault, d->stream));
-    if (launch_aos_to_soa(s.xv, s.xu, s.cap, 0, (size_t)ntot, d->stream)) return 1;
+    if (d->fp32) {
+      // fp64 AoS staged in a scratch buffer, converted into the fp32 store (positions relative to the chunk)
+      if (aos_scratch(d, sizeof(double) * NC * ntot)) return 1;
+      NIX_CUDA(cudaMemcpyAsync(d->aos_tmp, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyDefault, d->stream));
+      const double extent[3] = {g.N[0] * g.del[0], g.N[1] * g.del[1], g.N[2] * g.del[2]};
+      if (launch_aos_to_soa_f32(d->aos_tmp, reinterpret_cast<float*>(s.xu), s.cap, 0, (size_t)ntot, s.cbase, g.nchunk,
+                                d->origin_dev, extent, d->stream))
+        return 1;
+    } else {
+      // AoS staged in the xv buffer (same byte size), transposed into xu; the source may be host or device memory
+      NIX_CUDA(cudaMemcpyAsync(s.xv, xu_aos, sizeof(double) * NC * ntot, cudaMemcpyDefault, d->stream));
+      if (launch_aos_to_soa(s.xv, s.xu, s.cap, 0, (size_t)ntot, d->stream)) return 1;
+    }
   }
   // start[] of an unsorted container: only the chunk bases are meaningful until domain_sort()
   NIX_CUDA(cudaStreamSynchronize(d->stream));
@@ -780,6 +863,15 @@ int nixb200_chunk_get_particles(nixb200_domain* dd, int k, int is, double* xu_ao
   if (n > max_np) {
     set_error("output buffer too small");
     return 1;
+  }
+  if (d->fp32) {
+    if (aos_scratch(d, sizeof(double) * NC * n)) return 1;
+    if (launch_soa_to_aos_f32(reinterpret_cast<const float*>(s.xu), d->aos_tmp, s.cap, (size_t)cb[0], (size_t)n,
+                              d->origin_dev + 3 * k, d->stream))
+      return 1;
+    NIX_CUDA(cudaMemcpyAsync(xu_aos, d->aos_tmp, sizeof(double) * NC * n, cudaMemcpyDeviceToHost, d->stream));
+    NIX_CUDA(cudaStreamSynchronize(d->stream));
+    return 0;
   }
   // xv is scratch between steps (the reference's "temporary particle array", xtensor_particle.hpp:16)
   if (launch_soa_to_aos(s.xu, s.xv, s.cap, (size_t)cb[0], (size_t)n, d->stream)) return 1;
@@ -831,7 +923,7 @@ int nixb200_domain_sort(nixb200_domain* dd)
   if (!d) return 1;
   PhaseTimer pt(d, 4);
   for (auto& s : d->sp) {
-    if (launch_count_only(d->geo, d->cg_dev, s, d->err_dev, d->stream)) return 1;
+    if (launch_count_only(d->geo, d->cg_dev, s, d->err_dev, d->stream, d->fp32)) return 1;
     if (do_sort_species(d, s)) return 1;
   }
   return record_stats(d);
@@ -842,7 +934,7 @@ int nixb200_domain_clear_current(nixb200_domain* dd)
   NIX_ENTER(dd);
   if (!d) return 1;
   if (wait_copy(d, 1)) return 1;
-  NIX_CUDA(cudaMemsetAsync(d->uj, 0, sizeof(double) * 4 * d->cells_per_chunk * d->geo.nchunk, d->stream));
+  NIX_CUDA(cudaMemsetAsync(d->uj, 0, d->esz * 4 * d->cells_per_chunk * d->geo.nchunk, d->stream));
   return 0;
 }
 
@@ -864,6 +956,7 @@ int nixb200_domain_push_deposit(nixb200_domain* dd, double delt)
     a.delt = delt;
     a.err  = d->err_dev;
     a.pusher = d->desc.pusher;
+    a.fp32   = d->fp32;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     if (d->profiling) {
       for (auto& e : ev) cudaEventCreate(&e);
@@ -885,7 +978,7 @@ int nixb200_domain_exchange_current(nixb200_domain* dd)
   {
     PhaseTimer pt(d, 1);
     if (peer_exchange_halo(d, NIXB200_MODE_CURRENT)) return 1;
-    if (launch_halo_current(d->geo, d->cg_dev, d->uj, peer_tabs(d), peer_recvbuf(d), d->stream)) return 1;
+    if (launch_halo_current(d->geo, d->cg_dev, d->uj, peer_tabs(d), peer_recvbuf(d), d->stream, d->fp32)) return 1;
   }
   return mark_main_done(d, 1);
 }
@@ -898,7 +991,7 @@ int nixb200_domain_exchange_field(nixb200_domain* dd)
   {
     PhaseTimer pt(d, 2);
     if (peer_exchange_halo(d, NIXB200_MODE_FIELD)) return 1;
-    if (launch_halo_field(d->geo, d->cg_dev, d->uf, peer_tabs(d), peer_recvbuf(d), d->stream)) return 1;
+    if (launch_halo_field(d->geo, d->cg_dev, d->uf, peer_tabs(d), peer_recvbuf(d), d->stream, d->fp32)) return 1;
   }
   return mark_main_done(d, 0);
 }
@@ -913,7 +1006,7 @@ int nixb200_domain_migrate_sort(nixb200_domain* dd)
   const PeerTabs none = peer_tabs(d);
   for (auto& s : d->sp) {
     if (launch_mig_scan(d->geo, s, d->stream)) return 1;
-    if (launch_mig_route(d->geo, d->cg_dev, s, none, d->err_dev, d->stream)) return 1;
+    if (launch_mig_route(d->geo, d->cg_dev, s, none, d->err_dev, d->stream, d->fp32)) return 1;
     if (do_sort_species(d, s)) return 1;
   }
   return record_stats(d);
@@ -935,7 +1028,7 @@ int nixb200_domain_push_bfd(nixb200_domain* dd, double delt, int ext)
   if (wait_copy(d, 0)) return 1;
   {
     PhaseTimer pt(d, 7);
-    if (launch_push_bfd(d->geo, d->uf, delt, ext, d->stream)) return 1;
+    if (launch_push_bfd(d->geo, d->uf, delt, ext, d->stream, d->fp32)) return 1;
   }
   return mark_main_done(d, 0);
 }
@@ -946,7 +1039,7 @@ int nixb200_domain_push_efd(nixb200_domain* dd, double delt, double cfj)
   if (wait_copy(d, 0) || wait_copy(d, 1)) return 1;
   {
     PhaseTimer pt(d, 7);
-    if (launch_push_efd(d->geo, d->uf, d->uj, delt, cfj, d->stream)) return 1;
+    if (launch_push_efd(d->geo, d->uf, d->uj, delt, cfj, d->stream, d->fp32)) return 1;
   }
   return mark_main_done(d, 0) || mark_main_done(d, 1);
 }
@@ -971,7 +1064,7 @@ int nixb200_domain_field_energy(nixb200_domain* dd, double* host_e2b2)
   if (!host_e2b2) return 1;
   if (wait_copy(d, 0)) return 1;
   if (!d->energy_dev) NIX_CUDA(cudaMalloc(&d->energy_dev, sizeof(double) * 2 * d->geo.nchunk));
-  if (launch_field_energy(d->geo, d->uf, d->energy_dev, d->stream)) return 1;
+  if (launch_field_energy(d->geo, d->uf, d->energy_dev, d->stream, d->fp32)) return 1;
   NIX_CUDA(cudaMemcpyAsync(host_e2b2, d->energy_dev, sizeof(double) * 2 * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   return 0;
@@ -1015,10 +1108,14 @@ int nixb200_chunk_halo_pack(nixb200_domain* dd, int k, int mode, void* host_send
 {
   NIX_ENTER(dd);
   if (check_chunk(d, k) || !host_sendbuf) return 1;
+  if (d->fp32) {
+    set_error("fp32 mode: the MpiBuffer-layout halo calls are fp64 only");
+    return 1;
+  }
   int bs[27], ba[27];
   if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
   size_t total = (size_t)ba[26] + bs[26];
-  const double* data = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
+  const double* data = reinterpret_cast<const double*>((mode == NIXB200_MODE_FIELD) ? d->uf : d->uj);
   if (launch_halo_pack(d->geo, k, mode, data, d->halo_buf, d->stream)) return 1;
   NIX_CUDA(cudaMemcpyAsync(host_sendbuf, d->halo_buf, total, cudaMemcpyDeviceToHost, d->stream));
   NIX_CUDA(cudaStreamSynchronize(d->stream));
@@ -1029,6 +1126,10 @@ int nixb200_chunk_halo_unpack(nixb200_domain* dd, int k, int mode, const void* h
 {
   NIX_ENTER(dd);
   if (check_chunk(d, k) || !host_recvbuf) return 1;
+  if (d->fp32) {
+    set_error("fp32 mode: the MpiBuffer-layout halo calls are fp64 only");
+    return 1;
+  }
   int bs[27], ba[27];
   if (nixb200_halo_layout(dd, mode, bs, ba)) return 1;
   size_t total = (size_t)ba[26] + bs[26];
@@ -1036,7 +1137,7 @@ int nixb200_chunk_halo_unpack(nixb200_domain* dd, int k, int mode, const void* h
   for (int s = 0; s < 27; s++) valid[s] = nbvalid27 ? nbvalid27[s] : 1;
   NIX_CUDA(cudaMemcpyAsync(d->nbvalid_dev, valid, sizeof(valid), cudaMemcpyHostToDevice, d->stream));
   NIX_CUDA(cudaMemcpyAsync(d->halo_buf, host_recvbuf, total, cudaMemcpyHostToDevice, d->stream));
-  double* data = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
+  double* data = reinterpret_cast<double*>((mode == NIXB200_MODE_FIELD) ? d->uf : d->uj);
   if (launch_halo_unpack(d->geo, k, mode, data, d->halo_buf, d->nbvalid_dev, d->stream)) return 1;
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   return 0;

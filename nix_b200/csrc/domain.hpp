@@ -15,10 +15,19 @@ struct Domain {
   Geo                     geo;
   std::vector<ChunkGeo>   cg_host;
   ChunkGeo*               cg_dev = nullptr;
-  double*                 uf     = nullptr;
-  double*                 uj     = nullptr;
+  void*                   uf     = nullptr; // E/B of every chunk, in the domain's real type
+  void*                   uj     = nullptr; // rho / J
   std::vector<SpeciesDev> sp;
   cudaStream_t            stream = nullptr;
+  // real type of the device-resident data: fp64 (the reference's, default) or fp32 (desc.fp32)
+  bool                    fp32 = false;
+  size_t                  esz  = 8; // bytes per real
+  int                     nct  = 7; // reals per particle in the SoA store (fp32: the 64-bit id takes two)
+  int                     fcs  = 6; // reals per E/B cell (fp32: 8, TMA strides are multiples of 16 bytes)
+  std::vector<double>     origin_host;          // [nchunk][3] lower corner (z,y,x) of every chunk
+  double*                 origin_dev = nullptr; // fp32 mode: particle positions are relative to it
+  double*                 aos_tmp    = nullptr; // fp32 mode: fp64 AoS staging of the boundary (grown on demand)
+  size_t                  aos_tmp_bytes = 0;
   bool                    owns_stream = false; // false once the caller has handed over its own stream
   bool                    has_remote  = false; // a neighbour chunk lives on another rank (needs set_ranks + comm)
   // capacity bookkeeping: after every sort the device reports, per species, (total particles, leaver
@@ -98,7 +107,7 @@ PeerTabs peer_tabs(const Domain* d);
 void     peer_destroy(Domain* d);
 int      peer_alloc_species(Domain* d, SpeciesDev& s);
 int      peer_exchange_halo(Domain* d, int mode);       // pack -> NCCL send/recv (no-op without peers)
-const double* peer_recvbuf(const Domain* d);
+const void* peer_recvbuf(const Domain* d);
 int      peer_migrate(Domain* d);                       // the whole migrate + sort phase with peers
 int      do_sort_species(Domain* d, SpeciesDev& s);
 } // namespace nixb200

@@ -23,49 +23,55 @@ namespace nixb200
 {
 namespace
 {
+template <typename T>
 struct FdtdGeo {
-  int    M[3], N[3], nb;
-  double cz, cy, cx, cj;
+  int M[3], N[3], nb;
+  T   cz, cy, cx, cj;
 };
 
-__device__ __forceinline__ double m_(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double s_(double a, double b) { return __dsub_rn(a, b); }
-__device__ __forceinline__ double a_(double a, double b) { return __dadd_rn(a, b); }
+// explicit round-to-nearest operations in the oracle's order (no contraction) in both real types
+template <typename T> __device__ __forceinline__ T m_(T a, T b) { return mul<true>(a, b); }
+template <typename T> __device__ __forceinline__ T s_(T a, T b) { return sub<true>(a, b); }
+template <typename T> __device__ __forceinline__ T a_(T a, T b) { return add<true>(a, b); }
 
 // region = [nb-ext, nb+N-1+ext] on every axis; grid.y = chunk
-__global__ void __launch_bounds__(256) k_push_bfd(FdtdGeo g, double* __restrict__ uf, int ext)
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_bfd(FdtdGeo<T> g, T* __restrict__ uf, int ext)
 {
+  constexpr int FC = field_stride<T>();
   const int    ez = g.N[0] + 2 * ext, ey = g.N[1] + 2 * ext, ex = g.N[2] + 2 * ext;
   const int    n  = ez * ey * ex;
-  const size_t sy = (size_t)g.M[2] * 6, sz = (size_t)g.M[1] * g.M[2] * 6;
-  double*      u  = uf + (size_t)blockIdx.y * g.M[0] * sz;
+  const size_t sy = (size_t)g.M[2] * FC, sz = (size_t)g.M[1] * g.M[2] * FC;
+  T*           u  = uf + (size_t)blockIdx.y * g.M[0] * sz;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int ix = t % ex + g.nb - ext, iy = (t / ex) % ey + g.nb - ext, iz = t / (ex * ey) + g.nb - ext;
-    double*   p  = u + iz * sz + iy * sy + (size_t)ix * 6;
-    const double exx = p[0], eyy = p[1], ezz = p[2];
-    const double ez_ym = p[2 - (ptrdiff_t)sy], ex_ym = p[0 - (ptrdiff_t)sy];
-    const double ey_zm = p[1 - (ptrdiff_t)sz], ex_zm = p[0 - (ptrdiff_t)sz];
-    const double ez_xm = p[2 - 6], ey_xm = p[1 - 6];
+    T*        p  = u + iz * sz + iy * sy + (size_t)ix * FC;
+    const T exx = p[0], eyy = p[1], ezz = p[2];
+    const T ez_ym = p[2 - (ptrdiff_t)sy], ex_ym = p[0 - (ptrdiff_t)sy];
+    const T ey_zm = p[1 - (ptrdiff_t)sz], ex_zm = p[0 - (ptrdiff_t)sz];
+    const T ez_xm = p[2 - FC], ey_xm = p[1 - FC];
     p[3] = s_(p[3], s_(m_(g.cy, s_(ezz, ez_ym)), m_(g.cz, s_(eyy, ey_zm))));
     p[4] = s_(p[4], s_(m_(g.cz, s_(exx, ex_zm)), m_(g.cx, s_(ezz, ez_xm))));
     p[5] = s_(p[5], s_(m_(g.cx, s_(eyy, ey_xm)), m_(g.cy, s_(exx, ex_ym))));
   }
 }
 
-__global__ void __launch_bounds__(256) k_push_efd(FdtdGeo g, double* __restrict__ uf, const double* __restrict__ uj)
+template <typename T>
+__global__ void __launch_bounds__(256) k_push_efd(FdtdGeo<T> g, T* __restrict__ uf, const T* __restrict__ uj)
 {
+  constexpr int FC = field_stride<T>();
   const int    n  = g.N[0] * g.N[1] * g.N[2];
-  const size_t sy = (size_t)g.M[2] * 6, sz = (size_t)g.M[1] * g.M[2] * 6;
-  double*      u  = uf + (size_t)blockIdx.y * g.M[0] * sz;
-  const double* j = uj + (size_t)blockIdx.y * g.M[0] * g.M[1] * g.M[2] * 4;
+  const size_t sy = (size_t)g.M[2] * FC, sz = (size_t)g.M[1] * g.M[2] * FC;
+  T*           u  = uf + (size_t)blockIdx.y * g.M[0] * sz;
+  const T*     j  = uj + (size_t)blockIdx.y * g.M[0] * g.M[1] * g.M[2] * 4;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const int ix = t % g.N[2] + g.nb, iy = (t / g.N[2]) % g.N[1] + g.nb, iz = t / (g.N[2] * g.N[1]) + g.nb;
-    double*       p  = u + iz * sz + iy * sy + (size_t)ix * 6;
-    const double* pj = j + (((size_t)iz * g.M[1] + iy) * g.M[2] + ix) * 4;
-    const double bx = p[3], by = p[4], bz = p[5];
-    const double bz_yp = p[5 + sy], bx_yp = p[3 + sy];
-    const double by_zp = p[4 + sz], bx_zp = p[3 + sz];
-    const double bz_xp = p[5 + 6], by_xp = p[4 + 6];
+    T*       p  = u + iz * sz + iy * sy + (size_t)ix * FC;
+    const T* pj = j + (((size_t)iz * g.M[1] + iy) * g.M[2] + ix) * 4;
+    const T bx = p[3], by = p[4], bz = p[5];
+    const T bz_yp = p[5 + sy], bx_yp = p[3 + sy];
+    const T by_zp = p[4 + sz], bx_zp = p[3 + sz];
+    const T bz_xp = p[5 + FC], by_xp = p[4 + FC];
     p[0] = s_(a_(p[0], s_(m_(g.cy, s_(bz_yp, bz)), m_(g.cz, s_(by_zp, by)))), m_(g.cj, pj[1]));
     p[1] = s_(a_(p[1], s_(m_(g.cz, s_(bx_zp, bx)), m_(g.cx, s_(bz_xp, bz)))), m_(g.cj, pj[2]));
     p[2] = s_(a_(p[2], s_(m_(g.cx, s_(by_xp, by)), m_(g.cy, s_(bx_yp, bx)))), m_(g.cj, pj[3]));
@@ -74,18 +80,21 @@ __global__ void __launch_bounds__(256) k_push_efd(FdtdGeo g, double* __restrict_
 
 // one block per chunk; per-thread partial sums over a fixed stride, then a fixed shared-memory tree:
 // the result does not depend on scheduling
-__global__ void __launch_bounds__(256) k_field_energy(FdtdGeo g, const double* __restrict__ uf, double* __restrict__ out)
+template <typename T>
+__global__ void __launch_bounds__(256) k_field_energy(FdtdGeo<T> g, const T* __restrict__ uf, double* __restrict__ out)
 {
+  constexpr int FC = field_stride<T>();
   __shared__ double s_e[256], s_b[256];
-  const int     n  = g.N[0] * g.N[1] * g.N[2];
-  const size_t  sy = (size_t)g.M[2] * 6, sz = (size_t)g.M[1] * g.M[2] * 6;
-  const double* u  = uf + (size_t)blockIdx.x * g.M[0] * sz;
-  double        e2 = 0.0, b2 = 0.0;
+  const int    n  = g.N[0] * g.N[1] * g.N[2];
+  const size_t sy = (size_t)g.M[2] * FC, sz = (size_t)g.M[1] * g.M[2] * FC;
+  const T*     u  = uf + (size_t)blockIdx.x * g.M[0] * sz;
+  double       e2 = 0.0, b2 = 0.0; // (the diagnostic sums in fp64 in both modes)
   for (int t = threadIdx.x; t < n; t += blockDim.x) {
-    const int     ix = t % g.N[2] + g.nb, iy = (t / g.N[2]) % g.N[1] + g.nb, iz = t / (g.N[2] * g.N[1]) + g.nb;
-    const double* p  = u + iz * sz + iy * sy + (size_t)ix * 6;
-    e2 += p[0] * p[0] + p[1] * p[1] + p[2] * p[2];
-    b2 += p[3] * p[3] + p[4] * p[4] + p[5] * p[5];
+    const int ix = t % g.N[2] + g.nb, iy = (t / g.N[2]) % g.N[1] + g.nb, iz = t / (g.N[2] * g.N[1]) + g.nb;
+    const T*  p  = u + iz * sz + iy * sy + (size_t)ix * FC;
+    const double e0 = p[0], e1 = p[1], e2_ = p[2], b0 = p[3], b1 = p[4], b2_ = p[5];
+    e2 += e0 * e0 + e1 * e1 + e2_ * e2_;
+    b2 += b0 * b0 + b1 * b1 + b2_ * b2_;
   }
   s_e[threadIdx.x] = e2;
   s_b[threadIdx.x] = b2;
@@ -103,23 +112,24 @@ __global__ void __launch_bounds__(256) k_field_energy(FdtdGeo g, const double* _
   }
 }
 
-FdtdGeo make_geo(const Geo& g, double delt, double cfj)
+template <typename T>
+FdtdGeo<T> make_geo(const Geo& g, double delt, double cfj)
 {
-  FdtdGeo f;
+  FdtdGeo<T> f;
   for (int a = 0; a < 3; a++) {
     f.M[a] = g.M[a];
     f.N[a] = g.N[a];
   }
   f.nb = g.nb;
-  f.cz = g.cc * delt / g.del[0]; // the oracle's expressions (oracle/field_solver.c)
-  f.cy = g.cc * delt / g.del[1];
-  f.cx = g.cc * delt / g.del[2];
-  f.cj = cfj * delt;
+  f.cz = (T)(g.cc * delt / g.del[0]); // the oracle's expressions (oracle/field_solver.c)
+  f.cy = (T)(g.cc * delt / g.del[1]);
+  f.cx = (T)(g.cc * delt / g.del[2]);
+  f.cj = (T)(cfj * delt);
   return f;
 }
 } // namespace
 
-int launch_push_bfd(const Geo& g, double* uf, double delt, int ext, cudaStream_t st)
+int launch_push_bfd(const Geo& g, void* uf, double delt, int ext, cudaStream_t st, bool fp32)
 {
   if (ext < 0 || ext >= g.nb) {
     set_error("push_bfd: ext must be in [0, nb)");
@@ -127,23 +137,26 @@ int launch_push_bfd(const Geo& g, double* uf, double delt, int ext, cudaStream_t
   }
   const int n = (g.N[0] + 2 * ext) * (g.N[1] + 2 * ext) * (g.N[2] + 2 * ext);
   dim3      grid((n + 255) / 256, g.nchunk);
-  k_push_bfd<<<grid, 256, 0, st>>>(make_geo(g, delt, 0.0), uf, ext);
+  if (fp32) k_push_bfd<float><<<grid, 256, 0, st>>>(make_geo<float>(g, delt, 0.0), (float*)uf, ext);
+  else k_push_bfd<double><<<grid, 256, 0, st>>>(make_geo<double>(g, delt, 0.0), (double*)uf, ext);
   NIX_LAUNCHED();
   return 0;
 }
 
-int launch_push_efd(const Geo& g, double* uf, const double* uj, double delt, double cfj, cudaStream_t st)
+int launch_push_efd(const Geo& g, void* uf, const void* uj, double delt, double cfj, cudaStream_t st, bool fp32)
 {
   const int n = g.N[0] * g.N[1] * g.N[2];
   dim3      grid((n + 255) / 256, g.nchunk);
-  k_push_efd<<<grid, 256, 0, st>>>(make_geo(g, delt, cfj), uf, uj);
+  if (fp32) k_push_efd<float><<<grid, 256, 0, st>>>(make_geo<float>(g, delt, cfj), (float*)uf, (const float*)uj);
+  else k_push_efd<double><<<grid, 256, 0, st>>>(make_geo<double>(g, delt, cfj), (double*)uf, (const double*)uj);
   NIX_LAUNCHED();
   return 0;
 }
 
-int launch_field_energy(const Geo& g, const double* uf, double* out, cudaStream_t st)
+int launch_field_energy(const Geo& g, const void* uf, double* out, cudaStream_t st, bool fp32)
 {
-  k_field_energy<<<g.nchunk, 256, 0, st>>>(make_geo(g, 0.0, 0.0), uf, out);
+  if (fp32) k_field_energy<float><<<g.nchunk, 256, 0, st>>>(make_geo<float>(g, 0.0, 0.0), (const float*)uf, out);
+  else k_field_energy<double><<<g.nchunk, 256, 0, st>>>(make_geo<double>(g, 0.0, 0.0), (const double*)uf, out);
   NIX_LAUNCHED();
   return 0;
 }

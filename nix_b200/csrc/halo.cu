@@ -61,8 +61,9 @@ __device__ __forceinline__ size_t slab_index(const Geo& g, int slot, bool recv, 
 
 // ---- exchange: same-device neighbours are read in place, neighbours on other ranks from the
 //      peer-major receive buffer (peer.cu) ----------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __restrict__ cg, double* uf, PeerTabs pt,
-                                                    const double* __restrict__ recvbuf)
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __restrict__ cg, T* uf, PeerTabs pt,
+                                                    const T* __restrict__ recvbuf)
 {
   const int ch    = blockIdx.y;
   const int ncell = g.M[0] * g.M[1] * g.M[2];
@@ -82,24 +83,28 @@ __global__ void __launch_bounds__(256) k_halo_field(Geo g, const ChunkGeo* __res
     int slot = 9 * e[0] + 3 * e[1] + e[2];
     if (slot == 13) continue;
     int nb = cg[ch].nbr[slot];
-    const double2* src;
+    // one cell = 48 bytes (6 doubles) or 32 bytes (8 floats): whole 16-byte words either way
+    constexpr int FC = field_stride<T>(), NV = FC * (int)sizeof(T) / 16;
+    const int4* src;
     if (nb >= 0) {
-      src = reinterpret_cast<const double2*>(uf + cell_off(g, nb, s[0], s[1], s[2]) * 6);
+      src = reinterpret_cast<const int4*>(uf + cell_off(g, nb, s[0], s[1], s[2]) * FC);
     } else {
       int j = (pt.recv_slot != nullptr) ? pt.recv_slot[ch * 27 + slot] : -1;
       if (j < 0) continue;
-      src = reinterpret_cast<const double2*>(recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, true, i)) * 6);
+      src = reinterpret_cast<const int4*>(recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, true, i)) * FC);
     }
-    double2*       dst = reinterpret_cast<double2*>(uf + cell_off(g, ch, iz, iy, ix) * 6);
-    double2        a = src[0], b = src[1], c = src[2];
-    dst[0] = a;
-    dst[1] = b;
-    dst[2] = c;
+    int4* dst = reinterpret_cast<int4*>(uf + cell_off(g, ch, iz, iy, ix) * FC);
+    int4  v[NV];
+#pragma unroll
+    for (int q = 0; q < NV; q++) v[q] = src[q];
+#pragma unroll
+    for (int q = 0; q < NV; q++) dst[q] = v[q];
   }
 }
 
-__global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __restrict__ cg, double* uj, PeerTabs pt,
-                                                      const double* __restrict__ recvbuf)
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __restrict__ cg, T* uj, PeerTabs pt,
+                                                      const T* __restrict__ recvbuf)
 {
   const int ch    = blockIdx.y;
   const int ncell = g.N[0] * g.N[1] * g.N[2];
@@ -119,8 +124,8 @@ __global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __r
       any     = any || lowm[a] || higm[a];
     }
     if (!any) continue;
-    double2* dst = reinterpret_cast<double2*>(uj + cell_off(g, ch, i[0], i[1], i[2]) * 4);
-    double2  v0 = dst[0], v1 = dst[1];
+    T* dst = uj + cell_off(g, ch, i[0], i[1], i[2]) * 4;
+    T  v[4] = {dst[0], dst[1], dst[2], dst[3]};
     for (int slot = 0; slot < 27; slot++) {
       if (slot == 13) continue;
       int  e[3] = {slot / 9, (slot / 3) % 3, slot % 3};
@@ -133,30 +138,28 @@ __global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __r
       }
       if (!in) continue;
       int nb = cg[ch].nbr[slot];
-      const double2* src;
+      const T* src;
       if (nb >= 0) {
-        src = reinterpret_cast<const double2*>(uj + cell_off(g, nb, s[0], s[1], s[2]) * 4);
+        src = uj + cell_off(g, nb, s[0], s[1], s[2]) * 4;
       } else {
         int j = (pt.recv_slot != nullptr) ? pt.recv_slot[ch * 27 + slot] : -1;
         if (j < 0) continue;
-        src = reinterpret_cast<const double2*>(recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, false, i)) * 4);
+        src = recvbuf + ((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, false, i)) * 4;
       }
-      double2        a = src[0], b = src[1];
       // std::plus(buffer, cell)  xtensor_halo3d.hpp:125
-      v0.x = __dadd_rn(a.x, v0.x);
-      v0.y = __dadd_rn(a.y, v0.y);
-      v1.x = __dadd_rn(b.x, v1.x);
-      v1.y = __dadd_rn(b.y, v1.y);
+#pragma unroll
+      for (int c = 0; c < 4; c++) v[c] = add<true>(src[c], v[c]);
     }
-    dst[0] = v0;
-    dst[1] = v1;
+#pragma unroll
+    for (int c = 0; c < 4; c++) dst[c] = v[c];
   }
 }
 
 // every slab bound for another rank -> the peer-major send buffer.  Field: SEND slabs (interior);
 // current: RECV slabs (ghost, where the deposit spilled).  blockIdx.y = send entry.
-__global__ void __launch_bounds__(256) k_peer_pack(Geo g, int ncomp, bool recv_slab, const double* __restrict__ data,
-                                                   const PeerEntry* __restrict__ ent, double* __restrict__ buf)
+template <typename T>
+__global__ void __launch_bounds__(256) k_peer_pack(Geo g, int ncomp, bool recv_slab, const T* __restrict__ data,
+                                                   const PeerEntry* __restrict__ ent, T* __restrict__ buf)
 {
   const PeerEntry en = ent[blockIdx.y];
   int             lo[3], n[3];
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(256) k_peer_pack(Geo g, int ncomp, bool recv_s
   slab_bounds(g, 1, (en.dir / 3) % 3, recv_slab, lo[1], n[1]);
   slab_bounds(g, 2, en.dir % 3, recv_slab, lo[2], n[2]);
   const int total = en.cells * ncomp;
-  double*   dst   = buf + (size_t)en.celloff * ncomp;
+  T*        dst   = buf + (size_t)en.celloff * ncomp;
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
     int c  = t % ncomp;
     int r  = t / ncomp;
@@ -273,34 +276,40 @@ SlotTable make_table(const Geo& g, int ncomp)
 }
 } // namespace
 
-int launch_halo_field(const Geo& g, const ChunkGeo* cg, double* uf, const PeerTabs& pt, const double* recvbuf,
-                      cudaStream_t st)
+int launch_halo_field(const Geo& g, const ChunkGeo* cg, void* uf, const PeerTabs& pt, const void* recvbuf,
+                      cudaStream_t st, bool fp32)
 {
   int  ncell = g.M[0] * g.M[1] * g.M[2];
   dim3 grid((ncell + 255) / 256, g.nchunk);
-  k_halo_field<<<grid, 256, 0, st>>>(g, cg, uf, pt, recvbuf);
+  if (fp32) k_halo_field<float><<<grid, 256, 0, st>>>(g, cg, (float*)uf, pt, (const float*)recvbuf);
+  else k_halo_field<double><<<grid, 256, 0, st>>>(g, cg, (double*)uf, pt, (const double*)recvbuf);
   NIX_LAUNCHED();
   return 0;
 }
 
-int launch_halo_current(const Geo& g, const ChunkGeo* cg, double* uj, const PeerTabs& pt, const double* recvbuf,
-                        cudaStream_t st)
+int launch_halo_current(const Geo& g, const ChunkGeo* cg, void* uj, const PeerTabs& pt, const void* recvbuf,
+                        cudaStream_t st, bool fp32)
 {
   int  ncell = g.N[0] * g.N[1] * g.N[2];
   dim3 grid((ncell + 255) / 256, g.nchunk);
-  k_halo_current<<<grid, 256, 0, st>>>(g, cg, uj, pt, recvbuf);
+  if (fp32) k_halo_current<float><<<grid, 256, 0, st>>>(g, cg, (float*)uj, pt, (const float*)recvbuf);
+  else k_halo_current<double><<<grid, 256, 0, st>>>(g, cg, (double*)uj, pt, (const double*)recvbuf);
   NIX_LAUNCHED();
   return 0;
 }
 
-int launch_peer_pack(const Geo& g, int mode, const double* data, const PeerTabs& pt, double* sendbuf,
-                     cudaStream_t st)
+// words per cell in the peer buffers: the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4)
+int launch_peer_pack(const Geo& g, int mode, const void* data, const PeerTabs& pt, void* sendbuf,
+                     cudaStream_t st, bool fp32)
 {
   if (pt.nsend == 0) return 0;
-  const int ncomp = (mode == NIXB200_MODE_FIELD) ? 6 : 4;
+  const int ncomp = (mode == NIXB200_MODE_FIELD) ? (fp32 ? 8 : 6) : 4;
   int       big   = g.nb * std::max(g.N[0], std::max(g.N[1], g.N[2])) * std::max(g.N[1], g.N[2]) * ncomp;
   dim3      grid(std::min(8, (big + 255) / 256), pt.nsend);
-  k_peer_pack<<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, data, pt.send_ent, sendbuf);
+  if (fp32)
+    k_peer_pack<float><<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, (const float*)data, pt.send_ent, (float*)sendbuf);
+  else
+    k_peer_pack<double><<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, (const double*)data, pt.send_ent, (double*)sendbuf);
   NIX_LAUNCHED();
   return 0;
 }

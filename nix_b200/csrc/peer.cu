@@ -231,7 +231,7 @@ PeerTabs peer_tabs(const Domain* d)
   return t;
 }
 
-const double* peer_recvbuf(const Domain* d)
+const void* peer_recvbuf(const Domain* d)
 {
   return d->peer ? d->peer->hrecv : nullptr;
 }
@@ -265,8 +265,8 @@ int peer_alloc_species(Domain* d, SpeciesDev& s)
   if (s.ptab) cudaFree(s.ptab);
   s.paysend = s.payrecv = nullptr;
   s.ptab               = nullptr;
-  NIX_CUDA(cudaMalloc(&s.paysend, sizeof(double) * NC * s.lcap));
-  NIX_CUDA(cudaMalloc(&s.payrecv, sizeof(double) * NC * s.lcap));
+  NIX_CUDA(cudaMalloc(&s.paysend, d->esz * d->nct * s.lcap));
+  NIX_CUDA(cudaMalloc(&s.payrecv, d->esz * d->nct * s.lcap));
   NIX_CUDA(cudaMalloc(&s.ptab, sizeof(int32_t) * ptab_ints(c)));
   NIX_CUDA(cudaMemset(s.ptab, 0, sizeof(int32_t) * ptab_ints(c)));
   return 0;
@@ -281,16 +281,19 @@ int peer_exchange_halo(Domain* d, int mode)
     set_error("neighbours on other ranks but no communicator: call nixb200_domain_comm_init first");
     return 1;
   }
-  const int     ncomp = (mode == NIXB200_MODE_FIELD) ? 6 : 4;
-  const double* data  = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
-  if (launch_peer_pack(d->geo, mode, data, peer_tabs(d), c->hsend, d->stream)) return 1;
-  Nccl* n = nccl();
+  // bytes per cell in the peer buffers = the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4 reals)
+  const size_t cellb = ((mode == NIXB200_MODE_FIELD) ? d->fcs : 4) * d->esz;
+  const void*  data  = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
+  if (launch_peer_pack(d->geo, mode, data, peer_tabs(d), c->hsend, d->stream, d->fp32)) return 1;
+  Nccl* n  = nccl();
+  char* hs = reinterpret_cast<char*>(c->hsend);
+  char* hr = reinterpret_cast<char*>(c->hrecv);
   NIX_NCCL(n->GroupStart());
   for (size_t q = 0; q < c->plan->peers.size(); q++) {
     const int64_t s0 = c->send_cell_first[q], s1 = c->send_cell_first[q + 1];
     const int64_t r0 = c->recv_cell_first[q], r1 = c->recv_cell_first[q + 1];
-    NIX_NCCL(n->Send(c->hsend + s0 * ncomp, (size_t)(s1 - s0) * ncomp, ncclDouble, c->plan->peers[q], c->comm, d->stream));
-    NIX_NCCL(n->Recv(c->hrecv + r0 * ncomp, (size_t)(r1 - r0) * ncomp, ncclDouble, c->plan->peers[q], c->comm, d->stream));
+    NIX_NCCL(n->Send(hs + s0 * cellb, (size_t)(s1 - s0) * cellb, ncclChar, c->plan->peers[q], c->comm, d->stream));
+    NIX_NCCL(n->Recv(hr + r0 * cellb, (size_t)(r1 - r0) * cellb, ncclChar, c->plan->peers[q], c->comm, d->stream));
   }
   NIX_NCCL(n->GroupEnd());
   return 0;
@@ -362,7 +365,7 @@ int peer_migrate(Domain* d)
     c->last_sent += nsent[is];
     c->last_received += nrecvd[is];
     NIX_CUDA(cudaMemcpyAsync(d->sp[is].ptab, tab, sizeof(int32_t) * tabn, cudaMemcpyHostToDevice, d->stream));
-    if (launch_mig_route(g, d->cg_dev, d->sp[is], pt, d->err_dev, d->stream)) return 1;
+    if (launch_mig_route(g, d->cg_dev, d->sp[is], pt, d->err_dev, d->stream, d->fp32)) return 1;
   }
   // 4. payloads: one message per (peer, species)
   if (remote) {
@@ -374,17 +377,18 @@ int peer_migrate(Domain* d)
       for (size_t q = 0; q < c->plan->peers.size(); q++) {
         const int64_t s0 = spoff[c->plan->send_first[q]], s1 = spoff[c->plan->send_first[q + 1]];
         const int64_t r0 = rpoff[c->plan->recv_first[q]], r1 = rpoff[c->plan->recv_first[q + 1]];
+        const size_t pb = d->esz * d->nct; // bytes per particle (56 in fp64, xtensor_halo3d.hpp:259; 32 in fp32)
         if (s1 > s0)
-          NIX_NCCL(n->Send(d->sp[is].paysend + s0 * NC, (size_t)(s1 - s0) * NC, ncclDouble, c->plan->peers[q], c->comm, d->stream));
+          NIX_NCCL(n->Send(reinterpret_cast<char*>(d->sp[is].paysend) + s0 * pb, (size_t)(s1 - s0) * pb, ncclChar, c->plan->peers[q], c->comm, d->stream));
         if (r1 > r0)
-          NIX_NCCL(n->Recv(d->sp[is].payrecv + r0 * NC, (size_t)(r1 - r0) * NC, ncclDouble, c->plan->peers[q], c->comm, d->stream));
+          NIX_NCCL(n->Recv(reinterpret_cast<char*>(d->sp[is].payrecv) + r0 * pb, (size_t)(r1 - r0) * pb, ncclChar, c->plan->peers[q], c->comm, d->stream));
       }
     }
     NIX_NCCL(n->GroupEnd());
   }
   // 5. append what arrived, then count + sort
   for (int is = 0; is < ns; is++) {
-    if (launch_mig_recv(g, d->cg_dev, d->sp[is], pt, (int)nrecvd[is], d->err_dev, d->stream)) return 1;
+    if (launch_mig_recv(g, d->cg_dev, d->sp[is], pt, (int)nrecvd[is], d->err_dev, d->stream, d->fp32)) return 1;
     if (do_sort_species(d, d->sp[is])) return 1;
   }
   return 0;

@@ -60,8 +60,10 @@ namespace
 #ifndef NIX_MOV_FLUSH
 #define NIX_MOV_FLUSH NIX_MAXMOV // flush whole groups of XGROUP records: the expansion and face-node lanes stay busy
 #endif
-constexpr int MAXMOV  = NIX_MAXMOV; // compact mover records per warp (old + new position, bin: 64 bytes each)
-constexpr int CREC    = 8;  // doubles per compact record
+constexpr int MAXMOV  = NIX_MAXMOV; // compact mover records per warp (old + new position, bin)
+template <typename T>
+constexpr int crec_len() { return 6 + 4 * (int)sizeof(int) / (int)sizeof(T); } // reals per compact record: old + new position, 4 ints
+#define CREC (crec_len<T>())
 constexpr int XGROUP  = 10; // movers expanded to full 1-D weight records at a time (3 axes x 10 = 30 lanes)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int PF_DOUBLES_W = 6 * 32; // one cp.async staging stage: 6 components x 32 lanes (a lane fills its own slots)
@@ -105,7 +107,8 @@ struct Cfg {
   static constexpr int PADX = !NIX_TILE_PAD ? 0 : (O == 2 ? 1 : 0), PADY = !NIX_TILE_PAD ? 0 : (O == 2 ? 3 : (O == 3 ? 2 : 0));
   static constexpr int EZ = TZ + NW - 1, EY = TY + NW - 1 + PADY, EX = TX + NW - 1 + PADX;
   static constexpr int JZ = TZ + NS - 1, JY = TY + NS - 1, JX = TX + NS - 1; // J tile
-  static constexpr int EB_DOUBLES  = (EZ * EY * EX * 6 + 15) / 16 * 16;
+  template <typename T>
+  static constexpr int eb_len() { return (EZ * EY * EX * field_stride<T>() + 15) / 16 * 16; } // staged E/B tile, in T
   // J tile, component-major: s_j[comp * JC + node] -- lanes that add the same component of neighbouring
   // nodes hit neighbouring banks (node-major [node][4] puts them 32 bytes apart: 4-way conflicts)
   static constexpr int JN = JZ * JY * JX, JC = (JN + 7) / 8 * 8 + 2;
@@ -151,9 +154,11 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tmap, 
       : "memory");
 }
 
-__device__ __forceinline__ void cp_async8(void* dst, const void* src)
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* dst, const T* src)
 {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  if constexpr (sizeof(T) == 8) asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+  else asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit()
 {
@@ -165,31 +170,31 @@ __device__ __forceinline__ void cp_async_wait_all()
 }
 
 // ---- shape functions (primitives.hpp:257-298), association order preserved ----------------------
-template <int O, bool S>
-__device__ __forceinline__ void shape_mc(double x, double X, double rdx, double* s)
+template <int O, bool S, typename T>
+__device__ __forceinline__ void shape_mc(T x, T X, T rdx, T* s)
 {
-  double delta = mul<S>(sub<S>(x, X), rdx);
+  T delta = mul<S>(sub<S>(x, X), rdx);
   if constexpr (O == 1) {
-    s[0] = sub<S>(1.0, delta);
+    s[0] = sub<S>(T(1.0), delta);
     s[1] = delta;
   } else if constexpr (O == 2) {
-    double w0 = delta;
-    double w1 = sub<S>(0.5, w0);
-    double w2 = add<S>(0.5, w0);
-    s[0]      = mul<S>(mul<S>(0.50, w1), w1);
-    s[1]      = sub<S>(0.75, mul<S>(w0, w0));
-    s[2]      = mul<S>(mul<S>(0.50, w2), w2);
+    T w0 = delta;
+    T w1 = sub<S>(T(0.5), w0);
+    T w2 = add<S>(T(0.5), w0);
+    s[0]      = mul<S>(mul<S>(T(0.50), w1), w1);
+    s[1]      = sub<S>(T(0.75), mul<S>(w0, w0));
+    s[2]      = mul<S>(mul<S>(T(0.50), w2), w2);
   } else {
-    const double a  = 1 / 6.0;
-    double       w1 = delta;
-    double       w2 = sub<S>(1.0, delta);
-    double       w1_pow2 = mul<S>(w1, w1);
-    double       w2_pow2 = mul<S>(w2, w2);
-    double       w1_pow3 = mul<S>(w1_pow2, w1);
-    double       w2_pow3 = mul<S>(w2_pow2, w2);
+    const T a  = 1 / T(6.0);
+    T       w1 = delta;
+    T       w2 = sub<S>(T(1.0), delta);
+    T       w1_pow2 = mul<S>(w1, w1);
+    T       w2_pow2 = mul<S>(w2, w2);
+    T       w1_pow3 = mul<S>(w1_pow2, w1);
+    T       w2_pow3 = mul<S>(w2_pow2, w2);
     s[0] = mul<S>(a, w2_pow3);
-    s[1] = mul<S>(a, add<S>(sub<S>(4.0, mul<S>(6.0, w1_pow2)), mul<S>(3.0, w1_pow3)));
-    s[2] = mul<S>(a, add<S>(sub<S>(4.0, mul<S>(6.0, w2_pow2)), mul<S>(3.0, w2_pow3)));
+    s[1] = mul<S>(a, add<S>(sub<S>(T(4.0), mul<S>(T(6.0), w1_pow2)), mul<S>(T(3.0), w1_pow3)));
+    s[2] = mul<S>(a, add<S>(sub<S>(T(4.0), mul<S>(T(6.0), w2_pow2)), mul<S>(T(3.0), w2_pow3)));
     s[3] = mul<S>(a, w1_pow3);
   }
 }
@@ -197,21 +202,21 @@ __device__ __forceinline__ void shape_mc(double x, double X, double rdx, double*
 // One field component gathered over its exact support (interp3d_impl_sorted, interp.hpp:95-113:
 // same nesting and summation order; the reference's extra stencil slot carries a zero weight).
 // e points at the first support node of the component; sy / sz = row / plane strides in doubles.
-template <int O, bool S>
-__device__ __forceinline__ double gather1(const double* __restrict__ e, const double* wz, const double* wy,
-                                          const double* wx)
+template <int O, bool S, typename T>
+__device__ __forceinline__ T gather1(const T* __restrict__ e, const T* wz, const T* wy,
+                                          const T* wx)
 {
-  constexpr int sy = Cfg<O>::EX * 6, sz = Cfg<O>::EY * Cfg<O>::EX * 6;
-  double        rz = 0.0;
+  constexpr int FC = field_stride<T>(), sy = Cfg<O>::EX * FC, sz = Cfg<O>::EY * Cfg<O>::EX * FC;
+  T        rz = T(0.0);
 #pragma unroll
   for (int jz = 0; jz <= O; jz++) {
-    double ry = 0.0;
+    T ry = T(0.0);
 #pragma unroll
     for (int jy = 0; jy <= O; jy++) {
-      double        rx = 0.0;
-      const double* p  = e + jz * sz + jy * sy;
+      T        rx = T(0.0);
+      const T* p  = e + jz * sz + jy * sy;
 #pragma unroll
-      for (int jx = 0; jx <= O; jx++) rx = mad<S>(p[jx * 6], wx[jx], rx);
+      for (int jx = 0; jx <= O; jx++) rx = mad<S>(p[jx * FC], wx[jx], rx);
       ry = mad<S>(rx, wy[jy], ry);
     }
     rz = mad<S>(ry, wz[jz], rz);
@@ -219,22 +224,28 @@ __device__ __forceinline__ double gather1(const double* __restrict__ e, const do
   return rz;
 }
 
-struct Kparams {
+// kernel parameters; every real-valued constant is already in the kernel's real type T, so that no
+// fp64 operand sneaks into an fp32 instantiation
+template <typename T>
+struct KparamsT {
   Geo             geo;
   const ChunkGeo* cg;
-  double*         uj;
-  SpeciesDev      sp;
-  double          delt, dt1, q;
-  double          qdxdt[3]; // q * del/dt per axis (z,y,x)
+  T*              uj;
+  T*              xu; // [NCT][cap]
+  T*              xv;
+  SpeciesDev      sp; // (integer tables; its xu / xv are untyped bytes)
+  T               delt, dt1, q;
+  T               qdxdt[3]; // q * del/dt per axis (z,y,x)
+  T               del[3], rdel[3], cc, rc;
   int*            err;
   int             pusher;   // NIXB200_PUSH_*
 };
 
 // 1-D deposit weights of one particle on the central slots 1..N1 of the (O+3) mesh, per axis (z,y,x):
 // S0 = old weights, DS = new - old, CP[j] = sum of DS over slots < j (esirkepov.hpp:167-174)
-template <int O>
+template <int O, typename T>
 struct Wts {
-  double s0[3][O + 1], ds[3][O + 1], cp[3][O + 1];
+  T s0[3][O + 1], ds[3][O + 1], cp[3][O + 1];
 };
 
 // Esirkepov current of one particle on ONE z-plane of the central mesh, added into acc[PV]:
@@ -245,63 +256,64 @@ struct Wts {
 // ty / tx = axis records of y / x: S0[N1] DS[N1] CP[1..N1-1].  cpz is zero on plane 0 (structural
 // zero of the register set; the first face of a low-side mover is added by the mover path) and all
 // three z weights are zero on an idle lane, which then adds exact zeros.
-template <int O>
-__device__ __forceinline__ void plane_accumulate(const double s0z, const double dsz, const double cpz,
-                                                 const double* ty, const double* tx, const double q,
-                                                 const double* qd, double* acc)
+template <int O, typename T>
+__device__ __forceinline__ void plane_accumulate(const T s0z, const T dsz, const T cpz,
+                                                 const T* ty, const T* tx, const T q,
+                                                 const T* qd, T* acc)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1;
-  const double  A = 1.0 / 2, B = 1.0 / 3;
-  const double  qs1z = q * (s0z + dsz);
-  const double  azy = -qd[1] * (s0z + A * dsz), bzy = -qd[1] * (A * s0z + B * dsz);
-  const double  fz  = -qd[0] * cpz;
+  const T  A = T(1.0) / 2, B = T(1.0) / 3;
+  const T  qs1z = q * (s0z + dsz);
+  const T  azy = -qd[1] * (s0z + A * dsz), bzy = -qd[1] * (A * s0z + B * dsz);
+  const T  fz  = -qd[0] * cpz;
 #pragma unroll
   for (int jy = 0; jy < N1; jy++) {
-    const double s0y = ty[jy], dsy = ty[N1 + jy];
-    const double ar  = qs1z * (s0y + dsy);
-    const double wx  = -qd[2] * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
+    const T s0y = ty[jy], dsy = ty[N1 + jy];
+    const T ar  = qs1z * (s0y + dsy);
+    const T wx  = -qd[2] * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
 #pragma unroll
     for (int jx = 0; jx < N1; jx++) {
-      const double s0x = tx[jx], dsx = tx[N1 + jx];
+      const T s0x = tx[jx], dsx = tx[N1 + jx];
       acc[C::P_RHO + jy * N1 + jx] = fma(ar, s0x + dsx, acc[C::P_RHO + jy * N1 + jx]);
       if (jx >= 1)
         acc[C::P_JX + jy * (N1 - 1) + jx - 1] = fma(wx, tx[2 * N1 + jx - 1], acc[C::P_JX + jy * (N1 - 1) + jx - 1]);
       if (jy >= 1) {
-        const double wy = azy * s0x + bzy * dsx;
+        const T wy = azy * s0x + bzy * dsx;
         acc[C::P_JY + (jy - 1) * N1 + jx] = fma(wy, ty[2 * N1 + jy - 1], acc[C::P_JY + (jy - 1) * N1 + jx]);
       }
-      const double wz = (s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy;
+      const T wz = (s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy;
       acc[C::P_JZ + jy * N1 + jx] = fma(fz, wz, acc[C::P_JZ + jy * N1 + jx]);
     }
   }
 }
 
 // One deposit round: lane = (slot ps, plane pl) adds plane pl of particle p = first + ps to acc.
-template <int O>
-__device__ __forceinline__ void deposit_round(const double* wq, int p, int plc, bool pl_on, const double q,
-                                              const double* qd, double* acc)
+template <int O, typename T>
+__device__ __forceinline__ void deposit_round(const T* wq, int p, int plc, bool pl_on, const T q,
+                                              const T* qd, T* acc)
 {
   using C           = Cfg<O>;
   constexpr int NPR = C::NPR;
-  const double2* q2 = reinterpret_cast<const double2*>(wq);
-  double         ty[2 * NPR], tx[2 * NPR];
+  using R2 = typename Real<T>::vec2;
+  const R2* q2 = reinterpret_cast<const R2*>(wq);
+  T         ty[2 * NPR], tx[2 * NPR];
 #pragma unroll
   for (int pr = 0; pr < NPR; pr++) {
-    const double2 a = q2[pr * 32 + p], b = q2[(NPR + pr) * 32 + p];
+    const R2 a = q2[pr * 32 + p], b = q2[(NPR + pr) * 32 + p];
     ty[2 * pr] = a.x, ty[2 * pr + 1] = a.y;
     tx[2 * pr] = b.x, tx[2 * pr + 1] = b.y;
   }
-  const double2 z2 = q2[C::WQ_Z / 2 + plc * C::ZP + p];
-  const double  zc = wq[C::WQ_ZC + (plc >= 1 ? plc - 1 : 0) * C::ZP + p];
-  const double  s0z = pl_on ? z2.x : 0.0, dsz = pl_on ? z2.y : 0.0, cpz = (pl_on && plc >= 1) ? zc : 0.0;
-  plane_accumulate<O>(s0z, dsz, cpz, ty, tx, q, qd, acc);
+  const R2 z2 = q2[C::WQ_Z / 2 + plc * C::ZP + p];
+  const T  zc = wq[C::WQ_ZC + (plc >= 1 ? plc - 1 : 0) * C::ZP + p];
+  const T  s0z = pl_on ? z2.x : T(0.0), dsz = pl_on ? z2.y : T(0.0), cpz = (pl_on && plc >= 1) ? zc : T(0.0);
+  plane_accumulate<O, T>(s0z, dsz, cpz, ty, tx, q, qd, acc);
 }
 
 // N independent fp64 additions to shared memory.  fp64 shared-memory atomics are compare-and-swap
 // loops; running the N loops of a lane in lock step overlaps their round trips.
-template <int N>
-__device__ __forceinline__ void atomic_add_batch(double* const* ad, const double* val, bool* todo)
+template <int N, typename T>
+__device__ __forceinline__ void atomic_add_batch(T* const* ad, const T* val, bool* todo)
 {
 #if !NIX_BATCH_CAS
 #pragma unroll
@@ -330,9 +342,9 @@ __device__ __forceinline__ void atomic_add_batch(double* const* ad, const double
 
 // Add the extra values (outside the register-resident set) of up to XGROUP expanded mover records
 // (per axis z,y,x: S0[NS] DS[NS] CP[NS], then cellbase and mover code) to the J tile.
-template <int O>
-__device__ __forceinline__ void flush_group(double* s_j, const double* myrec, int* myml, int nrec, double q,
-                                            double qdz, double qdy, double qdx)
+template <int O, typename T>
+__device__ __forceinline__ void flush_group(T* s_j, const T* myrec, int* myml, int nrec, T q,
+                                            T qdz, T qdy, T qdx)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1, NS = C::NS, JY = C::JY, JX = C::JX;
@@ -345,11 +357,11 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
   const int      nsingle = __popc(single);
   if (lane < nrec && mycode >= 0) myml[__popc(single & ((1u << lane) - 1))] = lane;
   __syncwarp();
-  const double A = 1.0 / 2, B = 1.0 / 3;
-  auto         node = [&](const double* r, int jz, int jy, int jx, double& rho, double& wx, double& wy, double& wz) {
-    const double s0z = r[0 * NS + jz], dsz = r[1 * NS + jz];
-    const double s0y = r[3 * NS + jy], dsy = r[4 * NS + jy];
-    const double s0x = r[6 * NS + jx], dsx = r[7 * NS + jx];
+  const T A = T(1.0) / 2, B = T(1.0) / 3;
+  auto         node = [&](const T* r, int jz, int jy, int jx, T& rho, T& wx, T& wy, T& wz) {
+    const T s0z = r[0 * NS + jz], dsz = r[1 * NS + jz];
+    const T s0y = r[3 * NS + jy], dsy = r[4 * NS + jy];
+    const T s0x = r[6 * NS + jx], dsx = r[7 * NS + jx];
     rho = q * (s0z + dsz) * (s0y + dsy) * (s0x + dsx);
     wx  = -qdx * ((s0y + A * dsy) * s0z + (A * s0y + B * dsy) * dsz);
     wy  = -qdy * ((s0z + A * dsz) * s0x + (A * s0z + B * dsz) * dsx);
@@ -360,7 +372,7 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
     if (gi < nsingle * N1 * N1) {
       const int     m  = myml[gi / (N1 * N1)];
       const int     uv = gi % (N1 * N1);
-      const double* r  = myrec + m * C::REC;
+      const T* r  = myrec + m * C::REC;
       const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
       const int     cbase = ri[0], ax = ri[1] >> 1, o = (ri[1] & 1) ? NS - 1 : 0;
       // mesh slots z,y,x: the moving axis sits on its outer slot, the two in-plane axes (ascending
@@ -369,46 +381,47 @@ __device__ __forceinline__ void flush_group(double* s_j, const double* myrec, in
       const int jz = (ax == 0) ? o : u;
       const int jy = (ax == 1) ? o : ((ax == 0) ? u : v);
       const int jx = (ax == 2) ? o : v;
-      double    rho, wx, wy, wz;
+      T    rho, wx, wy, wz;
       node(r, jz, jy, jx, rho, wx, wy, wz);
-      double*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
-      const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+      T*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
+      const T vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
       // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
       const int     st = (ax == 0) ? JY * JX : ((ax == 1) ? JX : 1);
-      const double  w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
-      double* const ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
-      const double  val[5]  = {rho, vx, vy, vz, w1};
-      bool          todo[5] = {rho != 0.0, vx != 0.0, vy != 0.0, vz != 0.0, o == 0 && w1 != 0.0};
-      atomic_add_batch<5>(ad, val, todo);
+      const T  w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
+      T* const ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
+      const T  val[5]  = {rho, vx, vy, vz, w1};
+      bool          todo[5] = {rho != T(0.0), vx != T(0.0), vy != T(0.0), vz != T(0.0), o == 0 && w1 != T(0.0)};
+      atomic_add_batch<5, T>(ad, val, todo);
     }
   }
   // multi-axis movers: the whole (O+3)^3 mesh minus what the register path already holds
   while (multi) {
     const int m = __ffs(multi) - 1;
     multi &= multi - 1;
-    const double* r  = myrec + m * C::REC;
+    const T* r  = myrec + m * C::REC;
     const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
     const int cbase = ri[0];
     for (int n = lane; n < NS * NS * NS; n += 32) {
       const int  jz = n / (NS * NS), jy = (n / NS) % NS, jx = n % NS;
       const bool central = jz >= 1 && jz <= N1 && jy >= 1 && jy <= N1 && jx >= 1 && jx <= N1;
-      double     rho, wx, wy, wz;
+      T     rho, wx, wy, wz;
       node(r, jz, jy, jx, rho, wx, wy, wz);
-      double*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
-      const double vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
-      if (!central && rho != 0.0) atomicAdd(dst, rho);
-      if (!(central && jx >= 2) && vx != 0.0) atomicAdd(dst + C::JC, vx);
-      if (!(central && jy >= 2) && vy != 0.0) atomicAdd(dst + 2 * C::JC, vy);
-      if (!(central && jz >= 2) && vz != 0.0) atomicAdd(dst + 3 * C::JC, vz);
+      T*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
+      const T vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+      if (!central && rho != T(0.0)) atomicAdd(dst, rho);
+      if (!(central && jx >= 2) && vx != T(0.0)) atomicAdd(dst + C::JC, vx);
+      if (!(central && jy >= 2) && vy != T(0.0)) atomicAdd(dst + 2 * C::JC, vy);
+      if (!(central && jz >= 2) && vz != T(0.0)) atomicAdd(dst + 3 * C::JC, vz);
     }
   }
   __syncwarp();
 }
 
 
-struct MoverGeo { // what the expansion needs of the geometry, by value (no param-space pointers)
-  double del[3], rdel[3];
-  int    is_odd;
+template <typename T>
+struct MoverGeoT { // what the expansion needs of the geometry, by value (no param-space pointers)
+  T   del[3], rdel[3];
+  int is_odd;
 };
 
 // Flush the compact mover records of one warp: XGROUP at a time, lanes = (mover, axis) recompute the
@@ -417,9 +430,9 @@ struct MoverGeo { // what the expansion needs of the geometry, by value (no para
 // DS and its running sum CP, esirkepov.hpp:167-174) into the warp's reduction scratch, then
 // flush_group adds the values outside the register-resident set.  Kept out of line: it runs once per
 // ~20 movers.
-template <int O, bool S>
-__device__ __noinline__ void flush_movers(double* s_j, const double* crec, double* xrec, int* myml, int nrec,
-                                          const ChunkGeo* c, MoverGeo mg, double q, double qdz, double qdy, double qdx)
+template <int O, bool S, typename T>
+__device__ __noinline__ void flush_movers(T* s_j, const T* crec, T* xrec, int* myml, int nrec,
+                                          const ChunkGeoT<T>* c, MoverGeoT<T> mg, T q, T qdz, T qdy, T qdx)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1, NS = C::NS;
@@ -430,26 +443,26 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* crec, doubl
     __syncwarp();
     if (lane < 3 * ng) {
       const int     m = lane / 3, a = lane - 3 * m;
-      const double* cr = crec + (size_t)(m0 + m) * CREC;
+      const T* cr = crec + (size_t)(m0 + m) * CREC;
       const int*    ci = reinterpret_cast<const int*>(cr + 6);
-      const double  xo = cr[a], xn = cr[3 + a];
+      const T  xo = cr[a], xn = cr[3 + a];
       const int     bin = (a == 0) ? ci[2] : ((a == 1) ? (ci[3] & 0xffff) : (ci[3] >> 16));
       const int     ki = bin - mg.is_odd;
       const int     k1 = digitize(xn, c->off[a], mg.rdel[a]) - mg.is_odd;
       const int     sft = k1 - ki;
-      double        wi[N1], wn[N1];
-      shape_mc<O, S>(xo, add<S>(c->imin[a], mul<S>((double)ki, mg.del[a])), mg.rdel[a], wi);
-      shape_mc<O, S>(xn, add<S>(c->imin[a], mul<S>((double)k1, mg.del[a])), mg.rdel[a], wn);
-      double* r  = xrec + m * C::REC + 3 * a * NS;
-      double  cp = 0.0;
+      T        wi[N1], wn[N1];
+      shape_mc<O, S, T>(xo, add<S>(c->imin[a], mul<S>((T)ki, mg.del[a])), mg.rdel[a], wi);
+      shape_mc<O, S, T>(xn, add<S>(c->imin[a], mul<S>((T)k1, mg.del[a])), mg.rdel[a], wn);
+      T* r  = xrec + m * C::REC + 3 * a * NS;
+      T  cp = T(0.0);
 #pragma unroll
       for (int j = 0; j < NS; j++) {
-        const double s0 = (j >= 1 && j <= O + 1) ? wi[j - 1] : 0.0;
-        const double vm = (j >= 0 && j <= O) ? wn[j] : 0.0;         // shift -1: slot j <- wn[j]
-        const double v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : 0.0; // shift  0
-        const double vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : 0.0; // shift +1
-        const double s1 = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
-        const double ds = s1 - s0;
+        const T s0 = (j >= 1 && j <= O + 1) ? wi[j - 1] : T(0.0);
+        const T vm = (j >= 0 && j <= O) ? wn[j] : T(0.0);         // shift -1: slot j <- wn[j]
+        const T v0 = (j >= 1 && j <= O + 1) ? wn[j - 1] : T(0.0); // shift  0
+        const T vp = (j >= 2 && j <= O + 2) ? wn[j - 2] : T(0.0); // shift +1
+        const T s1 = (sft == 0) ? v0 : ((sft < 0) ? vm : vp);
+        const T ds = s1 - s0;
         r[j]            = s0;
         r[NS + j]       = ds;
         r[2 * NS + j]   = cp;
@@ -462,7 +475,7 @@ __device__ __noinline__ void flush_movers(double* s_j, const double* crec, doubl
       }
     }
     __syncwarp();
-    flush_group<O>(s_j, xrec, myml, ng, q, qdz, qdy, qdx);
+    flush_group<O, T>(s_j, xrec, myml, ng, q, qdz, qdy, qdx);
   }
   __syncwarp();
 }
@@ -505,21 +518,21 @@ constexpr int ID_CG   = ID_CS + 4 * 4 * (9 + 1);
 constexpr int ID_INTS = (ID_CG + (int)((sizeof(ChunkGeo) + 7) / 8 * 2) + 3) / 4 * 4;
 static_assert(ID_CG % 2 == 0, "s_cg must be 8-byte aligned");
 
-template <int O>
+template <int O, typename T>
 __host__ __device__ inline size_t push_smem()
 {
-  return sizeof(double) * ((size_t)Cfg<O>::EB_DOUBLES + PWARPS * 2 * PF_DOUBLES_W) + IP_INTS * sizeof(int);
+  return sizeof(T) * ((size_t)Cfg<O>::template eb_len<T>() + PWARPS * 2 * PF_DOUBLES_W) + IP_INTS * sizeof(int);
 }
-template <int O>
+template <int O, typename T>
 __host__ __device__ inline size_t deposit_smem()
 {
   using C = Cfg<O>;
-  return sizeof(double) * ((size_t)C::J_DOUBLES + (DWARPS * MAXMOV * CREC + 15) / 16 * 16 + DWARPS * C::SCR +
+  return sizeof(T) * ((size_t)C::J_DOUBLES + (DWARPS * MAXMOV * CREC + 15) / 16 * 16 + DWARPS * C::SCR +
                            DWARPS * PF_DOUBLES_W) + ID_INTS * sizeof(int);
 }
 
-template <int O, bool S>
-__global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_constant__ CUtensorMap tmap, const Kparams P)
+template <int O, bool S, typename T>
+__global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_constant__ CUtensorMap tmap, const KparamsT<T> P)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1;
@@ -540,19 +553,20 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     }
   }
   constexpr int EY = C::EY, EX = C::EX;
-  constexpr int esy = EX * 6, esz = EY * EX * 6;
+  constexpr int FC = field_stride<T>(), esy = EX * FC, esz = EY * EX * FC;
 
   if (P.err[1]) return; // a particle store overflowed earlier: the cell ranges no longer describe memory
-  extern __shared__ __align__(1024) double smem_d[];
-  double*   s_eb   = smem_d;
-  double*   s_pf   = smem_d + C::EB_DOUBLES;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  T* smem_d = reinterpret_cast<T*>(smem_raw);
+  T*   s_eb   = smem_d;
+  T*   s_pf   = smem_d + C::template eb_len<T>();
   int*      s_int  = reinterpret_cast<int*>(s_pf + PWARPS * 2 * PF_DOUBLES_W); // two staging stages
   uint64_t* s_bar  = reinterpret_cast<uint64_t*>(s_int + IP_BAR);
   int*      s_any  = s_int + IP_ANY;
   int*      s_next = s_int + IP_NEXT;
   int*      s_dcnt = s_int + IP_DCNT;
   int*      s_cs   = s_int + IP_CS;
-  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + IP_CG);
+  ChunkGeoT<T>* s_cg = reinterpret_cast<ChunkGeoT<T>*>(s_int + IP_CG);
 
   const int32_t* __restrict__ start = P.sp.start;
   const int cellkey0 = ch * g.ncell;
@@ -561,8 +575,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     *s_any  = 0;
     *s_next = PWARPS; // the first PWARPS rows are taken by the warps directly
   }
-  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += PTHREADS)
-    reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
+  stage_chunk_geo(s_cg, P.cg + ch, tid, PTHREADS);
   for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += PTHREADS) {
     const int r = t / CSW, x = t % CSW;
     if (x <= nbn[2]) {
@@ -584,17 +597,17 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   }
   __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(s_bar, (uint32_t)(C::EZ * EY * EX * 6 * sizeof(double)));
+    mbar_expect_tx(s_bar, (uint32_t)(C::EZ * EY * EX * FC * sizeof(T)));
     tma_load_5d(s_eb, &tmap, s_bar, 0, ex0, ey0, ez0, ch);
   }
 
-  const ChunkGeo& c   = *s_cg;
+  const ChunkGeoT<T>& c = *s_cg;
   const int       cb  = P.sp.cbase[ch];
   const size_t    cap = P.sp.cap;
-  double* __restrict__ xu = P.sp.xu;
-  double* __restrict__ xv = P.sp.xv;
+  T* __restrict__ xu = P.xu;
+  T* __restrict__ xv = P.xv;
   int*          mydc = s_dcnt + warp * 32;
-  double*       my_pf = s_pf + warp * 2 * PF_DOUBLES_W;
+  T*       my_pf = s_pf + warp * 2 * PF_DOUBLES_W;
   const int     nrow  = nbn[0] * nbn[1];
 
   // rows of the tile, handed out dynamically; one iteration = 32 consecutive particles of the row
@@ -612,7 +625,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   };
   auto prefetch = [&](int stage, int i) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) cp_async8(my_pf + (stage * 6 + k) * 32 + lane, xu + soa(k, cap, i));
+    for (int k = 0; k < 6; k++) cp_async_elem(my_pf + (stage * 6 + k) * 32 + lane, xu + soa(k, cap, i));
   };
 
   int  nr = warp, ni0 = 0, npe = 0;
@@ -631,7 +644,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
   int  prev_r = -1, open_lx = -1;
   bool carry = false; // mydc may hold counts of the open bin
   int  bz = 0, by = 0;
-  const double* erow = s_eb;
+  const T* erow = s_eb;
   const int*    csrow = s_cs;
 
   while (have) {
@@ -639,14 +652,14 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     have = advance(nr, ni0, npe);
     cp_async_wait_all();
     // two staging stages: the next iteration's particles are requested before this one's are used
-    const double* mine = my_pf + stage * 6 * 32 + lane;
+    const T* mine = my_pf + stage * 6 * 32 + lane;
     stage ^= 1;
     if (have && ni0 + lane < npe) prefetch(stage, ni0 + lane);
     cp_async_commit();
     if (r != prev_r) {
       const int lz = (nbn[1] == C::TY) ? r / C::TY : r / nbn[1], ly = r - lz * nbn[1];
       bz = b0[0] + lz, by = b0[1] + ly;
-      erow    = s_eb + (size_t)((lz * EY + ly) * EX) * 6;
+      erow    = s_eb + (size_t)((lz * EY + ly) * EX) * FC;
       csrow   = s_cs + r * CSW;
       open_lx = -1;
       carry   = false;
@@ -658,16 +671,16 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
     int        lxc   = 0;
 
     if (valid) {
-      const double pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // index 0,1,2 = z,y,x
+      const T pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // index 0,1,2 = z,y,x
       int    ki[3], bh[3], ii[3];
-      double wi[3][N1], wh[3][N1];
+      T wi[3][N1], wh[3][N1];
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        ii[a]  = digitize(pos[a], c.off[a], g.rdel[a]);
+        ii[a]  = digitize(pos[a], c.off[a], P.rdel[a]);
         ki[a]  = ii[a] - g.is_odd;
-        int hh = digitize(pos[a], c.hoff[a], g.rdel[a]);
-        shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
-        shape_mc<O, S>(pos[a], add<S>(c.lo[a], mul<S>((double)hh, g.del[a])), g.rdel[a], wh[a]);
+        int hh = digitize(pos[a], c.hoff[a], P.rdel[a]);
+        shape_mc<O, S, T>(pos[a], add<S>(c.imin[a], mul<S>((T)ki[a], P.del[a])), P.rdel[a], wi[a]);
+        shape_mc<O, S, T>(pos[a], add<S>(c.lo[a], mul<S>((T)hh, P.del[a])), P.rdel[a], wh[a]);
         bh[a] = (hh - ki[a] > 0) ? 1 : 0;
       }
       // the particle must sit in the bin that owns its slot of the cell-sorted container
@@ -675,58 +688,58 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
       lxc          = min(max(lx, 0), nbn[2] - 1);
       const bool sorted_ok = ii[0] == bz && ii[1] == by && lx == lxc && i >= csrow[lxc] && i < csrow[lxc + 1];
       if (!sorted_ok) atomicOr(P.err, NIXB200_ERR_UNSORTED);
-      const double* ecell = erow + lxc * 6;
+      const T* ecell = erow + lxc * FC;
 
-      double f6[6];
+      T f6[6];
 #pragma unroll
       for (int k = 0; k < 6; k++) {
         const bool hz = (0x1C >> k) & 1, hy = (0x2A >> k) & 1, hx = (0x31 >> k) & 1;
-        double     wz[N1], wy[N1], wx[N1];
+        T     wz[N1], wy[N1], wx[N1];
 #pragma unroll
         for (int j = 0; j < N1; j++) {
           wz[j] = hz ? wh[0][j] : wi[0][j];
           wy[j] = hy ? wh[1][j] : wi[1][j];
           wx[j] = hx ? wh[2][j] : wi[2][j];
         }
-        const double* e = ecell + (hz ? bh[0] : 0) * esz + (hy ? bh[1] : 0) * esy + (hx ? bh[2] : 0) * 6 + k;
-        f6[k] = gather1<O, S>(e, wz, wy, wx);
+        const T* e = ecell + (hz ? bh[0] : 0) * esz + (hy ? bh[1] : 0) * esy + (hx ? bh[2] : 0) * FC + k;
+        f6[k] = gather1<O, S, T>(e, wz, wy, wx);
       }
-      double ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
-      double bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
+      T ex = mul<S>(f6[0], P.dt1), ey = mul<S>(f6[1], P.dt1), ez = mul<S>(f6[2], P.dt1);
+      T bxx = mul<S>(f6[3], P.dt1), byy = mul<S>(f6[4], P.dt1), bzz = mul<S>(f6[5], P.dt1);
 
       // ---- momentum update: the reference's three pushers, association order preserved ---------
-      double ux = mine[3 * 32], uy = mine[4 * 32], uz = mine[5 * 32];
+      T ux = mine[3 * 32], uy = mine[4 * 32], uz = mine[5 * 32];
       if (P.pusher == NIXB200_PUSH_BORIS) { // push_boris, primitives.hpp:165-189
         ux = add<S>(ux, ex);
         uy = add<S>(uy, ey);
         uz = add<S>(uz, ez);
-        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+        T gm = div_<S>(T(1.0), sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(P.cc, P.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
         bxx = mul<S>(bxx, gm);
         byy = mul<S>(byy, gm);
         bzz = mul<S>(bzz, gm);
-        double bb = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
-        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
-        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
-        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+        T bb = div_<S>(T(2.0), add<S>(add<S>(add<S>(T(1.0), mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        T vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+        T vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+        T vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
         ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
         uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
         uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
       } else if (P.pusher == NIXB200_PUSH_VAY) { // push_vay, primitives.hpp:193-224
-        double gm = div_<S>(1.0, sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
-        double vx = add<S>(add<S>(ux, mul<S>(2.0, ex)), mul<S>(gm, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy))));
-        double vy = add<S>(add<S>(uy, mul<S>(2.0, ey)), mul<S>(gm, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz))));
-        double vz = add<S>(add<S>(uz, mul<S>(2.0, ez)), mul<S>(gm, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx))));
-        gm        = add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(vx, vx)), mul<S>(vy, vy)), mul<S>(vz, vz));
-        double bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
-        double bu = add<S>(add<S>(mul<S>(bxx, vx), mul<S>(byy, vy)), mul<S>(bzz, vz));
-        double xx = sub<S>(gm, bb);
-        double yy = add<S>(bb, mul<S>(bu, bu));
-        gm = div_<S>(1.0, sqrt_<S>(mul<S>(0.5, add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(4.0, yy)))))));
+        T gm = div_<S>(T(1.0), sqrt_<S>(add<S>(add<S>(add<S>(mul<S>(P.cc, P.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz))));
+        T vx = add<S>(add<S>(ux, mul<S>(T(2.0), ex)), mul<S>(gm, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy))));
+        T vy = add<S>(add<S>(uy, mul<S>(T(2.0), ey)), mul<S>(gm, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz))));
+        T vz = add<S>(add<S>(uz, mul<S>(T(2.0), ez)), mul<S>(gm, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx))));
+        gm        = add<S>(add<S>(add<S>(mul<S>(P.cc, P.cc), mul<S>(vx, vx)), mul<S>(vy, vy)), mul<S>(vz, vz));
+        T bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
+        T bu = add<S>(add<S>(mul<S>(bxx, vx), mul<S>(byy, vy)), mul<S>(bzz, vz));
+        T xx = sub<S>(gm, bb);
+        T yy = add<S>(bb, mul<S>(bu, bu));
+        gm = div_<S>(T(1.0), sqrt_<S>(mul<S>(T(0.5), add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(T(4.0), yy)))))));
         bxx = mul<S>(bxx, gm);
         byy = mul<S>(byy, gm);
         bzz = mul<S>(bzz, gm);
         bu  = add<S>(add<S>(mul<S>(bxx, vx), mul<S>(byy, vy)), mul<S>(bzz, vz));
-        bb  = div_<S>(1.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        bb  = div_<S>(T(1.0), add<S>(add<S>(add<S>(T(1.0), mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
         ux  = mul<S>(add<S>(add<S>(vx, mul<S>(bu, bxx)), sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy))), bb);
         uy  = mul<S>(add<S>(add<S>(vy, mul<S>(bu, byy)), sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz))), bb);
         uz  = mul<S>(add<S>(add<S>(vz, mul<S>(bu, bzz)), sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx))), bb);
@@ -734,19 +747,19 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
         ux = add<S>(ux, ex);
         uy = add<S>(uy, ey);
         uz = add<S>(uz, ez);
-        double gm = add<S>(add<S>(add<S>(mul<S>(g.cc, g.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz));
-        double bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
-        double bu = add<S>(add<S>(mul<S>(bxx, ux), mul<S>(byy, uy)), mul<S>(bzz, uz));
-        double xx = sub<S>(gm, bb);
-        double yy = add<S>(bb, mul<S>(bu, bu));
-        gm = div_<S>(1.0, sqrt_<S>(mul<S>(0.5, add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(4.0, yy)))))));
+        T gm = add<S>(add<S>(add<S>(mul<S>(P.cc, P.cc), mul<S>(ux, ux)), mul<S>(uy, uy)), mul<S>(uz, uz));
+        T bb = add<S>(add<S>(mul<S>(bxx, bxx), mul<S>(byy, byy)), mul<S>(bzz, bzz));
+        T bu = add<S>(add<S>(mul<S>(bxx, ux), mul<S>(byy, uy)), mul<S>(bzz, uz));
+        T xx = sub<S>(gm, bb);
+        T yy = add<S>(bb, mul<S>(bu, bu));
+        gm = div_<S>(T(1.0), sqrt_<S>(mul<S>(T(0.5), add<S>(xx, sqrt_<S>(add<S>(mul<S>(xx, xx), mul<S>(T(4.0), yy)))))));
         bxx = mul<S>(bxx, gm);
         byy = mul<S>(byy, gm);
         bzz = mul<S>(bzz, gm);
-        bb  = div_<S>(2.0, add<S>(add<S>(add<S>(1.0, mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
-        double vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
-        double vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
-        double vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
+        bb  = div_<S>(T(2.0), add<S>(add<S>(add<S>(T(1.0), mul<S>(bxx, bxx)), mul<S>(byy, byy)), mul<S>(bzz, bzz)));
+        T vx = add<S>(ux, sub<S>(mul<S>(uy, bzz), mul<S>(uz, byy)));
+        T vy = add<S>(uy, sub<S>(mul<S>(uz, bxx), mul<S>(ux, bzz)));
+        T vz = add<S>(uz, sub<S>(mul<S>(ux, byy), mul<S>(uy, bxx)));
         ux = add<S>(ux, add<S>(mul<S>(sub<S>(mul<S>(vy, bzz), mul<S>(vz, byy)), bb), ex));
         uy = add<S>(uy, add<S>(mul<S>(sub<S>(mul<S>(vz, bxx), mul<S>(vx, bzz)), bb), ey));
         uz = add<S>(uz, add<S>(mul<S>(sub<S>(mul<S>(vx, byy), mul<S>(vy, bxx)), bb), ez));
@@ -754,10 +767,10 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
 
       // ---- position update (lorentz_factor, primitives.hpp:158-161); the old position goes to the
       //      temporary array like the reference's xv[0:3] = xu[0:3] (test_esirkepov.cpp:1046-1051)
-      double uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
-      double gam = sqrt_<S>(add<S>(1.0, mul<S>(mul<S>(uu, g.rc), g.rc)));
-      double dtg = div_<S>(P.delt, gam);
-      double pn[3];
+      T uu  = add<S>(add<S>(mul<S>(ux, ux), mul<S>(uy, uy)), mul<S>(uz, uz));
+      T gam = sqrt_<S>(add<S>(T(1.0), mul<S>(mul<S>(uu, P.rc), P.rc)));
+      T dtg = div_<S>(P.delt, gam);
+      T pn[3];
       pn[2] = add<S>(pos[2], mul<S>(ux, dtg));
       pn[1] = add<S>(pos[1], mul<S>(uy, dtg));
       pn[0] = add<S>(pos[0], mul<S>(uz, dtg));
@@ -777,7 +790,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
       int  dcode  = 0;
 #pragma unroll
       for (int a = 0; a < 3; a++) {
-        i1[a]  = digitize(pn[a], c.off[a], g.rdel[a]);
+        i1[a]  = digitize(pn[a], c.off[a], P.rdel[a]);
         int dd = (pn[a] >= c.hi[a]) - (pn[a] < c.lo[a]) + 1;
         dcode  = dcode * 3 + dd;
         int sf = (i1[a] - g.is_odd) - ki[a];
@@ -830,8 +843,8 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
 }
 
 
-template <int O, bool S>
-__global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit(const Kparams P)
+template <int O, bool S, typename T>
+__global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit(const KparamsT<T> P)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1;
@@ -858,18 +871,19 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   constexpr int REC_D = (DWARPS * MAXMOV * CREC + 15) / 16 * 16;
 
   if (P.err[1]) return;
-  extern __shared__ __align__(1024) double smem_d[];
-  double*   s_j    = smem_d;
-  double*   s_rec  = s_j + C::J_DOUBLES;
-  double*   s_red  = s_rec + REC_D;
-  double*   s_pf   = s_red + DWARPS * C::SCR;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  T* smem_d = reinterpret_cast<T*>(smem_raw);
+  T*   s_j    = smem_d;
+  T*   s_rec  = s_j + C::J_DOUBLES;
+  T*   s_red  = s_rec + REC_D;
+  T*   s_pf   = s_red + DWARPS * C::SCR;
   int*      s_int  = reinterpret_cast<int*>(s_pf + DWARPS * PF_DOUBLES_W);
   int*      s_any  = s_int + ID_ANY;
   int*      s_next = s_int + ID_NEXT;
   int*      s_tbl  = s_int + ID_TBL;
   int*      s_mlst = s_int + ID_MLST;
   int*      s_cs   = s_int + ID_CS;
-  ChunkGeo* s_cg   = reinterpret_cast<ChunkGeo*>(s_int + ID_CG);
+  ChunkGeoT<T>* s_cg = reinterpret_cast<ChunkGeoT<T>*>(s_int + ID_CG);
 
   const int32_t* __restrict__ start = P.sp.start;
   const int cellkey0 = ch * g.ncell;
@@ -878,8 +892,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
     *s_any  = 0;
     *s_next = DWARPS;
   }
-  for (int t = tid; t < (int)(sizeof(ChunkGeo) / sizeof(int)); t += DTHREADS)
-    reinterpret_cast<int*>(s_cg)[t] = reinterpret_cast<const int*>(P.cg + ch)[t];
+  stage_chunk_geo(s_cg, P.cg + ch, tid, DTHREADS);
   for (int t = tid; t < nbn[0] * nbn[1] * CSW; t += DTHREADS) {
     const int r = t / CSW, x = t % CSW;
     if (x <= nbn[2]) {
@@ -896,8 +909,8 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   const int jz0 = b0[0] - g.is_odd - g.half + Lb - 1, jy0 = b0[1] - g.is_odd - g.half + Lb - 1,
             jx0 = b0[2] - g.is_odd - g.half + Lb - 1;
 
-  for (int t = tid; t < C::J_DOUBLES; t += DTHREADS) s_j[t] = 0.0;
-  for (int t = tid; t < DWARPS * C::SCR; t += DTHREADS) s_red[t] = 0.0;
+  for (int t = tid; t < C::J_DOUBLES; t += DTHREADS) s_j[t] = T(0.0);
+  for (int t = tid; t < DWARPS * C::SCR; t += DTHREADS) s_red[t] = T(0.0);
   for (int v = tid; v < PV; v += DTHREADS) {
     int comp, jy, jx;
     if (v < C::P_JX) {
@@ -916,28 +929,28 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   }
   __syncthreads();
 
-  const ChunkGeo& c   = *s_cg;
+  const ChunkGeoT<T>& c = *s_cg;
   const size_t    cap = P.sp.cap;
-  const double* __restrict__ xu = P.sp.xu; // new positions
-  const double* __restrict__ xv = P.sp.xv; // old positions (written by k_push)
-  double* myrec = s_rec + (size_t)warp * MAXMOV * CREC;
-  MoverGeo mgeo;
+  const T* __restrict__ xu = P.xu; // new positions
+  const T* __restrict__ xv = P.xv; // old positions (written by k_push)
+  T* myrec = s_rec + (size_t)warp * MAXMOV * CREC;
+  MoverGeoT<T> mgeo;
 #pragma unroll
-  for (int a = 0; a < 3; a++) mgeo.del[a] = g.del[a], mgeo.rdel[a] = g.rdel[a];
+  for (int a = 0; a < 3; a++) mgeo.del[a] = P.del[a], mgeo.rdel[a] = P.rdel[a];
   mgeo.is_odd = g.is_odd;
   int*    myml  = s_mlst + warp * MAXMOV;
-  double* my_red = s_red + warp * C::SCR;
-  double* my_pf  = s_pf + warp * PF_DOUBLES_W;
-  const double* mine = my_pf + lane;
+  T* my_red = s_red + warp * C::SCR;
+  T* my_pf  = s_pf + warp * PF_DOUBLES_W;
+  const T* mine = my_pf + lane;
 
   // deposit role of the lane: particle slot ps, z-plane pl (lanes with pl >= N1 idle along)
   constexpr int PLW = C::PLW, NPS = C::NPS;
   const int     ps = lane / PLW, pl = lane % PLW;
   const bool    pl_on = pl < N1;
   const int     plc   = pl_on ? pl : N1 - 1;
-  double acc[PV];
+  T acc[PV];
 #pragma unroll
-  for (int v = 0; v < PV; v++) acc[v] = 0.0;
+  for (int v = 0; v < PV; v++) acc[v] = T(0.0);
   // bin finished: sum the accumulators of the NPS slots through the (now idle) scratch -- lanes store
   // [value][lane], then lane g adds up the NPS entries of (value, plane) group g -- and add the sums
   // to the J tile.  Row stride 32 + N1: the strided 64-bit loads of 16 consecutive groups hit 16
@@ -960,17 +973,17 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
         const int gi = lane + 32 * k;
         const int vv = gi / N1, plg = gi - vv * N1, v = ch * VCH + vv;
         if (gi < G && v < PV) {
-          const double* src = my_red + vv * RS + plg;
-          double        sum = 0.0;
+          const T* src = my_red + vv * RS + plg;
+          T        sum = T(0.0);
 #pragma unroll
           for (int q = 0; q < NPS; q++) sum += src[q * PLW];
-          if (sum != 0.0) atomicAdd(s_j + cellbase + (plg + 1) * JY * JX + s_tbl[v], sum);
+          if (sum != T(0.0)) atomicAdd(s_j + cellbase + (plg + 1) * JY * JX + s_tbl[v], sum);
         }
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int v = 0; v < PV; v++) acc[v] = 0.0;
+    for (int v = 0; v < PV; v++) acc[v] = T(0.0);
   };
 
   const int ncell_t = nbn[0] * nbn[1] * nbn[2];
@@ -991,8 +1004,8 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   auto prefetch = [&](int i) {
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      cp_async8(my_pf + k * 32 + lane, xv + soa(k, cap, i));       // old x y z
-      cp_async8(my_pf + (3 + k) * 32 + lane, xu + soa(k, cap, i)); // new x y z
+      cp_async_elem(my_pf + k * 32 + lane, xv + soa(k, cap, i));       // old x y z
+      cp_async_elem(my_pf + (3 + k) * 32 + lane, xu + soa(k, cap, i)); // new x y z
     }
   };
 
@@ -1026,22 +1039,22 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
       const bool valid = i < pe;
       bool       dep_ok = false, mover = false;
       int        mcode = -1; // single-axis mover: axis*2 + (1 if high side); -1: multi-axis
-      double     pn[3] = {0.0, 0.0, 0.0};
-      double     wi[3][N1];
+      T     pn[3] = {T(0.0), T(0.0), T(0.0)};
+      T     wi[3][N1];
       int        ki[3] = {0, 0, 0}, sft[3] = {0, 0, 0};
 
       if (valid) {
-        const double pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // old z,y,x
+        const T pos[3] = {mine[2 * 32], mine[1 * 32], mine[0]}; // old z,y,x
         pn[0] = mine[5 * 32], pn[1] = mine[4 * 32], pn[2] = mine[3 * 32];
         bool sorted_ok = true, cfl_ok = true;
         int  nmove = 0;
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          const int ii = digitize(pos[a], c.off[a], g.rdel[a]);
+          const int ii = digitize(pos[a], c.off[a], P.rdel[a]);
           ki[a]        = ii - g.is_odd;
-          shape_mc<O, S>(pos[a], add<S>(c.imin[a], mul<S>((double)ki[a], g.del[a])), g.rdel[a], wi[a]);
+          shape_mc<O, S, T>(pos[a], add<S>(c.imin[a], mul<S>((T)ki[a], P.del[a])), P.rdel[a], wi[a]);
           sorted_ok = sorted_ok && (ii == ((a == 0) ? bz : ((a == 1) ? by : bx)));
-          const int i1 = digitize(pn[a], c.off[a], g.rdel[a]);
+          const int i1 = digitize(pn[a], c.off[a], P.rdel[a]);
           sft[a]       = (i1 - g.is_odd) - ki[a];
           cfl_ok       = cfl_ok && (sft[a] >= -1) && (sft[a] <= 1);
           if (sft[a] != 0) {
@@ -1061,7 +1074,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
         const int  rk   = __popc(mm & ((1u << lane) - 1));
         const bool take = mover && ((mm >> lane) & 1u) && rk < room;
         if (take) {
-          double* r = myrec + (nrec + rk) * CREC;
+          T* r = myrec + (nrec + rk) * CREC;
           r[0] = mine[2 * 32], r[1] = mine[1 * 32], r[2] = mine[0]; // old z, y, x
           r[3] = pn[0], r[4] = pn[1], r[5] = pn[2];                   // new z, y, x
           int* ri = reinterpret_cast<int*>(r + 6);
@@ -1074,7 +1087,7 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
         nrec += __popc(taken);
         mm &= ~taken;
         if (mm || nrec >= NIX_MOV_FLUSH) { // full batches: whole groups of XGROUP records keep the flush lanes busy
-          flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
+          flush_movers<O, S, T>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
           nrec = 0;
         }
       }
@@ -1087,21 +1100,22 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
       // ss[0][.][1..O+1] = old weights; ss[1][.][1+sft..] = new weights (test_esirkepov.cpp:1060-1085);
       // a particle that may not deposit (out of its bin / more than one bin per step) leaves zeros
       {
-        double2* q2 = reinterpret_cast<double2*>(my_red);
+        using R2 = typename Real<T>::vec2;
+        R2* q2 = reinterpret_cast<R2*>(my_red);
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          double s0[N1], ds[N1], cp[N1];
+          T s0[N1], ds[N1], cp[N1];
           if (valid && dep_ok) {
-            double wn[N1];
+            T wn[N1];
             int    k1 = ki[a] + sft[a];
-            shape_mc<O, S>(pn[a], add<S>(c.imin[a], mul<S>((double)k1, g.del[a])), g.rdel[a], wn);
-            double run = (sft[a] < 0) ? wn[0] : 0.0; // DS of mesh slot 0 (ds3d, esirkepov.hpp:167-174)
+            shape_mc<O, S, T>(pn[a], add<S>(c.imin[a], mul<S>((T)k1, P.del[a])), P.rdel[a], wn);
+            T run = (sft[a] < 0) ? wn[0] : T(0.0); // DS of mesh slot 0 (ds3d, esirkepov.hpp:167-174)
 #pragma unroll
             for (int j = 0; j < N1; j++) { // central slots j + 1
-              const double vm = (j + 1 <= O) ? wn[j + 1] : 0.0; // sft = -1 : slot <- wn[slot]
-              const double v0 = wn[j];                           // sft =  0
-              const double vp = (j >= 1) ? wn[j - 1] : 0.0;      // sft = +1
-              const double s1 = (sft[a] == 0) ? v0 : ((sft[a] < 0) ? vm : vp);
+              const T vm = (j + 1 <= O) ? wn[j + 1] : T(0.0); // sft = -1 : slot <- wn[slot]
+              const T v0 = wn[j];                           // sft =  0
+              const T vp = (j >= 1) ? wn[j - 1] : T(0.0);      // sft = +1
+              const T s1 = (sft[a] == 0) ? v0 : ((sft[a] < 0) ? vm : vp);
               s0[j] = wi[a][j];
               ds[j] = s1 - s0[j];
               cp[j] = run;
@@ -1109,46 +1123,46 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < N1; j++) s0[j] = ds[j] = cp[j] = 0.0;
+            for (int j = 0; j < N1; j++) s0[j] = ds[j] = cp[j] = T(0.0);
           }
           if (a == 0) {
 #pragma unroll
             for (int z = 0; z < N1; z++) {
-              q2[C::WQ_Z / 2 + z * C::ZP + lane] = make_double2(s0[z], ds[z]);
+              q2[C::WQ_Z / 2 + z * C::ZP + lane] = Real<T>::make2(s0[z], ds[z]);
               if (z >= 1) my_red[C::WQ_ZC + (z - 1) * C::ZP + lane] = cp[z];
             }
           } else {
             constexpr int NPR = C::NPR;
-            double        t[2 * NPR];
+            T        t[2 * NPR];
 #pragma unroll
             for (int j = 0; j < N1; j++) {
               t[j]      = s0[j];
               t[N1 + j] = ds[j];
               if (j >= 1) t[2 * N1 + j - 1] = cp[j];
             }
-            if (3 * N1 - 1 < 2 * NPR) t[2 * NPR - 1] = 0.0;
+            if (3 * N1 - 1 < 2 * NPR) t[2 * NPR - 1] = T(0.0);
 #pragma unroll
-            for (int pr = 0; pr < NPR; pr++) q2[((a - 1) * NPR + pr) * 32 + lane] = make_double2(t[2 * pr], t[2 * pr + 1]);
+            for (int pr = 0; pr < NPR; pr++) q2[((a - 1) * NPR + pr) * 32 + lane] = Real<T>::make2(t[2 * pr], t[2 * pr + 1]);
           }
         }
       }
       __syncwarp();
       {
         const int nround = (min(32, pe - i0) + NPS - 1) / NPS;
-        for (int r = 0; r < nround; r++) deposit_round<O>(my_red, r * NPS + ps, plc, pl_on, P.q, P.qdxdt, acc);
+        for (int r = 0; r < nround; r++) deposit_round<O, T>(my_red, r * NPS + ps, plc, pl_on, P.q, P.qdxdt, acc);
       }
       __syncwarp();
     }
     if (!have || ncl != cl) flush_bin(cellbase); // last iteration of a bin: its current -> J tile
   }
-  if (nrec) flush_movers<O, S>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
+  if (nrec) flush_movers<O, S, T>(s_j, myrec, my_red, myml, nrec, s_cg, mgeo, P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]);
 
   // ---- flush the J tile: the CTA's single scatter to global memory --------------------------------
   __syncthreads();
-  double* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
+  T* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
   for (int t = tid; t < JZ * JY * JX * 4; t += DTHREADS) {
-    const double v = s_j[(t & 3) * C::JC + (t >> 2)];
-    if (v != 0.0) {
+    const T v = s_j[(t & 3) * C::JC + (t >> 2)];
+    if (v != T(0.0)) {
       const int k = t & 3, n = t >> 2;
       const int gx = jx0 + n % JX, gy = jy0 + (n / JX) % JY, gz = jz0 + n / (JX * JY);
       if (gx >= 0 && gx < g.M[2] && gy >= 0 && gy < g.M[1] && gz >= 0 && gz < g.M[0])
@@ -1157,51 +1171,67 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit
   }
 }
 
-template <int O, bool S>
+template <int O, bool S, typename T>
 int launch_split_t(const PushArgs& a, const CUtensorMap* tmap, cudaStream_t st, cudaEvent_t* ev)
 {
-  Kparams P;
+  KparamsT<T> P;
   P.geo  = a.geo;
   P.cg   = a.cg;
-  P.uj   = a.uj;
+  P.uj   = reinterpret_cast<T*>(a.uj);
+  P.xu   = reinterpret_cast<T*>(a.sp.xu);
+  P.xv   = reinterpret_cast<T*>(a.sp.xv);
   P.sp   = a.sp;
-  P.delt = a.delt;
-  P.dt1  = 0.5 * a.sp.q / a.sp.m * a.delt; // ref_driver.cpp: dt1
-  P.q    = a.sp.q;
-  for (int d = 0; d < 3; d++) P.qdxdt[d] = a.sp.q * (a.geo.del[d] / a.delt);
+  P.delt = (T)a.delt;
+  P.dt1  = (T)(0.5 * a.sp.q / a.sp.m * a.delt); // ref_driver.cpp: dt1
+  P.q    = (T)a.sp.q;
+  for (int d = 0; d < 3; d++) {
+    P.qdxdt[d] = (T)(a.sp.q * (a.geo.del[d] / a.delt));
+    P.del[d]   = (T)a.geo.del[d];
+    P.rdel[d]  = (T)a.geo.rdel[d];
+  }
+  P.cc  = (T)a.geo.cc;
+  P.rc  = (T)a.geo.rc;
   P.err = a.err;
   P.pusher = a.pusher;
   int nblocks = a.geo.nchunk * a.geo.ntile;
   if (ev) cudaEventRecord(ev[0], st);
-  k_push<O, S><<<nblocks, PTHREADS, push_smem<O>(), st>>>(*tmap, P);
+  k_push<O, S, T><<<nblocks, PTHREADS, push_smem<O, T>(), st>>>(*tmap, P);
   NIX_LAUNCHED();
   if (ev) {
     cudaEventRecord(ev[1], st);
     cudaEventRecord(ev[2], st);
   }
-  k_deposit<O, S><<<nblocks, DTHREADS, deposit_smem<O>(), st>>>(P);
+  k_deposit<O, S, T><<<nblocks, DTHREADS, deposit_smem<O, T>(), st>>>(P);
   NIX_LAUNCHED();
   if (ev) cudaEventRecord(ev[3], st);
   return 0;
 }
 
-template <int O, bool S>
+template <int O, bool S, typename T>
 int prepare_t()
 {
-  NIX_CUDA(cudaFuncSetAttribute(k_push<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-  NIX_CUDA(cudaFuncSetAttribute(k_deposit<O, S>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  NIX_CUDA(cudaFuncSetAttribute(k_push<O, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+  NIX_CUDA(cudaFuncSetAttribute(k_deposit<O, S, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
   return 0;
 }
 } // namespace
 
 // The dynamic shared-memory limit is a per-DEVICE attribute of a kernel: set for the current device by
 // every nixb200_domain_create (cheap; several domains on several devices may live in one process).
-int push_deposit_prepare(int order)
+int push_deposit_prepare(int order, bool fp32)
 {
+  if (fp32) {
+    switch (order) {
+    case 1: return prepare_t<1, false, float>();
+    case 2: return prepare_t<2, false, float>();
+    case 3: return prepare_t<3, false, float>();
+    default: set_error("order must be 1, 2 or 3"); return 1;
+    }
+  }
   switch (order) {
-  case 1: return prepare_t<1, true>() || prepare_t<1, false>();
-  case 2: return prepare_t<2, true>() || prepare_t<2, false>();
-  case 3: return prepare_t<3, true>() || prepare_t<3, false>();
+  case 1: return prepare_t<1, true, double>() || prepare_t<1, false, double>();
+  case 2: return prepare_t<2, true, double>() || prepare_t<2, false, double>();
+  case 3: return prepare_t<3, true, double>() || prepare_t<3, false, double>();
   default: set_error("order must be 1, 2 or 3"); return 1;
   }
 }
@@ -1209,9 +1239,9 @@ int push_deposit_prepare(int order)
 size_t push_smem_bytes(const Geo& g)
 {
   switch (g.order) {
-  case 1: return std::max(push_smem<1>(), deposit_smem<1>());
-  case 2: return std::max(push_smem<2>(), deposit_smem<2>());
-  default: return std::max(push_smem<3>(), deposit_smem<3>());
+  case 1: return std::max(push_smem<1, double>(), deposit_smem<1, double>());
+  case 2: return std::max(push_smem<2, double>(), deposit_smem<2, double>());
+  default: return std::max(push_smem<3, double>(), deposit_smem<3, double>());
   }
 }
 
@@ -1249,10 +1279,18 @@ int launch_push_deposit(const PushArgs& a, const CUtensorMap* tmap, bool strict,
   NIX_CUDA(cudaMemsetAsync(a.sp.slabcnt, 0, sizeof(int32_t) * (size_t)a.geo.nchunk * a.geo.slaboff[27], st));
   NIX_CUDA(cudaMemsetAsync(a.sp.oob, 0, sizeof(int32_t) * a.geo.nchunk * LANES, st));
   NIX_CUDA(cudaMemsetAsync(a.sp.nleave, 0, sizeof(int32_t), st));
+  if (a.fp32) { // the fp32 mode has no bit-exact reference to follow: contracted arithmetic only
+    switch (a.geo.order) {
+    case 1: return launch_split_t<1, false, float>(a, tmap, st, ev);
+    case 2: return launch_split_t<2, false, float>(a, tmap, st, ev);
+    case 3: return launch_split_t<3, false, float>(a, tmap, st, ev);
+    default: set_error("order must be 1, 2 or 3"); return 1;
+    }
+  }
   switch (a.geo.order) {
-  case 1: return strict ? launch_split_t<1, true>(a, tmap, st, ev) : launch_split_t<1, false>(a, tmap, st, ev);
-  case 2: return strict ? launch_split_t<2, true>(a, tmap, st, ev) : launch_split_t<2, false>(a, tmap, st, ev);
-  case 3: return strict ? launch_split_t<3, true>(a, tmap, st, ev) : launch_split_t<3, false>(a, tmap, st, ev);
+  case 1: return strict ? launch_split_t<1, true, double>(a, tmap, st, ev) : launch_split_t<1, false, double>(a, tmap, st, ev);
+  case 2: return strict ? launch_split_t<2, true, double>(a, tmap, st, ev) : launch_split_t<2, false, double>(a, tmap, st, ev);
+  case 3: return strict ? launch_split_t<3, true, double>(a, tmap, st, ev) : launch_split_t<3, false, double>(a, tmap, st, ev);
   default: set_error("order must be 1, 2 or 3"); return 1;
   }
 }

@@ -39,35 +39,39 @@ __device__ __forceinline__ int find_chunk(const int32_t* __restrict__ cbase, int
 }
 
 // direction code 9*dz+3*dy+dx of a position relative to the chunk (xtensor_halo3d.hpp:291-293)
-__device__ __forceinline__ int dir_code(const ChunkGeo& c, double x, double y, double z)
+template <typename T>
+__device__ __forceinline__ int dir_code(const ChunkGeo& c, T x, T y, T z)
 {
-  int dz = (z >= c.hi[0]) - (z < c.lo[0]) + 1;
-  int dy = (y >= c.hi[1]) - (y < c.lo[1]) + 1;
-  int dx = (x >= c.hi[2]) - (x < c.lo[2]) + 1;
+  int dz = (z >= (T)c.hi[0]) - (z < (T)c.lo[0]) + 1;
+  int dy = (y >= (T)c.hi[1]) - (y < (T)c.lo[1]) + 1;
+  int dx = (x >= (T)c.hi[2]) - (x < (T)c.lo[2]) + 1;
   return 9 * dz + 3 * dy + dx;
 }
 
 // flat cell index of an in-bounds position (xtensor_particle.hpp:345-348)
-__device__ __forceinline__ int cell_index(const Geo& g, const ChunkGeo& c, double x, double y, double z)
+template <typename T>
+__device__ __forceinline__ int cell_index(const Geo& g, const ChunkGeo& c, T x, T y, T z)
 {
-  int ix = digitize(x, c.off[2], g.rdel[2]);
-  int iy = digitize(y, c.off[1], g.rdel[1]);
-  int iz = digitize(z, c.off[0], g.rdel[0]);
+  int ix = digitize(x, (T)c.off[2], (T)g.rdel[2]);
+  int iy = digitize(y, (T)c.off[1], (T)g.rdel[1]);
+  int iz = digitize(z, (T)c.off[0], (T)g.rdel[0]);
   return (iz * g.R[1] + iy) * g.R[2] + ix;
 }
 
 // ---------------------------------------------------------------------------------------------
 // count only (initial binning): every particle is a resident or is dropped
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void k_count(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp)
 {
   const int ntot = sp.cbase[g.nchunk];
+  const T* __restrict__ xu = reinterpret_cast<const T*>(sp.xu);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ntot; i += gridDim.x * blockDim.x) {
     int             ch = find_chunk(sp.cbase, g.nchunk, i);
     const ChunkGeo& c  = cg[ch];
-    double          x  = sp.xu[soa(0, sp.cap, i)];
-    double          y  = sp.xu[soa(1, sp.cap, i)];
-    double          z  = sp.xu[soa(2, sp.cap, i)];
+    T               x  = xu[soa(0, sp.cap, i)];
+    T               y  = xu[soa(1, sp.cap, i)];
+    T               z  = xu[soa(2, sp.cap, i)];
     int             lane = (i - sp.cbase[ch]) & (LANES - 1);
     int             key  = -1;
     if (dir_code(c, x, y, z) == 13) {
@@ -171,30 +175,49 @@ __global__ void k_mig_offsets(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev
 }
 
 // a migrating particle arrives in chunk B as its pre-sort particle ipB: periodic wrap, bin, count,
-// message slot m (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
+// message slot m (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548).
+// dir = the direction it left its old chunk in.  fp64: positions are global and wrap around the box;
+// fp32: positions are relative to the chunk's origin (an fp32 global coordinate would lose 1e-5 of a cell at
+// x ~ 100 cells), so arriving means shifting by one chunk extent and periodicity is in the neighbour table.
+template <typename T>
 __device__ __forceinline__ void deliver(const Geo& g, const ChunkGeo* __restrict__ cg, const SpeciesDev& sp, int B,
-                                        int m, int ipB, double* v)
+                                        int m, int ipB, T* v, int dir)
 {
-  // xtensor_particle.hpp:371-375   x += (x < X1)*L - (x >= X2)*L   (z,y,x stored as v[2],v[1],v[0])
+  constexpr int NCT = Real<T>::NCT;
+  if constexpr (sizeof(T) == 8) {
+    // xtensor_particle.hpp:371-375   x += (x < X1)*L - (x >= X2)*L   (z,y,x stored as v[2],v[1],v[0])
 #pragma unroll
-  for (int a = 0; a < 3; a++) {
-    double p  = v[2 - a];
-    double L  = g.glen[a];
-    double s1 = (p < g.glo[a]) ? L : 0.0;
-    double s2 = (p >= g.ghi[a]) ? L : 0.0;
-    v[2 - a]  = __dadd_rn(p, __dsub_rn(s1, s2));
+    for (int a = 0; a < 3; a++) {
+      double p  = v[2 - a];
+      double L  = g.glen[a];
+      double s1 = (p < g.glo[a]) ? L : 0.0;
+      double s2 = (p >= g.ghi[a]) ? L : 0.0;
+      v[2 - a]  = __dadd_rn(p, __dsub_rn(s1, s2));
+    }
+  } else {
+    const int e[3] = {dir / 9 - 1, (dir / 3) % 3 - 1, dir % 3 - 1};
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      const T ext = (T)(g.N[a] * g.del[a]);
+      T       p   = v[2 - a] - (T)e[a] * ext; // e = +1: exact (Sterbenz); e = -1: rounds
+      // a particle that left through the low face by less than half an ulp of the extent must not land ON the
+      // neighbour's upper bound (it would be counted out of bounds and dropped, 1e-7-rare in fp32)
+      if (e[a] < 0 && p >= ext) p = __int_as_float(__float_as_int(ext) - 1);
+      v[2 - a] = p;
+    }
   }
   const ChunkGeo& c    = cg[B];
   int             lane = ipB & (LANES - 1);
   int             key  = -1;
-  if (dir_code(c, v[0], v[1], v[2]) == 13) {
-    key = (B * g.ncell + cell_index(g, c, v[0], v[1], v[2])) * LANES + lane;
+  if (dir_code<T>(c, v[0], v[1], v[2]) == 13) {
+    key = (B * g.ncell + cell_index<T>(g, c, v[0], v[1], v[2])) * LANES + lane;
     atomicAdd(&sp.hist[key], 1);
   } else {
     atomicAdd(&sp.oob[B * LANES + lane], 1);
   }
+  T* msg = reinterpret_cast<T*>(sp.msg);
 #pragma unroll
-  for (int k = 0; k < NC; k++) sp.msg[soa(k, sp.lcap, m)] = v[k];
+  for (int k = 0; k < NCT; k++) msg[soa(k, sp.lcap, m)] = v[k];
   sp.msgkey[m] = key;
 }
 
@@ -221,8 +244,12 @@ __global__ void k_stats(Geo g, SpeciesDev sp, int32_t* __restrict__ out4)
 
 // one thread per leaver: destination chunk, pre-sort index there, periodic wrap, count
 // (post_unpack: set_boundary_periodic + count(reset=false), xtensor_halo3d.hpp:541-548)
+template <typename T>
 __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt, int* err)
 {
+  constexpr int NCT = Real<T>::NCT;
+  const T* __restrict__ xu = reinterpret_cast<const T*>(sp.xu);
+  T* paysend = reinterpret_cast<T*>(sp.paysend);
   const int nl = min(*sp.nleave, (int)sp.lcap);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nl; j += gridDim.x * blockDim.x) {
     int4 r    = sp.lrec[j];
@@ -232,7 +259,7 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
     int  B    = cg[A].nbr[dir];
     int idx   = sp.slabcnt[(size_t)A * g.slaboff[27] + r.z] + (r.w >> 5);
     if (B < 0) {
-      // neighbour on another rank: raw payload (the receiver wraps and bins it) at the slot the
+      // neighbour on another rank: raw payload (the receiver wraps / shifts and bins it) at the slot the
       // reference's pack order gives it, peer-major
       int js = (pt.send_slot != nullptr) ? pt.send_slot[A * 27 + dir] : -1;
       if (js < 0) continue; // no neighbour
@@ -242,7 +269,7 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
         continue;
       }
 #pragma unroll
-      for (int k = 0; k < NC; k++) sp.paysend[pos * NC + k] = sp.xu[soa(k, sp.cap, i)];
+      for (int k = 0; k < NCT; k++) paysend[pos * NCT + k] = xu[soa(k, sp.cap, i)];
       continue;
     }
     int m     = sp.msgoff[B * 27 + (26 - dir)] + idx;
@@ -251,16 +278,19 @@ __global__ void k_mig_key(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp,
       atomicOr(err, NIXB200_ERR_CAPACITY);
       continue;
     }
-    double v[NC];
+    T v[NCT];
 #pragma unroll
-    for (int k = 0; k < NC; k++) v[k] = sp.xu[soa(k, sp.cap, i)];
-    deliver(g, cg, sp, B, m, ipB, v);
+    for (int k = 0; k < NCT; k++) v[k] = xu[soa(k, sp.cap, i)];
+    deliver<T>(g, cg, sp, B, m, ipB, v, dir);
   }
 }
 
 // particles received from other ranks: one thread per particle of the peer-major payload
+template <typename T>
 __global__ void k_mig_recv(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp, PeerTabs pt, int ntot, int* err)
 {
+  constexpr int NCT = Real<T>::NCT;
+  const T* __restrict__ payrecv = reinterpret_cast<const T*>(sp.payrecv);
   const int32_t* rpoff = sp.ptab + (pt.nsend + 1);
   for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < ntot; t += gridDim.x * blockDim.x) {
     int lo = 0, hi = pt.nrecv; // rpoff[lo] <= t < rpoff[hi]
@@ -277,10 +307,10 @@ __global__ void k_mig_recv(Geo g, const ChunkGeo* __restrict__ cg, SpeciesDev sp
       atomicOr(err, NIXB200_ERR_CAPACITY);
       continue;
     }
-    double v[NC];
+    T v[NCT];
 #pragma unroll
-    for (int k = 0; k < NC; k++) v[k] = sp.payrecv[(size_t)t * NC + k];
-    deliver(g, cg, sp, en.k, m, ipB, v);
+    for (int k = 0; k < NCT; k++) v[k] = payrecv[(size_t)t * NCT + k];
+    deliver<T>(g, cg, sp, en.k, m, ipB, v, 26 - en.dir); // received in slot e = sent in direction 26 - e
   }
 }
 
@@ -465,12 +495,17 @@ __global__ void k_place_msg(Geo g, SpeciesDev sp, const int* __restrict__ err)
 // (xtensor_particle.hpp:303-313).  Unsigned compare: received particles (top bit set) follow the
 // residents.
 // ---------------------------------------------------------------------------------------------
+template <typename T>
 __global__ void __launch_bounds__(256) k_gather(Geo g, SpeciesDev sp, const int* __restrict__ err)
 {
   if (err[1]) return;
+  constexpr int NCT = Real<T>::NCT;
   const size_t nkey = (size_t)g.nchunk * g.ncell * LANES;
   const int    ntot = min(sp.start[nkey], (int)sp.cap);
   const int32_t* __restrict__ ordl = sp.ordl;
+  const T* __restrict__ xu  = reinterpret_cast<const T*>(sp.xu);
+  const T* __restrict__ msg = reinterpret_cast<const T*>(sp.msg);
+  T* __restrict__ xv        = reinterpret_cast<T*>(sp.xv);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < ntot; j += gridDim.x * blockDim.x) {
     const int      v   = ordl[j];
     const bool     res = v >= 0;
@@ -480,14 +515,14 @@ __global__ void __launch_bounds__(256) k_gather(Geo g, SpeciesDev sp, const int*
     const unsigned uv = (unsigned)v;
     int            r  = 0;
     for (int e = lo; e < hi; e++) r += ((unsigned)ordl[e] < uv) ? 1 : 0;
-    const int     dst = lo + r;
-    const double* src = res ? sp.xu : sp.msg;
-    const size_t  scp = res ? (size_t)sp.cap : (size_t)sp.lcap;
-    double        val[NC];
+    const int    dst = lo + r;
+    const T*     src = res ? xu : msg;
+    const size_t scp = res ? (size_t)sp.cap : (size_t)sp.lcap;
+    T            val[NCT];
 #pragma unroll
-    for (int c = 0; c < NC; c++) val[c] = src[soa(c, scp, m)];
+    for (int c = 0; c < NCT; c++) val[c] = src[soa(c, scp, m)];
 #pragma unroll
-    for (int c = 0; c < NC; c++) sp.xv[soa(c, sp.cap, dst)] = val[c];
+    for (int c = 0; c < NCT; c++) xv[soa(c, sp.cap, dst)] = val[c];
   }
 }
 
@@ -506,13 +541,14 @@ size_t scan_tmp_bytes(size_t n)
   return (nblk + 2) * sizeof(int32_t);
 }
 
-int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st)
+int launch_count_only(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, cudaStream_t st, bool fp32)
 {
   (void)err;
   NIX_CUDA(cudaMemsetAsync(sp.oob, 0, sizeof(int32_t) * g.nchunk * LANES, st));
   NIX_CUDA(cudaMemsetAsync(sp.nleave, 0, sizeof(int32_t), st));
   NIX_CUDA(cudaMemsetAsync(sp.nmsg, 0, sizeof(int32_t), st));
-  k_count<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, cg, sp);
+  if (fp32) k_count<float><<<grid_for(sp.cap, 256), 256, 0, st>>>(g, cg, sp);
+  else k_count<double><<<grid_for(sp.cap, 256), 256, 0, st>>>(g, cg, sp);
   NIX_LAUNCHED();
   return 0;
 }
@@ -536,13 +572,14 @@ int launch_peer_counts(const Geo& g, const SpeciesDev& sp, const PeerTabs& pt, i
 }
 
 int launch_mig_route(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int* err,
-                     cudaStream_t st)
+                     cudaStream_t st, bool fp32)
 {
   k_mig_offsets<<<1, 1024, 0, st>>>(g, cg, sp, pt);
   NIX_LAUNCHED();
   k_mig_guard<<<148, 256, 0, st>>>(sp, err);
   NIX_LAUNCHED();
-  k_mig_key<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, err);
+  if (fp32) k_mig_key<float><<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, err);
+  else k_mig_key<double><<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, err);
   NIX_LAUNCHED();
   return 0;
 }
@@ -555,10 +592,11 @@ int launch_stats(const Geo& g, const SpeciesDev& sp, int32_t* out4, cudaStream_t
 }
 
 int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const PeerTabs& pt, int nrecv_particles,
-                    int* err, cudaStream_t st)
+                    int* err, cudaStream_t st, bool fp32)
 {
   if (nrecv_particles <= 0) return 0;
-  k_mig_recv<<<grid_for(nrecv_particles, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, nrecv_particles, err);
+  if (fp32) k_mig_recv<float><<<grid_for(nrecv_particles, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, nrecv_particles, err);
+  else k_mig_recv<double><<<grid_for(nrecv_particles, 256, 148 * 4), 256, 0, st>>>(g, cg, sp, pt, nrecv_particles, err);
   NIX_LAUNCHED();
   return 0;
 }
@@ -566,7 +604,7 @@ int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const Peer
 // hist -> start, place, scatter; leaves the sorted particles in sp.xv and the new chunk bases in
 // sp.cbase_new (the caller swaps, xtensor_particle.hpp:317)
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
-                cudaStream_t st)
+                cudaStream_t st, bool fp32)
 {
   (void)cg;
   const size_t n     = (size_t)g.nchunk * g.ncell * LANES;
@@ -585,7 +623,8 @@ int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void
   NIX_LAUNCHED();
   k_place_msg<<<grid_for(sp.lcap, 256, 148 * 4), 256, 0, st>>>(g, sp, err);
   NIX_LAUNCHED();
-  k_gather<<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp, err);
+  if (fp32) k_gather<float><<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp, err);
+  else k_gather<double><<<grid_for(sp.cap, 256), 256, 0, st>>>(g, sp, err);
   NIX_LAUNCHED();
   return 0;
 }
