@@ -308,21 +308,25 @@ def run_gpu(args):
     ufi_host.numpy()[...] = ufn.reshape((nchunk,) + tuple(prob.M) + (6,))[
         :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
     npc = prob.ncell() * prob.ppc
-    for s in range(prob.ns):
-        if w["name"] == "cfg2":  # the contract line keeps the numpy inputs the parity tests use
-            flat = np.empty((nchunk * npc, 7), dtype=np.float64)
-            for k in range(nchunk):
-                flat[k * npc:(k + 1) * npc] = prob.particles(ids[k], s)
-            dom.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
-            del flat
-        else:
-            t = device_particles(torch, prob, w, ids, s, seed=2024)
-            torch.cuda.synchronize()
-            dom.set_particles_ptr(s, t.data_ptr(), np.full(nchunk, npc, dtype=np.int64))
-            del t
-            torch.cuda.empty_cache()
-    dom.sort()
-    dom.synchronize()
+
+    def load_particles(dm):
+        for s in range(prob.ns):
+            if w["name"] == "cfg2":  # the contract line keeps the numpy inputs the parity tests use
+                flat = np.empty((nchunk * npc, 7), dtype=np.float64)
+                for k in range(nchunk):
+                    flat[k * npc:(k + 1) * npc] = prob.particles(ids[k], s)
+                dm.set_particles_flat(s, flat, np.full(nchunk, npc, dtype=np.int64))
+                del flat
+            else:
+                t = device_particles(torch, prob, w, ids, s, seed=2024)
+                torch.cuda.synchronize()
+                dm.set_particles_ptr(s, t.data_ptr(), np.full(nchunk, npc, dtype=np.int64))
+                del t
+                torch.cuda.empty_cache()
+        dm.sort()
+        dm.synchronize()
+
+    load_particles(dom)
     ntot = dom.total_particles()
 
     def barrier():
@@ -433,13 +437,44 @@ def run_gpu(args):
     ntot_end = dom.total_particles()
     traffic = dom.peer_traffic()
 
-    t = torch.tensor([ms, ms_e2e, ms_other, ms_e2e_host], dtype=torch.float64, device="cuda")
+    # ---- secondary line: the fp32 mode (north star: "1e-5 (fp32 mode)"; SURVEY 8d: 120 B per particle-update),
+    #      same workload, same steps.  The headline stays fp64 = the reference's real type. ----
+    fp32 = None
+    if not args.no_fp32:
+        dom.close()
+        torch.cuda.empty_cache()
+        d32 = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, device=local,
+                          id_range=(ids[0], ids[-1] + 1), strict_fp=False, capacity_factor=1.12,
+                          stream=stream.cuda_stream, fp32=True)
+        if world > 1:
+            d32.set_ranks(bd, rank)
+            d32.comm_init_torch()
+        d32.field_upload_async(core.FIELD_UF, uf_host.data_ptr())
+        d32.exchange_field()
+        load_particles(d32)
+        for _ in range(3):
+            d32.step(dt)
+        d32.set_profiling(True)
+        d32.phase_ms()
+        ms32 = timed_steps(args.steps, lambda: d32.step(dt))
+        ph32 = d32.phase_ms()
+        d32.set_profiling(False)
+        ms32_em = timed_steps(args.steps, lambda: d32.step_em(dt, cfj))
+        err = d32.check()
+        if err:
+            raise SystemExit(f"bench.py: device error bits {err} in the fp32 leg")
+        n32 = d32.total_particles()
+        fp32 = (ms32, ph32, ms32_em, n32)
+        dom = d32
+
+    t = torch.tensor([ms, ms_e2e, ms_other, ms_e2e_host, fp32[0] if fp32 else 0.0, fp32[2] if fp32 else 0.0],
+                     dtype=torch.float64, device="cuda")
     n = torch.tensor([float(ntot), float(ntot_end), float(traffic["particles_sent"]),
                       float(traffic["halo_cells_sent"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(n, op=dist.ReduceOp.SUM)
-    ms, ms_e2e, ms_other, ms_e2e_host = (float(v) for v in t)
+    ms, ms_e2e, ms_other, ms_e2e_host, ms32_max, ms32_em_max = (float(v) for v in t)
     nglobal = float(n[0])
 
     if rank == 0:
@@ -533,6 +568,26 @@ def run_gpu(args):
             "phases_ms_per_step_e2e": {k: (v[0] / args.steps) for k, v in phases_e2e.items()},
             "field_energy_last": [float(energies[-1, :, 0].sum()), float(energies[-1, :, 1].sum())],
         }
+        if fp32:
+            ms32, ph32, ms32_em, n32 = fp32
+            k32 = []
+            for name, ab in (("k_push", 64.0), ("k_deposit", 24.0)):
+                k_ms, k_calls = ph32[name]
+                lm = k_ms / max(k_calls, 1)
+                part = n32 / prob.ns
+                ach = ab * part / (lm * 1e-3) / 1e9 if lm > 0 else 0.0
+                k32.append({"kernel": name + "<%d,f32>" % w["order"], "launch_ms": lm, "algorithmic_bytes_per_particle": ab,
+                            "achieved": ach, "frac": ach / peak})
+            g32 = 120.0 * n32 / (ms32_max / args.steps * 1e-3) / 1e9
+            out["fp32"] = {
+                "dtype": "f32", "value": nglobal * args.steps / (ms32_max * 1e-3), "ms_per_step": ms32_max / args.steps,
+                "value_with_field_solver": nglobal * args.steps / (ms32_em_max * 1e-3),
+                "phases_ms_per_step": {k: (v[0] / args.steps) for k, v in ph32.items()},
+                "kernels": k32,
+                "step": {"algorithmic_bytes_per_update": 120.0, "achieved": g32, "frac": g32 / peak},
+                "what": "same workload and steps with fp32 particles, E/B and J on the device (positions relative to "
+                        "the chunk origin); agrees with the fp64 oracle to 1e-5 (tests/test_gpu_fp32.py); no reference "
+                        "exists for this mode, the headline stays fp64"}
         if world == 1 and not args.no_cpu:
             r = cpu_reference_run(w, steps=3, warmup=1, budget_s=25.0)
             out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample", "backend", "simd_lanes", "scalar_path_value")}
@@ -557,6 +612,7 @@ def main():
     ap.add_argument("--small", action="store_true", help="2x2x2 chunks (smoke / profiling)")
     ap.add_argument("--cdims", default="", help="override chunks per axis, e.g. 4,4,4")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the secondary fp32 line")
     # exploration only (the contract line is the default: order 2, 16^3-cell chunks, 64 ppc per species)
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS), help="BASELINE.json config (default cfg2 = configs[1])")
     ap.add_argument("--order", type=int, default=0, help="override the shape order 1/2/3")
