@@ -250,6 +250,14 @@ void nixo_domain_step_em(nixo_domain* d, double delt, double cc, double cfj, int
   nixo_domain_exchange(d, NIXO_MODE_PARTICLE);
 }
 
+void nixo_domain_deposit_moment(nixo_domain* d, double cc)
+{
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < d->nchunk; k++)
+    nixo_chunk_deposit_moment(d->chunk[k], cc);
+  nixo_domain_exchange(d, NIXO_MODE_MOMENT);
+}
+
 int64_t nixo_domain_total_particles(nixo_domain* d)
 {
   int64_t n = 0;

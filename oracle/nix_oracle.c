@@ -53,8 +53,9 @@ struct nixo_chunk {
   int       nbvalid[27];
   double*   uf;
   double*   uj;
+  double*   um;                           /* [Mz][My][Mx][ns][14] moments */
   particle_t* up;
-  mpibuf_t  mpibuf[3];
+  mpibuf_t  mpibuf[4];
   int*      num_unpacked;
 };
 
@@ -104,7 +105,75 @@ void nixo_shape_mc(int order, double x, double X, double rdx, double* s)
     s[1]                 = a * (4 - 6 * w1_pow2 + 3 * w1_pow3);
     s[2]                 = a * (4 - 6 * w2_pow2 + 3 * w2_pow3);
     s[3]                 = a * w1_pow3;
+  } else if (order == 4) { /* shape_mc4, primitives.hpp:302-331 */
+    const double a = 1 / 384.0, b = 1 / 96.0, cc = 115 / 192.0, d = 1 / 8.0;
+    double p1 = 1 + delta, m1 = 1 - delta, p2 = 1 + delta * 2, m2 = 1 - delta * 2;
+    double d2 = delta * delta;
+    double p1_2 = p1 * p1, m1_2 = m1 * m1, p1_3 = p1_2 * p1, m1_3 = m1_2 * m1, p1_4 = p1_3 * p1, m1_4 = m1_3 * m1;
+    s[0] = a * (m2 * m2 * m2 * m2);
+    s[1] = b * (55 + 20 * p1 - 120 * p1_2 + 80 * p1_3 - 16 * p1_4);
+    s[2] = cc + d * d2 * (2 * d2 - 5);
+    s[3] = b * (55 + 20 * m1 - 120 * m1_2 + 80 * m1_3 - 16 * m1_4);
+    s[4] = a * (p2 * p2 * p2 * p2);
   }
+}
+
+/* shape functions of the WT scheme (time-step dependent assignment weights; Lu et al., JCP 413, 109388):
+ * primitives.hpp:333-495, dispatch :555-570.  Three branches selected by where delta sits relative to
+ * +-dt (even orders) or 1/2 +- dt (odd orders), blended by 0/1 masks exactly as the reference does. */
+void nixo_shape_wt(int order, double x, double X, double rdx, double dt, double rdt, double* s)
+{
+  double delta = (x - X) * rdx;
+  if (order == 1) {
+    double v = 0.25 * rdt * (1 + 2 * dt - 2 * delta);
+    double ss = fmin(1.0, fmax(0.0, v));
+    s[0] = ss;
+    s[1] = 1 - ss;
+    return;
+  }
+  const int    odd = order & 1;
+  const double lo = odd ? 0.5 - dt : -dt, hi = odd ? 0.5 + dt : +dt;
+  const double t1 = (delta < lo) ? 1.0 : 0.0, t2 = 1 - t1, t3 = (delta < hi) ? 1.0 : 0.0, t4 = 1 - t3;
+  double       A[5] = {0}, B[5] = {0}, C[5] = {0}; /* the three branches */
+  if (order == 2) {
+    double w0 = fabs(delta), w1 = dt - delta, w2 = dt + delta;
+    A[0] = w0, A[1] = 1 - w0, A[2] = 0;
+    B[0] = 0.25 * rdt * w1 * w1;
+    B[1] = 0.50 * rdt * (dt * (2 - dt) - w0 * w0);
+    B[2] = 0.25 * rdt * w2 * w2;
+    C[0] = A[2], C[1] = A[1], C[2] = A[0];
+  } else if (order == 3) {
+    const double a = 1 / 96.0, b = 1 / 24.0, c = 1 / 12.0, adt = a * rdt;
+    double w0 = delta, w1 = 1 - delta, w3 = 1 - 2 * delta, w4 = 1 + 2 * delta;
+    double w5 = 2 * dt + w3, w6 = 2 * dt - w3, w7 = 3 - 2 * delta;
+    double w0_2 = w0 * w0, w1_2 = w1 * w1, w3_2 = w3 * w3, w3_3 = w3_2 * w3, w4_2 = w4 * w4;
+    double w5_3 = w5 * w5 * w5, w6_3 = w6 * w6 * w6, w7_2 = w7 * w7;
+    double dt2 = dt * dt, dt3 = dt2 * dt, dt2_4 = 4 * dt2;
+    double so = adt * (-8 * dt3 - 6 * dt * w3_2), se = adt * (-36 * dt2 * w3 - 3 * w3_3);
+    A[0] = b * (dt2_4 + 3 * w3_2), A[1] = c * (9 - dt2_4 - 12 * w0_2), A[2] = b * (dt2_4 + 3 * w4_2), A[3] = 0;
+    B[0] = adt * w5_3, B[1] = so + se + w1, B[2] = so - se + w0, B[3] = adt * w6_3;
+    C[0] = 0, C[1] = b * (dt2_4 + 3 * w7_2), C[2] = c * (9 - dt2_4 - 12 * w1_2), C[3] = b * (dt2_4 + 3 * w3_2);
+  } else if (order == 4) {
+    const double a = 1 / 48.0, b = 1 / 24.0, c = 1 / 12.0, d = 1 / 6.0, adt = a * rdt, bdt = b * rdt, cdt = c * rdt;
+    double w0 = fabs(delta), w1 = 1 - w0, w2 = 1 - delta, w3 = 1 + delta, w4 = dt - delta, w5 = dt + delta;
+    double w0_2 = w0 * w0, w0_3 = w0_2 * w0, w0_4 = w0_3 * w0, w1_2 = w1 * w1, w1_3 = w1_2 * w1;
+    double w2_3 = w2 * w2 * w2, w3_3 = w3 * w3 * w3, w4_4 = w4 * w4 * w4 * w4, w5_4 = w5 * w5 * w5 * w5;
+    double dt2 = dt * dt, dt3 = dt2 * dt, dt4 = dt3 * dt;
+    double ss1 = -dt4 - 6 * w0_2 * dt2 - w0_4;
+    double ss2 = 3 * dt4 - 8 * dt3 + 18 * w0_2 * dt2 + (16 - 24 * w0_2) * dt + 3 * w0_4;
+    A[0] = d * w0 * (w0_2 + dt2);
+    A[1] = d * (4 - 6 * w1_2 + 3 * w1_3 + (1 - 3 * w0) * dt2);
+    A[2] = d * (4 - 6 * w0_2 + 3 * w0_3 - (2 - 3 * w0) * dt2);
+    A[3] = d * w1 * (w1_2 + dt2);
+    A[4] = 0;
+    B[0] = adt * w4_4;
+    B[1] = cdt * (ss1 + 2 * dt3 * w3 + 2 * dt * (-6 * delta + w3_3));
+    B[2] = bdt * ss2;
+    B[3] = cdt * (ss1 + 2 * dt3 * w2 + 2 * dt * (+6 * delta + w2_3));
+    B[4] = adt * w5_4;
+    for (int j = 0; j < 5; j++) C[j] = A[4 - j];
+  }
+  for (int j = 0; j <= order; j++) s[j] = A[j] * t1 + B[j] * t2 * t3 + C[j] * t4;
 }
 
 /* primitives.hpp:158-161 */
@@ -428,12 +497,14 @@ nixo_chunk* nixo_chunk_create(const nixo_geom* g, int ns, const int* np_required
   size_t ncell = (size_t)c->M[0] * c->M[1] * c->M[2];
   c->uf        = (double*)calloc(ncell * 6, sizeof(double));
   c->uj        = (double*)calloc(ncell * 4, sizeof(double));
+  c->um        = (double*)calloc(ncell * (size_t)ns * 14, sizeof(double));
   c->up        = (particle_t*)calloc((size_t)ns, sizeof(particle_t));
   for (int is = 0; is < ns; is++)
     particle_init(c, &c->up[is], np_required[is], q[is], m[is]);
   set_mpi_buffer(c, &c->mpibuf[NIXO_MODE_FIELD], 0, 8 * 6);
   set_mpi_buffer(c, &c->mpibuf[NIXO_MODE_CURRENT], 0, 8 * 4);
   set_mpi_buffer(c, &c->mpibuf[NIXO_MODE_PARTICLE], HEAD_BYTE, ELEM_BYTE);
+  set_mpi_buffer(c, &c->mpibuf[NIXO_MODE_MOMENT], 0, 8 * ns * 14);
   c->num_unpacked = (int*)calloc((size_t)ns, sizeof(int));
   return c;
 }
@@ -449,13 +520,14 @@ void nixo_chunk_destroy(nixo_chunk* c)
     free(c->up[is].pindex);
     free(c->up[is].pcount);
   }
-  for (int mode = 0; mode < 3; mode++) {
+  for (int mode = 0; mode < 4; mode++) {
     free(c->mpibuf[mode].sendbuf);
     free(c->mpibuf[mode].recvbuf);
   }
   free(c->up);
   free(c->uf);
   free(c->uj);
+  free(c->um);
   free(c->num_unpacked);
   free(c);
 }
@@ -957,6 +1029,9 @@ void nixo_chunk_halo_pack(nixo_chunk* c, int mode)
         if (mode == NIXO_MODE_FIELD) {
           get_bounds(c, iz, iy, ix, 0, lo, hi); /* send slab (interior), :35-41 */
           slab_copy(c, c->uf, 6, lo, hi, buf, 0);
+        } else if (mode == NIXO_MODE_MOMENT) {
+          get_bounds(c, iz, iy, ix, 1, lo, hi); /* recv slab (ghost), XtensorHaloMoment3D::pack :144-160 */
+          slab_copy(c, c->um, c->ns * 14, lo, hi, buf, 0);
         } else {
           get_bounds(c, iz, iy, ix, 1, lo, hi); /* recv slab (ghost), :93-99 */
           slab_copy(c, c->uj, 4, lo, hi, buf, 0);
@@ -986,6 +1061,9 @@ void nixo_chunk_halo_unpack(nixo_chunk* c, int mode)
         } else if (mode == NIXO_MODE_CURRENT) {
           get_bounds(c, iz, iy, ix, 0, lo, hi); /* send slab (interior) +=, :119-125 */
           slab_copy(c, c->uj, 4, lo, hi, buf, 2);
+        } else if (mode == NIXO_MODE_MOMENT) {
+          get_bounds(c, iz, iy, ix, 0, lo, hi); /* send slab (interior) +=, XtensorHaloMoment3D::unpack :163-186 */
+          slab_copy(c, c->um, c->ns * 14, lo, hi, buf, 2);
         } else {
           particle_unpack(c, s);
         }
@@ -1030,4 +1108,137 @@ uint8_t* nixo_chunk_recvbuf(nixo_chunk* c, int mode)
 int nixo_chunk_recvbuf_size(nixo_chunk* c, int mode)
 {
   return c->mpibuf[mode].recvsize;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* moments (N4) and the diagnostic packers (N3)                                               */
+/* ------------------------------------------------------------------------------------------ */
+double* nixo_chunk_um(nixo_chunk* c)
+{
+  return c->um;
+}
+
+/* The reference ships the scatter (append_moment3d<Order>, primitives.hpp:896-930: um(iz0+jz, iy0+jy, ix0+jx,
+ * is, k) += moment[jz][jy][jx][k]) but not the loop that fills moment[][][][14] -- it is the downstream
+ * application's.  The composition used here (and by the GPU kernel), per particle of mass m, u = gamma v:
+ *   weights  shape_mc<O> about the integer node, the stencil of the gather (base i - O/2 + Lb);
+ *   moment[jz][jy][jx][k] = ((wz wy) wx) mom[k],   mom = { m;  m u_i/gamma (x,y,z);  m gamma c^2;  m u_i c (x,y,z);
+ *                                                         m u_i u_j / gamma for (xx, yy, zz, xy, yz, zx) }          */
+void nixo_chunk_deposit_moment(nixo_chunk* c, double cc)
+{
+  const int    order = c->g.order, is_odd = order % 2, half = order / 2, n1 = order + 1;
+  const size_t ncell = (size_t)c->M[0] * c->M[1] * c->M[2];
+  const int    my = c->M[1], mx = c->M[2], ns = c->ns;
+  memset(c->um, 0, sizeof(double) * ncell * (size_t)ns * 14);
+  const double del[3] = {c->g.del[0], c->g.del[1], c->g.del[2]};
+  const double rc = 1 / cc;
+  for (int is = 0; is < ns; is++) {
+    particle_t* p = &c->up[is];
+    for (int ip = 0; ip < p->Np; ip++) {
+      const double* xu = &p->xu[(size_t)ip * NC];
+      const double  pos[3] = {xu[2], xu[1], xu[0]}; /* z, y, x */
+      double        w[3][MAXO + 2];
+      int           i0[3];
+      for (int a = 0; a < 3; a++) {
+        const double lo  = c->lim[a][0];
+        const double rdx = 1 / del[a];
+        int          i   = nixo_digitize(pos[a], lo - 0.5 * del[a] * is_odd, rdx) - is_odd;
+        nixo_shape_mc(order, pos[a], (lo + 0.5 * del[a]) + i * del[a], rdx, w[a]);
+        i0[a] = i - half + c->Lb[a];
+      }
+      const double ux = xu[3], uy = xu[4], uz = xu[5], m = p->m;
+      const double gam = nixo_lorentz_factor(ux, uy, uz, rc);
+      const double mom[14] = {m,           m * ux / gam, m * uy / gam, m * uz / gam, m * gam * cc * cc,
+                              m * ux * cc, m * uy * cc,  m * uz * cc,  m * ux * ux / gam, m * uy * uy / gam,
+                              m * uz * uz / gam, m * ux * uy / gam, m * uy * uz / gam, m * uz * ux / gam};
+      for (int jz = 0; jz < n1; jz++)
+        for (int jy = 0; jy < n1; jy++)
+          for (int jx = 0; jx < n1; jx++) {
+            const double ww  = (w[0][jz] * w[1][jy]) * w[2][jx];
+            double*      dst = &c->um[(((((size_t)(i0[0] + jz)) * my + (i0[1] + jy)) * mx + (i0[2] + jx)) * ns + is) * 14];
+            for (int k = 0; k < 14; k++) dst[k] += ww * mom[k];
+          }
+    }
+  }
+}
+
+/* XtensorPacker3D::decimate_size, xtensor_packer3d.hpp:232-241 */
+static int decimate_size(int lb, int ub, int decimate)
+{
+  int size = ub - lb + 1;
+  return (size <= decimate) ? 1 : size / decimate;
+}
+
+/* XtensorPacker3D::decimate_field (xtensor_packer3d.hpp:185-230): block averages of the interior of
+ * x[Mz][My][Mx][nc], accumulated block offset by block offset (that order fixes the rounding) */
+static int decimate_array(const nixo_chunk* c, const double* x, int nc, int decimate, double* out)
+{
+  const int sz = decimate_size(c->Lb[0], c->Ub[0], decimate), sy = decimate_size(c->Lb[1], c->Ub[1], decimate),
+            sx = decimate_size(c->Lb[2], c->Ub[2], decimate);
+  const int n = sz * sy * sx * nc;
+  if (!out) return n;
+  const int    bz = (c->Ub[0] - c->Lb[0] + 1) / sz, by = (c->Ub[1] - c->Lb[1] + 1) / sy, bx = (c->Ub[2] - c->Lb[2] + 1) / sx;
+  const double factor = 1.0 / (bz * by * bx);
+  memset(out, 0, sizeof(double) * (size_t)n);
+  for (int kz = 0; kz < bz; kz++)
+    for (int ky = 0; ky < by; ky++)
+      for (int kx = 0; kx < bx; kx++)
+        for (int jz = 0; jz < sz; jz++)
+          for (int jy = 0; jy < sy; jy++)
+            for (int jx = 0; jx < sx; jx++) {
+              const int     iz = c->Lb[0] + jz * bz + kz, iy = c->Lb[1] + jy * by + ky, ix = c->Lb[2] + jx * bx + kx;
+              const double* src = &x[(((size_t)iz * c->M[1] + iy) * c->M[2] + ix) * nc];
+              double*       dst = &out[(((size_t)jz * sy + jy) * sx + jx) * nc];
+              for (int ic = 0; ic < nc; ic++) dst[ic] += factor * src[ic];
+            }
+  return n;
+}
+
+/* XtensorPacker3D::pack_field (xtensor_packer3d.hpp:62-82): colocate E/B at the cell centres
+ * (colocate_field_3d, :279-302), then decimate */
+int nixo_chunk_pack_field(nixo_chunk* c, int decimate, double* out)
+{
+  if (!out) return decimate_array(c, c->uf, 6, decimate, NULL);
+  const size_t ncell = (size_t)c->M[0] * c->M[1] * c->M[2];
+  const int    my = c->M[1], mx = c->M[2];
+  double*      y = (double*)calloc(ncell * 6, sizeof(double));
+#define X6(z, yy, x, k) c->uf[((((size_t)(z)) * my + (yy)) * mx + (x)) * 6 + (k)]
+  for (int iz = c->Lb[0]; iz <= c->Ub[0]; iz++)
+    for (int iy = c->Lb[1]; iy <= c->Ub[1]; iy++)
+      for (int ix = c->Lb[2]; ix <= c->Ub[2]; ix++) {
+        double* d = &y[(((size_t)iz * my + iy) * mx + ix) * 6];
+        d[0] = 0.50 * (X6(iz, iy, ix, 0) + X6(iz, iy, ix + 1, 0));
+        d[1] = 0.50 * (X6(iz, iy, ix, 1) + X6(iz, iy + 1, ix, 1));
+        d[2] = 0.50 * (X6(iz, iy, ix, 2) + X6(iz + 1, iy, ix, 2));
+        d[3] = 0.25 * (X6(iz, iy, ix, 3) + X6(iz + 1, iy + 1, ix, 3) + X6(iz, iy + 1, ix, 3) + X6(iz + 1, iy, ix, 3));
+        d[4] = 0.25 * (X6(iz, iy, ix, 4) + X6(iz + 1, iy, ix + 1, 4) + X6(iz + 1, iy, ix, 4) + X6(iz, iy, ix + 1, 4));
+        d[5] = 0.25 * (X6(iz, iy, ix, 5) + X6(iz, iy + 1, ix + 1, 5) + X6(iz, iy, ix + 1, 5) + X6(iz, iy + 1, ix, 5));
+      }
+#undef X6
+  int n = decimate_array(c, y, 6, decimate, out);
+  free(y);
+  return n;
+}
+
+/* XtensorPacker3D::pack_moment (xtensor_packer3d.hpp:84-104): decimate only.  which: 0 = uj (4), 1 = um (ns*14) */
+int nixo_chunk_pack_moment(nixo_chunk* c, int which, int decimate, double* out)
+{
+  return which == 0 ? decimate_array(c, c->uj, 4, decimate, out) : decimate_array(c, c->um, c->ns * 14, decimate, out);
+}
+
+/* XtensorPacker3D::pack_tracer (xtensor_packer3d.hpp:122-140): the particles whose 64-bit id is negative,
+ * in container order */
+int nixo_chunk_pack_tracer(nixo_chunk* c, int is, double* out)
+{
+  particle_t* p = &c->up[is];
+  int         n = 0;
+  for (int ip = 0; ip < p->Np; ip++) {
+    int64_t id;
+    memcpy(&id, &p->xu[(size_t)ip * NC + 6], sizeof(id));
+    if (id < 0) {
+      if (out) memcpy(&out[(size_t)n * NC], &p->xu[(size_t)ip * NC], sizeof(double) * NC);
+      n++;
+    }
+  }
+  return n;
 }

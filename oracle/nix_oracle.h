@@ -26,6 +26,7 @@ extern "C" {
 #define NIXO_MODE_FIELD 0    /* XtensorHaloField3D    xtensor_halo3d.hpp:19-71   */
 #define NIXO_MODE_CURRENT 1  /* XtensorHaloCurrent3D  xtensor_halo3d.hpp:77-129  */
 #define NIXO_MODE_PARTICLE 2 /* XtensorHaloParticle3D xtensor_halo3d.hpp:251-557 */
+#define NIXO_MODE_MOMENT 3   /* XtensorHaloMoment3D   xtensor_halo3d.hpp:135-187 */
 
 /* Geometry of one chunk: exactly the inputs of Chunk::Chunk / set_boundary_margin /
  * set_global_context / set_coordinate (chunk.cpp:6-16,118-247). */
@@ -69,7 +70,8 @@ void     nixo_particle_set_boundary_periodic(nixo_chunk* c, int is, int lbp, int
 
 /* ---- numerical primitives (scalar instantiations), for known-answer tests ---- */
 int    nixo_digitize(double x, double xmin, double rdx);                 /* primitives.hpp:46-58  */
-void   nixo_shape_mc(int order, double x, double X, double rdx, double* s); /* :257-298,519-532  */
+void   nixo_shape_mc(int order, double x, double X, double rdx, double* s); /* order 1..4  :257-331,519-532 */
+void   nixo_shape_wt(int order, double x, double X, double rdx, double dt, double rdt, double* s); /* :333-495,555-570 */
 void   nixo_push_boris(double* u, const double* eb, double cc);          /* primitives.hpp:165-189 */
 void   nixo_push_vay(double* u, const double* eb, double cc);            /* primitives.hpp:193-224 */
 void   nixo_push_higuera_cary(double* u, const double* eb, double cc);   /* primitives.hpp:227-253 */
@@ -117,6 +119,15 @@ void         nixo_domain_sort_only(nixo_domain* d);          /* count(reset) + s
 /* one full step: clear J, push+deposit, J halo, E/B halo, particle migration (count+pack+unpack+sort) */
 void    nixo_domain_step(nixo_domain* d, double delt, double cc, int simd);
 int64_t nixo_domain_total_particles(nixo_domain* d);
+
+/* ---- moments (append_moment3d primitives.hpp:896-930, XtensorHaloMoment3D) and the diagnostic packers
+ *      (XtensorPacker3D, xtensor_packer3d.hpp:62-140); `out` may be NULL (query: returns the element count) ---- */
+double* nixo_chunk_um(nixo_chunk* c); /* [Mz][My][Mx][ns][14] */
+void    nixo_chunk_deposit_moment(nixo_chunk* c, double cc);
+int     nixo_chunk_pack_field(nixo_chunk* c, int decimate, double* out);
+int     nixo_chunk_pack_moment(nixo_chunk* c, int which /* 0: uj, 1: um */, int decimate, double* out);
+int     nixo_chunk_pack_tracer(nixo_chunk* c, int is, double* out);
+void    nixo_domain_deposit_moment(nixo_domain* d, double cc); /* every chunk + the moment halo */
 
 /* ---- Yee FDTD field update (oracle/field_solver.c).  NOT part of the reference tree: parity unpinned by
  *      the reference, pinned by known answers (tests/test_field_solver.py).  uf [Mz][My][Mx][6],

@@ -16,7 +16,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-MODE_FIELD, MODE_CURRENT, MODE_PARTICLE = 0, 1, 2
+MODE_FIELD, MODE_CURRENT, MODE_PARTICLE, MODE_MOMENT = 0, 1, 2, 3
 
 _LIBS = {
     "port": os.path.join(HERE, "libnixoracle.so"),
@@ -140,6 +140,13 @@ def load(name="port"):
     sig("nixo_domain_sort_only", None, P)
     sig("nixo_domain_step", None, P, D, D, I)
     sig("nixo_domain_total_particles", C.c_int64, P)
+    sig("nixo_shape_wt", None, I, D, D, D, D, D, PD)
+    sig("nixo_chunk_um", PD, P)
+    sig("nixo_chunk_deposit_moment", None, P, D)
+    sig("nixo_chunk_pack_field", I, P, I, PD)
+    sig("nixo_chunk_pack_moment", I, P, I, I, PD)
+    sig("nixo_chunk_pack_tracer", I, P, I, PD)
+    sig("nixo_domain_deposit_moment", None, P, D)
     sig("nixo_fdtd_push_bfd", None, PD, PI, I, PD, D, D, I)
     sig("nixo_fdtd_push_efd", None, PD, PD, PI, I, PD, D, D, D)
     sig("nixo_fdtd_energy", None, PD, PI, I, PD)
@@ -200,6 +207,32 @@ class Chunk:
         return np.ctypeslib.as_array(self.lib.nixo_chunk_uj(self.h), shape=self.M + (4,))
 
     # --- particle container ---
+    @property
+    def um(self):
+        return np.ctypeslib.as_array(self.lib.nixo_chunk_um(self.h), shape=self.M + (self.ns, 14))
+
+    def deposit_moment(self, cc=1.0):
+        self.lib.nixo_chunk_deposit_moment(self.h, float(cc))
+
+    def pack_field(self, decimate=1):
+        n = self.lib.nixo_chunk_pack_field(self.h, int(decimate), None)
+        out = np.zeros(n)
+        self.lib.nixo_chunk_pack_field(self.h, int(decimate), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def pack_moment(self, which, decimate=1):
+        n = self.lib.nixo_chunk_pack_moment(self.h, int(which), int(decimate), None)
+        out = np.zeros(n)
+        self.lib.nixo_chunk_pack_moment(self.h, int(which), int(decimate), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
+    def pack_tracer(self, s=0):
+        n = self.lib.nixo_chunk_pack_tracer(self.h, int(s), None)
+        out = np.zeros((n, 7))
+        if n:
+            self.lib.nixo_chunk_pack_tracer(self.h, int(s), out.ctypes.data_as(C.POINTER(C.c_double)))
+        return out
+
     def ng(self, s=0):
         return self.lib.nixo_particle_ng(self.h, s)
 
@@ -341,6 +374,10 @@ class Domain:
 
     def step_em(self, delt, cc, cfj=1.0, simd=False):
         self.lib.nixo_domain_step_em(self.h, delt, cc, cfj, int(simd))
+
+    def deposit_moment(self, cc=1.0):
+        """every chunk's moments + XtensorHaloMoment3D exchange"""
+        self.lib.nixo_domain_deposit_moment(self.h, float(cc))
 
     def field_energy(self):
         """[nchunk][2]: sum E^2, sum B^2 over the interior cells of every chunk"""

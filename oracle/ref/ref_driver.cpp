@@ -17,6 +17,7 @@
 #include "interp.hpp"
 #include "primitives.hpp"
 #include "xtensor_halo3d.hpp"
+#include "xtensor_packer3d.hpp"
 
 #include "../nix_oracle.h"
 
@@ -31,8 +32,9 @@ public:
   int                     Ns;
   xt::xtensor<float64, 4> uf;
   xt::xtensor<float64, 4> uj;
+  xt::xtensor<float64, 5> um; // [Mz][My][Mx][Ns][14]
   ParticleVec             up;
-  MpiBufferPtr            mpibuf[3];
+  MpiBufferPtr            mpibuf[4];
 
   RefChunk(const nixo_geom* g, int ns, const int* np_required, const double* q, const double* m)
       : Chunk(Dims3D{g->dims[0], g->dims[1], g->dims[2]}, Bool3D{true, true, true}, 0),
@@ -54,6 +56,8 @@ public:
     uj.resize({mz, my, mx, 4ul});
     uf.fill(0);
     uj.fill(0);
+    um.resize({mz, my, mx, (size_t)ns, 14ul});
+    um.fill(0);
 
     for (int is = 0; is < ns; is++) {
       auto p = std::make_shared<XtensorParticle>(np_required[is], *this);
@@ -70,6 +74,8 @@ public:
     mpibuf[NIXO_MODE_PARTICLE] = std::make_shared<MpiBuffer>();
     set_mpi_buffer(mpibuf[NIXO_MODE_PARTICLE], 0, XtensorHaloParticle3D<RefChunk>::head_byte,
                    XtensorHaloParticle3D<RefChunk>::elem_byte);
+    mpibuf[NIXO_MODE_MOMENT] = std::make_shared<MpiBuffer>();
+    set_mpi_buffer(mpibuf[NIXO_MODE_MOMENT], 0, 0, sizeof(float64) * ns * 14);
   }
 
   int get_order() const
@@ -348,6 +354,63 @@ inline RefChunk* R(nixo_chunk* c)
 }
 } // namespace
 
+namespace
+{
+// per-particle composition documented in nix_oracle.c (the reference ships the scatter, not the loop)
+template <int Order>
+void deposit_moment_t(RefChunk& c, float64 cc)
+{
+  using namespace nix::primitives;
+  constexpr int is_odd = Order % 2, half = Order / 2, n1 = Order + 1;
+  const auto [Lbx, Ubx] = c.get_xbound();
+  const auto [Lby, Uby] = c.get_ybound();
+  const auto [Lbz, Ubz] = c.get_zbound();
+  const float64 rc = 1 / cc;
+  c.um.fill(0);
+  for (int is = 0; is < c.Ns; is++) {
+    auto&         p    = *c.up[is];
+    const float64 del[3] = {p.delz, p.dely, p.delx};
+    const float64 lo[3]  = {p.zmin, p.ymin, p.xmin};
+    const int     Lb[3]  = {Lbz, Lby, Lbx};
+    for (int ip = 0; ip < p.Np; ip++) {
+      const float64 pos[3] = {p.xu(ip, 2), p.xu(ip, 1), p.xu(ip, 0)};
+      float64       w[3][n1];
+      int           i0[3];
+      for (int a = 0; a < 3; a++) {
+        const float64 rdx = 1 / del[a];
+        int           i   = digitize(pos[a], lo[a] - 0.5 * del[a] * is_odd, rdx) - is_odd;
+        shape_mc<Order>(pos[a], (lo[a] + 0.5 * del[a]) + i * del[a], rdx, w[a]);
+        i0[a] = i - half + Lb[a];
+      }
+      const float64 ux = p.xu(ip, 3), uy = p.xu(ip, 4), uz = p.xu(ip, 5), m = p.m;
+      const float64 gam = lorentz_factor(ux, uy, uz, rc);
+      const float64 mom[14] = {m,           m * ux / gam, m * uy / gam, m * uz / gam, m * gam * cc * cc,
+                               m * ux * cc, m * uy * cc,  m * uz * cc,  m * ux * ux / gam, m * uy * uy / gam,
+                               m * uz * uz / gam, m * ux * uy / gam, m * uy * uz / gam, m * uz * ux / gam};
+      float64 moment[n1][n1][n1][14];
+      for (int jz = 0; jz < n1; jz++)
+        for (int jy = 0; jy < n1; jy++)
+          for (int jx = 0; jx < n1; jx++) {
+            const float64 ww = (w[0][jz] * w[1][jy]) * w[2][jx];
+            for (int k = 0; k < 14; k++) moment[jz][jy][jx][k] = ww * mom[k];
+          }
+      append_moment3d<Order>(c.um, i0[0], i0[1], i0[2], is, moment);
+    }
+  }
+}
+
+struct PackData {
+  int Lbz, Ubz, Lby, Uby, Lbx, Ubx;
+};
+PackData pack_data(RefChunk& c)
+{
+  const auto [Lbx, Ubx] = c.get_xbound();
+  const auto [Lby, Uby] = c.get_ybound();
+  const auto [Lbz, Ubz] = c.get_zbound();
+  return PackData{Lbz, Ubz, Lby, Uby, Lbx, Ubx};
+}
+} // namespace
+
 extern "C" {
 
 const char* nixo_impl_name(void)
@@ -455,6 +518,29 @@ void nixo_shape_mc(int order, double x, double X, double rdx, double* s)
     break;
   case 3:
     primitives::shape_mc<3>(x, X, rdx, s);
+    break;
+  case 4:
+    primitives::shape_mc<4>(x, X, rdx, s);
+    break;
+  default:
+    break;
+  }
+}
+
+void nixo_shape_wt(int order, double x, double X, double rdx, double dt, double rdt, double* s)
+{
+  switch (order) {
+  case 1:
+    primitives::shape_wt<1>(x, X, rdx, dt, rdt, s);
+    break;
+  case 2:
+    primitives::shape_wt<2>(x, X, rdx, dt, rdt, s);
+    break;
+  case 3:
+    primitives::shape_wt<3>(x, X, rdx, dt, rdt, s);
+    break;
+  case 4:
+    primitives::shape_wt<4>(x, X, rdx, dt, rdt, s);
     break;
   default:
     break;
@@ -565,6 +651,9 @@ void nixo_chunk_halo_pack(nixo_chunk* c, int mode)
   } else if (mode == NIXO_MODE_CURRENT) {
     XtensorHaloCurrent3D<RefChunk> halo(r->uj, *r);
     r->pack_bc_exchange(r->mpibuf[mode], halo);
+  } else if (mode == NIXO_MODE_MOMENT) {
+    XtensorHaloMoment3D<RefChunk> halo(r->um, *r);
+    r->pack_bc_exchange(r->mpibuf[mode], halo);
   } else {
     XtensorHaloParticle3D<RefChunk> halo(r->up, *r);
     r->pack_bc_exchange(r->mpibuf[mode], halo);
@@ -579,6 +668,9 @@ void nixo_chunk_halo_unpack(nixo_chunk* c, int mode)
     r->unpack_bc_exchange(r->mpibuf[mode], halo);
   } else if (mode == NIXO_MODE_CURRENT) {
     XtensorHaloCurrent3D<RefChunk> halo(r->uj, *r);
+    r->unpack_bc_exchange(r->mpibuf[mode], halo);
+  } else if (mode == NIXO_MODE_MOMENT) {
+    XtensorHaloMoment3D<RefChunk> halo(r->um, *r);
     r->unpack_bc_exchange(r->mpibuf[mode], halo);
   } else {
     XtensorHaloParticle3D<RefChunk> halo(r->up, *r);
@@ -631,6 +723,45 @@ uint8_t* nixo_chunk_recvbuf(nixo_chunk* c, int mode)
 int nixo_chunk_recvbuf_size(nixo_chunk* c, int mode)
 {
   return R(c)->mpibuf[mode]->recvbuf.size;
+}
+
+// ---- moments and diagnostic packers: the reference's own append_moment3d / XtensorPacker3D ----
+double* nixo_chunk_um(nixo_chunk* c)
+{
+  return R(c)->um.data();
+}
+
+void nixo_chunk_deposit_moment(nixo_chunk* c, double cc)
+{
+  RefChunk* r = R(c);
+  switch (r->order) {
+  case 1: deposit_moment_t<1>(*r, cc); break;
+  case 2: deposit_moment_t<2>(*r, cc); break;
+  case 3: deposit_moment_t<3>(*r, cc); break;
+  }
+}
+
+int nixo_chunk_pack_field(nixo_chunk* c, int decimate, double* out)
+{
+  RefChunk*       r = R(c);
+  XtensorPacker3D packer;
+  return (int)(packer.pack_field(r->uf, pack_data(*r), decimate, reinterpret_cast<uint8_t*>(out), 0) / sizeof(float64));
+}
+
+int nixo_chunk_pack_moment(nixo_chunk* c, int which, int decimate, double* out)
+{
+  RefChunk*       r = R(c);
+  XtensorPacker3D packer;
+  size_t          n = which == 0 ? packer.pack_moment(r->uj, pack_data(*r), decimate, reinterpret_cast<uint8_t*>(out), 0)
+                                 : packer.pack_moment(r->um, pack_data(*r), decimate, reinterpret_cast<uint8_t*>(out), 0);
+  return (int)(n / sizeof(float64));
+}
+
+int nixo_chunk_pack_tracer(nixo_chunk* c, int is, double* out)
+{
+  RefChunk*       r = R(c);
+  XtensorPacker3D packer;
+  return (int)(packer.pack_tracer(r->up[is], reinterpret_cast<uint8_t*>(out), 0) / (sizeof(float64) * 7));
 }
 
 } // extern "C"

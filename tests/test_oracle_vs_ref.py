@@ -158,3 +158,53 @@ def test_anisotropic_cells_and_c_bit_exact(oracle_port, oracle_ref, order):
             for s in range(prob.ns):
                 assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s))), f"step {step}: particles"
                 assert np.array_equal(ca.pindex(s), cb.pindex(s))
+
+
+# ---- N3 / N4: shapes of order 4 and of the WT scheme, moments, moment halo, diagnostic packers -------------
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_shape_mc4_and_shape_wt_bit_identical(oracle_port, oracle_ref, order):
+    rng = np.random.default_rng(order)
+    s1, s2 = np.zeros(order + 1), np.zeros(order + 1)
+    for _ in range(400):
+        X = rng.uniform(-5, 5)
+        x = X + rng.uniform(-0.5, 1.0)
+        rdx = rng.uniform(0.5, 2.0)
+        oracle_port.nixo_shape_mc(order, x, X, rdx, s1.ctypes.data_as(PD))
+        oracle_ref.nixo_shape_mc(order, x, X, rdx, s2.ctypes.data_as(PD))
+        assert np.array_equal(s1.view(np.int64), s2.view(np.int64))
+        dt = rng.uniform(0.05, 0.5)
+        oracle_port.nixo_shape_wt(order, x, X, rdx, dt, 1 / dt, s1.ctypes.data_as(PD))
+        oracle_ref.nixo_shape_wt(order, x, X, rdx, dt, 1 / dt, s2.ctypes.data_as(PD))
+        assert np.array_equal(s1.view(np.int64), s2.view(np.int64)), (order, x, X, rdx, dt)
+
+
+@pytest.mark.parametrize("order", [1, 2, 3])
+def test_moments_halo_and_packers_bit_identical(oracle_port, oracle_ref, order):
+    """deposit_moment (append_moment3d) + XtensorHaloMoment3D exchange, then XtensorPacker3D::pack_field /
+    pack_moment (decimate 1, 2, 4) / pack_tracer: the plain-C port equals the reference's classes bit for bit"""
+    from nix_b200.synth import Problem
+    from helpers import oracle_domain
+    prob = Problem((2, 1, 2), (8, 8, 8), order, ppc=5, seed=7 + order, vth=(0.4, 0.1))
+    parts = prob.particles
+
+    def tagged(k, s):  # every third particle is a tracer (negative id)
+        xu = parts(k, s)
+        ids = np.ascontiguousarray(xu[:, 6]).view(np.int64).copy()
+        ids[::3] = -ids[::3] - 1
+        xu[:, 6] = ids.view(np.float64)
+        return xu
+    prob.particles = tagged
+    doms = [oracle_domain(lib, prob) for lib in (oracle_port, oracle_ref)]
+    for d in doms:
+        d.step(0.5, 1.0)
+        d.deposit_moment(1.0)
+    for a, b in zip(doms[0].chunks, doms[1].chunks):
+        assert np.abs(a.um).max() > 0
+        assert np.array_equal(a.um, b.um)
+        for dec in (1, 2, 4, 16):
+            assert np.array_equal(a.pack_field(dec), b.pack_field(dec)), dec
+            assert np.array_equal(a.pack_moment(0, dec), b.pack_moment(0, dec))
+            assert np.array_equal(a.pack_moment(1, dec), b.pack_moment(1, dec))
+        for s in range(prob.ns):
+            ta, tb = a.pack_tracer(s), b.pack_tracer(s)
+            assert len(ta) > 0 and np.array_equal(ta.view(np.int64), tb.view(np.int64))
