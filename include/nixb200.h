@@ -32,6 +32,7 @@ extern "C" {
 #define NIXB200_MODE_FIELD 0    /* XtensorHaloField3D    xtensor_halo3d.hpp:19-71   */
 #define NIXB200_MODE_CURRENT 1  /* XtensorHaloCurrent3D  xtensor_halo3d.hpp:77-129  */
 #define NIXB200_MODE_PARTICLE 2 /* XtensorHaloParticle3D xtensor_halo3d.hpp:251-557 */
+#define NIXB200_MODE_MOMENT 3   /* XtensorHaloMoment3D   xtensor_halo3d.hpp:135-187 */
 
 #define NIXB200_FIELD_UF 0
 #define NIXB200_FIELD_UJ 1
@@ -166,6 +167,29 @@ int nixb200_domain_step_em(nixb200_domain* d, double delt, double cfj);
 int nixb200_domain_field_energy(nixb200_domain* d, double* host_e2b2);
 /* 1: push arithmetic without FMA contraction (bit-identical to the reference's scalar templates), 0: contracted */
 int nixb200_domain_set_strict_fp(nixb200_domain* d, int on);
+
+/* ---- diagnostics / output on the device (SURVEY.md 8f, N3 + N4): only the packed output crosses PCIe ----
+ * moments: um[Mz][My][Mx][ns][14] per chunk = append_moment3d<Order> (primitives.hpp:896-930) over every
+ *   particle, then XtensorHaloMoment3D (xtensor_halo3d.hpp:135-187) incl. neighbours on other ranks.  The
+ *   14 moments per particle (the loop is the downstream application's; ours, as in the oracle):
+ *   m; m u_i/gamma (x,y,z); m gamma c^2; m u_i c (x,y,z); m u_i u_j/gamma (xx,yy,zz,xy,yz,zx)
+ * pack_field   XtensorPacker3D::pack_field  (xtensor_packer3d.hpp:62-82): E/B colocated at the cell centres,
+ *              then block-averaged by `decimate`  -> host[sz][sy][sx][6]
+ * pack_moment  XtensorPacker3D::pack_moment (:84-104): block averages of uj (which = 0, 4 values) or um
+ *              (which = 1, ns*14 values)
+ * pack_tracer  XtensorPacker3D::pack_tracer (:122-140): the particles of a chunk with a negative 64-bit id, in
+ *              container order, AoS [n][7]
+ * host == NULL queries the element count.  pack_field / pack_moment reproduce the reference's rounding. */
+int nixb200_domain_deposit_moment(nixb200_domain* d);
+int nixb200_chunk_moment_download(nixb200_domain* d, int k, double* host);
+int nixb200_chunk_pack_field(nixb200_domain* d, int k, int decimate, double* host, int64_t* count);
+int nixb200_chunk_pack_moment(nixb200_domain* d, int k, int which, int decimate, double* host, int64_t* count);
+int nixb200_chunk_pack_tracer(nixb200_domain* d, int k, int is, double* host_aos, int64_t max_np, int64_t* np);
+/* the shape functions the push does not use, as device primitives (bit-identical to the reference's scalar
+ * templates): kind 0 = shape_mc<order> (order 1..4, primitives.hpp:257-331), 1 = shape_wt<order> (:333-495);
+ * out[n][order+1] */
+int nixb200_shape_eval(int device, int kind, int order, int n, const double* x, const double* X, double rdx, double dt,
+                       double rdt, double* out);
 
 /* ---- per-chunk halo buffers in the reference's MpiBuffer layout (chunk.cpp:257-286), for
  *      neighbours that live on another rank and for drop-in use behind Chunk::set_boundary_* ---- */

@@ -35,7 +35,8 @@ SYMBOLS = [
     "nixb200_domain_set_comm", "nixb200_domain_peer_traffic", "nixb200_domain_reserve",
     "nixb200_domain_get_capacity", "nixb200_domain_push_bfd", "nixb200_domain_push_efd", "nixb200_domain_step_em",
     "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp", "nixb200_comm_create", "nixb200_comm_destroy",
-    "nixb200_device_count",
+    "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
+    "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -137,10 +138,30 @@ def load_library():
     sig("nixb200_domain_step_em", I, P, D, D)
     sig("nixb200_domain_field_energy", I, P, PD)
     sig("nixb200_domain_set_strict_fp", I, P, I)
+    sig("nixb200_domain_deposit_moment", I, P)
+    sig("nixb200_chunk_moment_download", I, P, I, PD)
+    sig("nixb200_chunk_pack_field", I, P, I, I, PD, PL)
+    sig("nixb200_chunk_pack_moment", I, P, I, I, I, PD, PL)
+    sig("nixb200_chunk_pack_tracer", I, P, I, I, PD, C.c_int64, PL)
+    sig("nixb200_shape_eval", I, I, I, I, I, PD, PD, D, D, D, PD)
     sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
     sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib
     return lib
+
+
+def shape_eval(kind, order, x, X, rdx, dt=0.0, rdt=0.0, device=0):
+    """shape_mc<order> (kind 0) / shape_wt<order> (kind 1) of the reference, evaluated on the device: [n][order+1]"""
+    lib = load_library()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    X = np.ascontiguousarray(X, dtype=np.float64)
+    out = np.empty((len(x), order + 1), dtype=np.float64)
+    PD = C.POINTER(C.c_double)
+    rc = lib.nixb200_shape_eval(int(device), int(kind), int(order), len(x), x.ctypes.data_as(PD), X.ctypes.data_as(PD),
+                                float(rdx), float(dt), float(rdt), out.ctypes.data_as(PD))
+    if rc != 0:
+        raise NixB200Error(lib.nixb200_last_error().decode())
+    return out
 
 
 def launch_count():
@@ -402,6 +423,38 @@ class Domain:
 
     def set_strict_fp(self, on):
         self._ck(self.lib.nixb200_domain_set_strict_fp(self.h, int(bool(on))))
+
+    # ---- diagnostics / output on the device (rows N3, N4) ----
+    def deposit_moment(self):
+        self._ck(self.lib.nixb200_domain_deposit_moment(self.h))
+
+    def get_moment(self, k):
+        a = np.empty(self.M + (self.ns, 14), dtype=np.float64)
+        self._ck(self.lib.nixb200_chunk_moment_download(self.h, k, a.ctypes.data_as(C.POINTER(C.c_double))))
+        return a
+
+    def pack_field(self, k, decimate=1):
+        n = C.c_int64(0)
+        self._ck(self.lib.nixb200_chunk_pack_field(self.h, k, int(decimate), None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        self._ck(self.lib.nixb200_chunk_pack_field(self.h, k, int(decimate), out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return out
+
+    def pack_moment(self, k, which, decimate=1):
+        n = C.c_int64(0)
+        self._ck(self.lib.nixb200_chunk_pack_moment(self.h, k, int(which), int(decimate), None, C.byref(n)))
+        out = np.empty(n.value, dtype=np.float64)
+        self._ck(self.lib.nixb200_chunk_pack_moment(self.h, k, int(which), int(decimate),
+                                                    out.ctypes.data_as(C.POINTER(C.c_double)), C.byref(n)))
+        return out
+
+    def pack_tracer(self, k, s):
+        n = C.c_int64(0)
+        self._ck(self.lib.nixb200_chunk_pack_tracer(self.h, k, s, None, 0, C.byref(n)))
+        out = np.empty((n.value, 7), dtype=np.float64)
+        if n.value:
+            self._ck(self.lib.nixb200_chunk_pack_tracer(self.h, k, s, out.ctypes.data_as(C.POINTER(C.c_double)), n.value, C.byref(n)))
+        return out
 
     # ---- per-chunk halo buffers in the reference's MpiBuffer layout ----
     def halo_layout(self, mode):

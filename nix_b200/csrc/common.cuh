@@ -282,7 +282,20 @@ int launch_halo_field(const Geo& g, const ChunkGeo* cg, void* uf, const PeerTabs
 int launch_halo_current(const Geo& g, const ChunkGeo* cg, void* uj, const PeerTabs& pt, const void* recvbuf,
                         cudaStream_t st, bool fp32);
 int launch_peer_pack(const Geo& g, int mode, const void* data, const PeerTabs& pt, void* sendbuf,
+                     cudaStream_t st, bool fp32, int ncomp_moment = 0);
+int launch_halo_moment(const Geo& g, const ChunkGeo* cg, void* um, int ncomp, const PeerTabs& pt, const void* recvbuf,
+                       cudaStream_t st, bool fp32);
+
+// diagnostics / output path (diag.cu)
+int pack_count(const Geo& g, int decimate, int nc);
+int launch_pack_grid(const Geo& g, const void* chunk_ptr, bool colocate, int decimate, int nc, int fc, double* out,
                      cudaStream_t st, bool fp32);
+int launch_pack_tracer(const SpeciesDev& sp, int first, int np, const double* origin3, double* out, int max_out,
+                       int* count_dev, cudaStream_t st, bool fp32);
+int launch_moment(const Geo& g, const ChunkGeo* cg, const SpeciesDev& sp, int is, int ns, void* um, cudaStream_t st,
+                  bool fp32);
+int launch_shape_eval(int kind, int order, int n, const double* x, const double* X, double rdx, double dt, double rdt,
+                      double* out, cudaStream_t st);
 int launch_halo_pack(const Geo& g, int k, int mode, const double* data, double* buf, cudaStream_t st);
 int launch_halo_unpack(const Geo& g, int k, int mode, double* data, const double* buf,
                        const int* nbvalid_dev, cudaStream_t st);

@@ -540,6 +540,9 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->stat_dev) cudaFree(d->stat_dev);
   if (d->energy_dev) cudaFree(d->energy_dev);
   if (d->origin_dev) cudaFree(d->origin_dev);
+  if (d->um) cudaFree(d->um);
+  if (d->pack_dev) cudaFree(d->pack_dev);
+  if (d->count_dev) cudaFree(d->count_dev);
   if (d->aos_tmp) cudaFree(d->aos_tmp);
   if (d->stat_host) cudaFreeHost(d->stat_host);
   if (d->ev_stat) cudaEventDestroy(d->ev_stat);
@@ -1075,6 +1078,145 @@ int nixb200_domain_set_strict_fp(nixb200_domain* dd, int on)
   NIX_ENTER(dd);
   d->desc.strict_fp = on ? 1 : 0;
   return 0;
+}
+
+// ---- diagnostics / output (diag.cu) ---------------------------------------------------------------------
+static int pack_scratch(Domain* d, size_t bytes)
+{
+  if (!d->count_dev) NIX_CUDA(cudaMalloc(&d->count_dev, sizeof(int)));
+  if (bytes <= d->pack_bytes) return 0;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  if (d->pack_dev) cudaFree(d->pack_dev);
+  d->pack_dev = nullptr, d->pack_bytes = 0;
+  NIX_CUDA(cudaMalloc(&d->pack_dev, bytes));
+  d->pack_bytes = bytes;
+  return 0;
+}
+
+static size_t moment_chunk_values(const Domain* d)
+{
+  return d->cells_per_chunk * d->sp.size() * 14;
+}
+
+int nixb200_domain_deposit_moment(nixb200_domain* dd)
+{
+  NIX_ENTER(dd);
+  if (need_peers(d)) return 1;
+  const size_t bytes = moment_chunk_values(d) * d->geo.nchunk * d->esz;
+  if (!d->um) NIX_CUDA(cudaMalloc(&d->um, bytes));
+  NIX_CUDA(cudaMemsetAsync(d->um, 0, bytes, d->stream));
+  const int ns = (int)d->sp.size();
+  for (int is = 0; is < ns; is++)
+    if (launch_moment(d->geo, d->cg_dev, d->sp[is], is, ns, d->um, d->stream, d->fp32)) return 1;
+  if (peer_exchange_halo(d, NIXB200_MODE_MOMENT)) return 1;
+  return launch_halo_moment(d->geo, d->cg_dev, d->um, ns * 14, peer_tabs(d), peer_recvbuf_moment(d), d->stream, d->fp32);
+}
+
+int nixb200_chunk_moment_download(nixb200_domain* dd, int k, double* host)
+{
+  NIX_ENTER(dd);
+  if (check_chunk(d, k) || !host) return 1;
+  if (!d->um) {
+    set_error("no moments on the device: call nixb200_domain_deposit_moment first");
+    return 1;
+  }
+  const size_t n = moment_chunk_values(d);
+  if (d->fp32) {
+    if (pack_scratch(d, sizeof(double) * n)) return 1;
+    if (launch_cells_convert(false, d->pack_dev, reinterpret_cast<float*>(d->um) + (size_t)k * n, n, 1, 1, d->stream)) return 1;
+    NIX_CUDA(cudaMemcpyAsync(host, d->pack_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d->stream));
+  } else {
+    NIX_CUDA(cudaMemcpyAsync(host, reinterpret_cast<double*>(d->um) + (size_t)k * n, sizeof(double) * n, cudaMemcpyDeviceToHost, d->stream));
+  }
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+static int pack_grid(Domain* d, int k, const void* base, bool colocate, int decimate, int nc, int fc, double* host, int64_t* count)
+{
+  if (decimate < 1) {
+    set_error("decimate must be >= 1");
+    return 1;
+  }
+  const int n = pack_count(d->geo, decimate, nc);
+  if (count) *count = n;
+  if (!host) return 0;
+  if (pack_scratch(d, sizeof(double) * n)) return 1;
+  const char* chunk = reinterpret_cast<const char*>(base) + (size_t)k * d->cells_per_chunk * fc * d->esz;
+  if (launch_pack_grid(d->geo, chunk, colocate, decimate, nc, fc, d->pack_dev, d->stream, d->fp32)) return 1;
+  NIX_CUDA(cudaMemcpyAsync(host, d->pack_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+int nixb200_chunk_pack_field(nixb200_domain* dd, int k, int decimate, double* host, int64_t* count)
+{
+  NIX_ENTER(dd);
+  if (check_chunk(d, k)) return 1;
+  return pack_grid(d, k, d->uf, true, decimate, 6, d->fcs, host, count);
+}
+
+int nixb200_chunk_pack_moment(nixb200_domain* dd, int k, int which, int decimate, double* host, int64_t* count)
+{
+  NIX_ENTER(dd);
+  if (check_chunk(d, k)) return 1;
+  if (which == 0) return pack_grid(d, k, d->uj, false, decimate, 4, 4, host, count);
+  if (!d->um) {
+    set_error("no moments on the device: call nixb200_domain_deposit_moment first");
+    return 1;
+  }
+  const int nc = (int)d->sp.size() * 14;
+  return pack_grid(d, k, d->um, false, decimate, nc, nc, host, count);
+}
+
+int nixb200_chunk_pack_tracer(nixb200_domain* dd, int k, int is, double* host_aos, int64_t max_np, int64_t* np)
+{
+  NIX_ENTER(dd);
+  if (check_chunk(d, k) || check_species(d, is) || !np) return 1;
+  SpeciesDev& s = d->sp[is];
+  int32_t     cb[2];
+  NIX_CUDA(cudaMemcpyAsync(cb, s.cbase + k, sizeof(int32_t) * 2, cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  const int n = cb[1] - cb[0];
+  const int room = host_aos ? (int)std::min<int64_t>(max_np, n) : 0;
+  if (pack_scratch(d, sizeof(double) * NC * std::max(1, room))) return 1;
+  if (launch_pack_tracer(s, cb[0], n, d->origin_dev + 3 * k, d->pack_dev, room, d->count_dev, d->stream, d->fp32)) return 1;
+  int cnt = 0;
+  NIX_CUDA(cudaMemcpyAsync(&cnt, d->count_dev, sizeof(int), cudaMemcpyDeviceToHost, d->stream));
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  *np = cnt;
+  if (!host_aos) return 0;
+  if (cnt > max_np) {
+    set_error("output buffer too small");
+    return 1;
+  }
+  if (cnt > 0) {
+    NIX_CUDA(cudaMemcpyAsync(host_aos, d->pack_dev, sizeof(double) * NC * cnt, cudaMemcpyDeviceToHost, d->stream));
+    NIX_CUDA(cudaStreamSynchronize(d->stream));
+  }
+  return 0;
+}
+
+int nixb200_shape_eval(int device, int kind, int order, int n, const double* x, const double* X, double rdx, double dt,
+                       double rdt, double* out)
+{
+  if (!x || !X || !out || n < 0 || order < 1 || order > 4 || kind < 0 || kind > 1) {
+    set_error("shape_eval: bad argument (order 1..4, kind 0 = shape_mc, 1 = shape_wt)");
+    return 1;
+  }
+  DeviceGuard dev_guard(device);
+  double *dx = nullptr, *dX = nullptr, *dout = nullptr;
+  NIX_CUDA(cudaMalloc(&dx, sizeof(double) * std::max(1, n)));
+  NIX_CUDA(cudaMalloc(&dX, sizeof(double) * std::max(1, n)));
+  NIX_CUDA(cudaMalloc(&dout, sizeof(double) * std::max(1, n) * (order + 1)));
+  NIX_CUDA(cudaMemcpy(dx, x, sizeof(double) * n, cudaMemcpyHostToDevice));
+  NIX_CUDA(cudaMemcpy(dX, X, sizeof(double) * n, cudaMemcpyHostToDevice));
+  int rc = launch_shape_eval(kind, order, n, dx, dX, rdx, dt, rdt, dout, 0);
+  if (!rc) NIX_CUDA(cudaMemcpy(out, dout, sizeof(double) * n * (order + 1), cudaMemcpyDeviceToHost));
+  cudaFree(dx);
+  cudaFree(dX);
+  cudaFree(dout);
+  return rc;
 }
 
 int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufaddr27)

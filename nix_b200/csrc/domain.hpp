@@ -17,6 +17,10 @@ struct Domain {
   ChunkGeo*               cg_dev = nullptr;
   void*                   uf     = nullptr; // E/B of every chunk, in the domain's real type
   void*                   uj     = nullptr; // rho / J
+  void*                   um     = nullptr; // moments [nchunk][Mz][My][Mx][ns][14], allocated on first use
+  double*                 pack_dev = nullptr; // device staging of the packers' output (grown on demand)
+  size_t                  pack_bytes = 0;
+  int*                    count_dev = nullptr;
   std::vector<SpeciesDev> sp;
   cudaStream_t            stream = nullptr;
   // real type of the device-resident data: fp64 (the reference's, default) or fp32 (desc.fp32)
@@ -108,6 +112,7 @@ void     peer_destroy(Domain* d);
 int      peer_alloc_species(Domain* d, SpeciesDev& s);
 int      peer_exchange_halo(Domain* d, int mode);       // pack -> NCCL send/recv (no-op without peers)
 const void* peer_recvbuf(const Domain* d);
+const void* peer_recvbuf_moment(const Domain* d);
 int      peer_migrate(Domain* d);                       // the whole migrate + sort phase with peers
 int      do_sort_species(Domain* d, SpeciesDev& s);
 } // namespace nixb200

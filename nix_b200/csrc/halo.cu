@@ -155,6 +155,57 @@ __global__ void __launch_bounds__(256) k_halo_current(Geo g, const ChunkGeo* __r
   }
 }
 
+// XtensorHaloMoment3D (xtensor_halo3d.hpp:135-187): the same gather-and-add as the current for an array with
+// `ncomp` values per cell (ns * 14 moments); one thread per (interior cell, component)
+template <typename T>
+__global__ void __launch_bounds__(256) k_halo_moment(Geo g, const ChunkGeo* __restrict__ cg, T* um, int ncomp, PeerTabs pt,
+                                                     const T* __restrict__ recvbuf)
+{
+  const int ch    = blockIdx.y;
+  const int ncell = g.N[0] * g.N[1] * g.N[2];
+  const int Lb = g.nb, nbw = g.nb;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)ncell * ncomp;
+       t += (long long)gridDim.x * blockDim.x) {
+    const int comp = (int)(t % ncomp), cidx = (int)(t / ncomp);
+    int       i[3];
+    i[2] = cidx % g.N[2] + Lb;
+    i[1] = (cidx / g.N[2]) % g.N[1] + Lb;
+    i[0] = cidx / (g.N[2] * g.N[1]) + Lb;
+    bool lowm[3], higm[3], any = false;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      int Ub  = Lb + g.N[a] - 1;
+      lowm[a] = i[a] <= Lb + nbw - 1;
+      higm[a] = i[a] >= Ub - nbw + 1;
+      any     = any || lowm[a] || higm[a];
+    }
+    if (!any) continue;
+    T* dst = um + cell_off(g, ch, i[0], i[1], i[2]) * ncomp + comp;
+    T  v   = *dst;
+    for (int slot = 0; slot < 27; slot++) {
+      if (slot == 13) continue;
+      int  e[3] = {slot / 9, (slot / 3) % 3, slot % 3};
+      bool in   = true;
+      int  s[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        in   = in && (e[a] == 1 || (e[a] == 0 && lowm[a]) || (e[a] == 2 && higm[a]));
+        s[a] = i[a] + (1 - e[a]) * g.N[a];
+      }
+      if (!in) continue;
+      int nb = cg[ch].nbr[slot];
+      if (nb >= 0) {
+        v = add<true>(um[cell_off(g, nb, s[0], s[1], s[2]) * ncomp + comp], v);
+      } else {
+        int j = (pt.recv_slot != nullptr) ? pt.recv_slot[ch * 27 + slot] : -1;
+        if (j < 0) continue;
+        v = add<true>(recvbuf[((size_t)pt.recv_ent[j].celloff + slab_index(g, slot, false, i)) * ncomp + comp], v);
+      }
+    }
+    *dst = v;
+  }
+}
+
 // every slab bound for another rank -> the peer-major send buffer.  Field: SEND slabs (interior);
 // current: RECV slabs (ghost, where the deposit spilled).  blockIdx.y = send entry.
 template <typename T>
@@ -298,18 +349,30 @@ int launch_halo_current(const Geo& g, const ChunkGeo* cg, void* uj, const PeerTa
   return 0;
 }
 
-// words per cell in the peer buffers: the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4)
+int launch_halo_moment(const Geo& g, const ChunkGeo* cg, void* um, int ncomp, const PeerTabs& pt, const void* recvbuf,
+                       cudaStream_t st, bool fp32)
+{
+  const long long n = (long long)g.N[0] * g.N[1] * g.N[2] * ncomp;
+  dim3            grid((unsigned)std::min<long long>((n + 255) / 256, 4096), g.nchunk);
+  if (fp32) k_halo_moment<float><<<grid, 256, 0, st>>>(g, cg, (float*)um, ncomp, pt, (const float*)recvbuf);
+  else k_halo_moment<double><<<grid, 256, 0, st>>>(g, cg, (double*)um, ncomp, pt, (const double*)recvbuf);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+// words per cell in the peer buffers: the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4;
+// moments: ncomp_moment = ns * 14)
 int launch_peer_pack(const Geo& g, int mode, const void* data, const PeerTabs& pt, void* sendbuf,
-                     cudaStream_t st, bool fp32)
+                     cudaStream_t st, bool fp32, int ncomp_moment)
 {
   if (pt.nsend == 0) return 0;
-  const int ncomp = (mode == NIXB200_MODE_FIELD) ? (fp32 ? 8 : 6) : 4;
+  const int ncomp = (mode == NIXB200_MODE_FIELD) ? (fp32 ? 8 : 6) : ((mode == NIXB200_MODE_MOMENT) ? ncomp_moment : 4);
   int       big   = g.nb * std::max(g.N[0], std::max(g.N[1], g.N[2])) * std::max(g.N[1], g.N[2]) * ncomp;
   dim3      grid(std::min(8, (big + 255) / 256), pt.nsend);
   if (fp32)
-    k_peer_pack<float><<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, (const float*)data, pt.send_ent, (float*)sendbuf);
+    k_peer_pack<float><<<grid, 256, 0, st>>>(g, ncomp, mode != NIXB200_MODE_FIELD, (const float*)data, pt.send_ent, (float*)sendbuf);
   else
-    k_peer_pack<double><<<grid, 256, 0, st>>>(g, ncomp, mode == NIXB200_MODE_CURRENT, (const double*)data, pt.send_ent, (double*)sendbuf);
+    k_peer_pack<double><<<grid, 256, 0, st>>>(g, ncomp, mode != NIXB200_MODE_FIELD, (const double*)data, pt.send_ent, (double*)sendbuf);
   NIX_LAUNCHED();
   return 0;
 }

@@ -206,6 +206,8 @@ struct PeerCtx {
   // halo buffers, peer-major, sized for the 6-component field (the current uses 4/6 of them)
   double* hsend = nullptr;
   double* hrecv = nullptr;
+  void*   msend = nullptr; // moment halo (ns * 14 values per cell), allocated on first use
+  void*   mrecv = nullptr;
   std::vector<int64_t> send_cell_first, recv_cell_first; // [npeer+1] first cell of each peer
   // particle counts: per peer one message [ns][entries of the peer]
   int32_t* cnt_send = nullptr; // device [ns * nsend]
@@ -236,11 +238,16 @@ const void* peer_recvbuf(const Domain* d)
   return d->peer ? d->peer->hrecv : nullptr;
 }
 
+const void* peer_recvbuf_moment(const Domain* d)
+{
+  return d->peer ? d->peer->mrecv : nullptr;
+}
+
 void peer_destroy(Domain* d)
 {
   PeerCtx* c = d->peer;
   if (!c) return;
-  void* dev[] = {c->send_ent, c->recv_ent, c->send_slot, c->recv_slot, c->hsend, c->hrecv, c->cnt_send, c->cnt_recv};
+  void* dev[] = {c->send_ent, c->recv_ent, c->send_slot, c->recv_slot, c->hsend, c->hrecv, c->cnt_send, c->cnt_recv, c->msend, c->mrecv};
   for (void* p : dev)
     if (p) cudaFree(p);
   if (c->cnt_host) cudaFreeHost(c->cnt_host);
@@ -281,13 +288,23 @@ int peer_exchange_halo(Domain* d, int mode)
     set_error("neighbours on other ranks but no communicator: call nixb200_domain_comm_init first");
     return 1;
   }
-  // bytes per cell in the peer buffers = the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4 reals)
-  const size_t cellb = ((mode == NIXB200_MODE_FIELD) ? d->fcs : 4) * d->esz;
-  const void*  data  = (mode == NIXB200_MODE_FIELD) ? d->uf : d->uj;
-  if (launch_peer_pack(d->geo, mode, data, peer_tabs(d), c->hsend, d->stream, d->fp32)) return 1;
+  // bytes per cell in the peer buffers = the device's own cell layout (E/B: 6 doubles or 8 floats; J: 4 reals;
+  // moments: ns * 14 reals, in buffers of their own that exist only once moments were asked for)
+  const int    ncm   = (int)d->sp.size() * 14;
+  const size_t cellb = ((mode == NIXB200_MODE_FIELD) ? d->fcs : (mode == NIXB200_MODE_MOMENT ? ncm : 4)) * d->esz;
+  const void*  data  = (mode == NIXB200_MODE_FIELD) ? d->uf : (mode == NIXB200_MODE_MOMENT ? d->um : d->uj);
+  void *       sbuf = c->hsend, *rbuf = c->hrecv;
+  if (mode == NIXB200_MODE_MOMENT) {
+    if (!c->msend) {
+      NIX_CUDA(cudaMalloc(&c->msend, cellb * std::max<int64_t>(1, c->send_cell_first.back())));
+      NIX_CUDA(cudaMalloc(&c->mrecv, cellb * std::max<int64_t>(1, c->recv_cell_first.back())));
+    }
+    sbuf = c->msend, rbuf = c->mrecv;
+  }
+  if (launch_peer_pack(d->geo, mode, data, peer_tabs(d), sbuf, d->stream, d->fp32, ncm)) return 1;
   Nccl* n  = nccl();
-  char* hs = reinterpret_cast<char*>(c->hsend);
-  char* hr = reinterpret_cast<char*>(c->hrecv);
+  char* hs = reinterpret_cast<char*>(sbuf);
+  char* hr = reinterpret_cast<char*>(rbuf);
   NIX_NCCL(n->GroupStart());
   for (size_t q = 0; q < c->plan->peers.size(); q++) {
     const int64_t s0 = c->send_cell_first[q], s1 = c->send_cell_first[q + 1];
