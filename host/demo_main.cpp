@@ -13,6 +13,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <fstream>
 
 using namespace nixb200host;
@@ -115,6 +116,28 @@ int main(int argc, char** argv)
       bool same = g2->get_id() == id && g2->order == order && (int)g2->up.size() == ns && g2->uf == g->uf && g2->uj == g->uj;
       for (int is = 0; same && is < ns; is++) same = g2->up[is]->Np == g->up[is]->Np && g2->up[is]->xu == g->up[is]->xu;
       if (!same) throw std::runtime_error("pack/unpack round trip differs for chunk " + std::to_string(id));
+      // the DEVICE-made payload (nixb200_chunk_wire_pack) behind the reference's own header, read back by the
+      // reference's own unpack (nix::Chunk::unpack + XtensorParticle::unpack): same chunk
+      int     hdr = g->nix::Chunk::pack(nullptr, 0);
+      int64_t pay = 0;
+      check(nixb200_chunk_wire_size(dom->h, id, &pay), "wire_size");
+      std::vector<uint8_t> rec((size_t)hdr + pay);
+      g->nix::Chunk::pack(rec.data(), 0);
+      check(nixb200_chunk_wire_pack(dom->h, id, rec.data() + hdr, pay), "wire_pack");
+      auto  c3 = factory.create_chunk(nix::Dims3D{N, N, N}, nix::Bool3D{true, true, true}, 0);
+      auto* g3 = static_cast<GpuChunk*>(c3.get());
+      if (g3->unpack(rec.data(), 0) != hdr + pay) throw std::runtime_error("device wire record: size mismatch");
+      bool wsame = g3->get_id() == id && g3->order == order && (int)g3->up.size() == ns && g3->uf == g->uf && g3->uj == g->uj;
+      for (int is = 0; wsame && is < ns; is++) {
+        auto& a = *g3->up[is];
+        auto& b = *g->up[is];
+        wsame   = a.Np == b.Np && a.Ng == b.Ng && a.q == b.q && a.m == b.m && a.xmin == b.xmin && a.zmax == b.zmax &&
+                a.delx == b.delx && a.Lbx == b.Lbx && a.Ubz == b.Ubz && a.xmax_global == b.xmax_global;
+        for (int ip = 0; wsame && ip < a.Np; ip++)
+          for (int c = 0; c < 7; c++) wsame = wsame && std::memcmp(&a.xu(ip, c), &b.xu(ip, c), 8) == 0;
+        for (int ii = 0; wsame && ii <= a.Ng; ii++) wsame = a.pindex(ii) == b.pindex(ii);
+      }
+      if (!wsame) throw std::runtime_error("device wire record differs for chunk " + std::to_string(id));
     }
     std::printf("ok chunks=%d particles=%lld launches=%lld\n", nchunk, total, (long long)nixb200_launch_count());
   } catch (const std::exception& e) {

@@ -235,6 +235,23 @@ int nixb200_device_count(int* n);
 int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int64_t* particles_sent,
                                 int64_t* particles_received);
 
+/* ---- chunks in the reference's wire format, made on the device; device-to-device rebalance ----
+ * wire_size / wire_pack: the bytes that follow nix::Chunk::pack's own header (chunk.cpp:18-60) in the record of a
+ *   PIC chunk: int order, int ns, uf[Mz][My][Mx][6], uj[Mz][My][Mx][4], then per species XtensorParticle::pack
+ *   (xtensor_particle.hpp:128-169: 29 scalars, xu[Np_total][7], xv, gindex, pindex[Ng+1], pcount[Ng+1][8]; Np_total
+ *   = ((Np + 128) / 128) * 128; xv and gindex -- scratch in the reference as well -- are zero).  `buffer` may be
+ *   host or device memory.  Header + payload is a record the reference's own unpack reads (checkpoints,
+ *   Balancer::sendrecv_chunk).
+ * domain_rebalance: COLLECTIVE over the ranks of the communicator.  boundary = the new rank boundaries (the
+ *   host's unchanged Balancer::assign, balancer.cpp:126-132).  Chunks that change owner travel GPU to GPU over
+ *   NCCL in the wire format above, to rank-1 / rank+1 only (as Balancer::sendrecv_chunk, balancer.hpp:122-332:
+ *   the old and the new range of a rank must overlap); chunks that stay are moved device to device into the
+ *   re-sized arrays.  On return the handle covers [boundary[rank], boundary[rank+1]), rank tables and communicator
+ *   are in place, counts are rebuilt.  Needs old + new arrays at once. */
+int nixb200_chunk_wire_size(nixb200_domain* d, int k, int64_t* bytes);
+int nixb200_chunk_wire_pack(nixb200_domain* d, int k, void* buffer, int64_t bytes);
+int nixb200_domain_rebalance(nixb200_domain* d, int nrank, const int* boundary, int rank);
+
 /* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
  * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only),
  * 5 the k_push launches of phase 0 alone, 6 its k_deposit launches alone (one call = one launch = one species),

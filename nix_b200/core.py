@@ -37,6 +37,7 @@ SYMBOLS = [
     "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp", "nixb200_comm_create", "nixb200_comm_destroy",
     "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
+    "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -144,6 +145,9 @@ def load_library():
     sig("nixb200_chunk_pack_moment", I, P, I, I, I, PD, PL)
     sig("nixb200_chunk_pack_tracer", I, P, I, I, PD, C.c_int64, PL)
     sig("nixb200_shape_eval", I, I, I, I, I, PD, PD, D, D, D, PD)
+    sig("nixb200_chunk_wire_size", I, P, I, PL)
+    sig("nixb200_chunk_wire_pack", I, P, I, P, C.c_int64)
+    sig("nixb200_domain_rebalance", I, P, I, PI, I)
     sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
     sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib
@@ -274,6 +278,21 @@ class Domain:
         dist.broadcast(t, src=0, group=group)
         raw = bytes(t.cpu().tolist())
         self._ck(self.lib.nixb200_domain_comm_init(self.h, C.c_char_p(raw)))
+
+    def rebalance(self, boundary, rank):
+        """Collective: move to the new rank boundaries; chunks travel GPU to GPU in the reference's wire format."""
+        bd = np.ascontiguousarray(boundary, dtype=np.int32)
+        self._ck(self.lib.nixb200_domain_rebalance(self.h, len(bd) - 1, bd.ctypes.data_as(C.POINTER(C.c_int)), int(rank)))
+        self.id_begin, self.id_end = int(bd[rank]), int(bd[rank + 1])
+        self.nchunk = self.id_end - self.id_begin
+
+    def wire_pack(self, k):
+        """payload of chunk k in the reference's wire format (bytes after nix::Chunk::pack's header)"""
+        n = C.c_int64(0)
+        self._ck(self.lib.nixb200_chunk_wire_size(self.h, k, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        self._ck(self.lib.nixb200_chunk_wire_pack(self.h, k, buf.ctypes.data_as(C.c_void_p), n.value))
+        return buf
 
     def peer_traffic(self):
         a, b, c = C.c_int64(0), C.c_int64(0), C.c_int64(0)

@@ -113,7 +113,7 @@ static int alloc_leavers(Domain* d, SpeciesDev& s, int64_t lcap)
   return 0;
 }
 
-static int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
+int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
 {
   void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.paysend, s.payrecv};
   for (void* p : old)
@@ -272,6 +272,19 @@ static int ensure_capacity(Domain* d)
   }
   return 0;
 }
+// device staging shared by the packers and the chunk wire format
+int pack_scratch(Domain* d, size_t bytes)
+{
+  if (!d->count_dev) NIX_CUDA(cudaMalloc(&d->count_dev, sizeof(int)));
+  if (bytes <= d->pack_bytes) return 0;
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  if (d->pack_dev) cudaFree(d->pack_dev);
+  d->pack_dev = nullptr, d->pack_bytes = 0;
+  NIX_CUDA(cudaMalloc(&d->pack_dev, bytes));
+  d->pack_bytes = bytes;
+  return 0;
+}
+
 } // namespace nixb200
 
 using namespace nixb200;
@@ -1081,18 +1094,6 @@ int nixb200_domain_set_strict_fp(nixb200_domain* dd, int on)
 }
 
 // ---- diagnostics / output (diag.cu) ---------------------------------------------------------------------
-static int pack_scratch(Domain* d, size_t bytes)
-{
-  if (!d->count_dev) NIX_CUDA(cudaMalloc(&d->count_dev, sizeof(int)));
-  if (bytes <= d->pack_bytes) return 0;
-  NIX_CUDA(cudaStreamSynchronize(d->stream));
-  if (d->pack_dev) cudaFree(d->pack_dev);
-  d->pack_dev = nullptr, d->pack_bytes = 0;
-  NIX_CUDA(cudaMalloc(&d->pack_dev, bytes));
-  d->pack_bytes = bytes;
-  return 0;
-}
-
 static size_t moment_chunk_values(const Domain* d)
 {
   return d->cells_per_chunk * d->sp.size() * 14;

@@ -106,6 +106,16 @@ int grow_particles(Domain* d, SpeciesDev& s, int64_t newcap);           // keeps
 int grow_leavers(Domain* d, SpeciesDev& s, int64_t newlcap, bool keep); // keep: lrec survives
 int record_stats(Domain* d);
 
+int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot); // (re)sizes the stores of one species
+int pack_scratch(Domain* d, size_t bytes);                           // d->pack_dev, grown on demand
+
+// peer.cu: raw transport for rebalance.cu
+void* peer_comm(const Domain* d);
+bool  peer_take_comm(Domain* d, void** comm); // detach the communicator from d (returns whether d owned it)
+int   peer_give_comm(Domain* d, void* comm, bool own);
+int   peer_sendrecv_bytes(void* comm, cudaStream_t st, int n, const int* ranks, const void* const* sbuf, const size_t* sbytes,
+                          void* const* rbuf, const size_t* rbytes);
+
 // peer.cu
 PeerTabs peer_tabs(const Domain* d);
 void     peer_destroy(Domain* d);

@@ -411,6 +411,52 @@ int peer_migrate(Domain* d)
   return 0;
 }
 
+void* peer_comm(const Domain* d)
+{
+  return d->peer ? d->peer->comm : nullptr;
+}
+
+bool peer_take_comm(Domain* d, void** comm)
+{
+  *comm = nullptr;
+  if (!d->peer) return false;
+  *comm          = d->peer->comm;
+  const bool own = d->peer->own_comm;
+  d->peer->comm     = nullptr;
+  d->peer->own_comm = false;
+  return own;
+}
+
+int peer_give_comm(Domain* d, void* comm, bool own)
+{
+  if (!d->peer) {
+    set_error("no rank partition on this domain");
+    return 1;
+  }
+  d->peer->comm     = reinterpret_cast<ncclComm_t>(comm);
+  d->peer->own_comm = own;
+  return 0;
+}
+
+// n messages each way inside one NCCL group (a rank of MPI_PROC_NULL-like value < 0 is skipped)
+int peer_sendrecv_bytes(void* comm, cudaStream_t st, int nmsg, const int* ranks, const void* const* sbuf, const size_t* sbytes,
+                        void* const* rbuf, const size_t* rbytes)
+{
+  Nccl* n = nccl();
+  if (!n || !comm) {
+    set_error("no NCCL communicator");
+    return 1;
+  }
+  NIX_NCCL(n->GroupStart());
+  for (int q = 0; q < nmsg; q++) {
+    if (ranks[q] < 0) continue;
+    if (sbytes[q]) NIX_NCCL(n->Send(sbuf[q], sbytes[q], ncclChar, ranks[q], reinterpret_cast<ncclComm_t>(comm), st));
+    if (rbytes[q]) NIX_NCCL(n->Recv(rbuf[q], rbytes[q], ncclChar, ranks[q], reinterpret_cast<ncclComm_t>(comm), st));
+  }
+  NIX_NCCL(n->GroupEnd());
+  return 0;
+}
+
 static int peer_setup(Domain* d, Plan* plan)
 {
   peer_destroy(d);

@@ -240,3 +240,108 @@ def _growth_worker(rank, world, port, reserve, q):
 @pytest.mark.parametrize("reserve", [True, False])
 def test_two_ranks_particle_store_growth(oracle_port, gpu_lib, reserve):
     _run_ranks(2, _growth_worker, (reserve,))
+
+
+def _rebalance_worker(rank, world, port, fp32, q):
+    """Rank boundaries move twice during a run (chunks travel GPU to GPU in the reference's wire format,
+    nixb200_domain_rebalance); after every step every rank still equals the single-process oracle."""
+    try:
+        import torch
+        import torch.distributed as dist
+        from nix_b200 import core
+        from oracle import nixoracle as no
+        from helpers import oracle_domain
+        torch.cuda.set_device(rank)
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        prob = Problem((2, 2, 4), (8, 8, 8), 2, ppc=8, seed=123, vth=(0.35, 0.08),
+                       density=lambda c, cd: 1.0 + 0.8 * np.sin(2 * np.pi * (c[2] + 0.5) / cd[2]))
+        n = prob.nchunk
+        plans = {2: [[0, 8, 16], [0, 5, 16], [0, 11, 16]],
+                 4: [[0, 4, 8, 12, 16], [0, 3, 9, 11, 16], [0, 5, 8, 13, 16]]}[world]
+        bd = plans[0]
+        ids = list(range(bd[rank], bd[rank + 1]))
+        gd = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord,
+                         id_range=(ids[0], ids[-1] + 1), device=rank, strict_fp=not fp32, fp32=fp32)
+        gd.set_ranks(bd, rank)
+        gd.comm_init_torch()
+        _load(gd, prob, ids)
+        od = oracle_domain(no.load("port"), prob)
+        step = 0
+        for phase, bd in enumerate(plans):
+            if phase > 0:
+                gd.rebalance(bd, rank)
+                ids = list(range(bd[rank], bd[rank + 1]))
+                assert gd.nchunk == len(ids)
+                if not fp32:
+                    _compare(rank, prob, od, gd, ids, f"after rebalance {phase}")
+            for _ in range(2):
+                od.step(0.5, 1.0)
+                gd.step(0.5)
+                assert gd.check() == 0, f"rank {rank}: device error bits"
+                if not fp32:
+                    _compare(rank, prob, od, gd, ids, f"phase {phase} step {step}")
+                step += 1
+        tot = torch.tensor([gd.total_particles()], dtype=torch.int64)
+        dist.all_reduce(tot)
+        assert int(tot[0]) == od.total_particles()
+        if fp32:
+            for k, i in enumerate(ids):
+                c = od.chunks[i]
+                assert np.abs(gd.get_current(k) - c.uj).max() / np.abs(c.uj).max() < 1e-2
+                for s in range(prob.ns):
+                    assert abs(len(gd.get_particles(k, s)) - len(c.particles(s))) <= 2
+        gd.close()
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok"))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: " + "".join(traceback.format_exception(exc))))
+
+
+@pytest.mark.parametrize("world,fp32", [(2, False), (4, False), (2, True)])
+def test_device_to_device_rebalance(oracle_port, gpu_lib, world, fp32):
+    _run_ranks(world, _rebalance_worker, (fp32,))
+
+
+def test_single_rank_rebalance_and_wire_record(oracle_port, gpu_lib):
+    """nrank = 1: the rebuild path alone (nothing moves) keeps the state bit for bit; the wire payload has the
+    size the reference's XtensorParticle::pack has for the same particle counts (the content is checked through
+    the reference's own unpack in tests/test_host_cpp.py::test_demo_equals_oracle)."""
+    from nix_b200 import core
+    from helpers import oracle_domain
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=8, seed=5, vth=(0.35, 0.08))
+    od = oracle_domain(oracle_port, prob)
+    gd = core.Domain(prob.cdims, prob.dims, prob.nb, prob.order, prob.q, prob.m, coord=prob.coord, strict_fp=True)
+    gd.set_ranks([0, prob.nchunk], 0)
+    _load(gd, prob, list(range(prob.nchunk)))
+    for step in range(2):
+        od.step(0.5, 1.0)
+        gd.step(0.5)
+    gd.rebalance([0, prob.nchunk], 0)
+    _compare(0, prob, od, gd, list(range(prob.nchunk)), "after a no-op rebalance")
+    od.step(0.5, 1.0)
+    gd.step(0.5)
+    _compare(0, prob, od, gd, list(range(prob.nchunk)), "step after it")
+    cells = int(np.prod(gd.M))
+    for k, c in enumerate(od.chunks):
+        w = gd.wire_pack(k)
+        want = 8 + cells * 10 * 8
+        for s in range(prob.ns):
+            npt = ((c.np(s) + 128) // 128) * 128
+            want += 175 + npt * 7 * 8 * 2 + npt * 4 + (cells + 1) * 4 + (cells + 1) * 8 * 4
+        assert len(w) == want
+        assert np.frombuffer(w[:8].tobytes(), dtype=np.int32).tolist() == [prob.order, prob.ns]
+        uf = np.frombuffer(w[8:8 + cells * 48].tobytes(), dtype=np.float64).reshape(c.uf.shape)
+        assert np.array_equal(uf, c.uf)
+        off = 8 + cells * 80
+        for s in range(prob.ns):
+            hdr = w[off:off + 175].tobytes()
+            npt, npp, ng = np.frombuffer(hdr[:12], dtype=np.int32)
+            assert npp == c.np(s) and ng == cells
+            xu = np.frombuffer(w[off + 175:off + 175 + npt * 56].tobytes(), dtype=np.float64).reshape(npt, 7)
+            assert np.array_equal(xu[:npp].view(np.int64), c.particles(s).view(np.int64))
+            pidx = np.frombuffer(w[off + 175 + npt * 116:off + 175 + npt * 116 + (cells + 1) * 4].tobytes(), dtype=np.int32)
+            assert np.array_equal(pidx, c.pindex(s))
+            off += 175 + npt * 116 + (cells + 1) * 36
+    gd.close()
