@@ -276,6 +276,8 @@ int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const Peer
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
                 cudaStream_t st, bool fp32);
 size_t scan_tmp_bytes(size_t n);
+int launch_hist_from_start(const int32_t* start, int32_t* hist, size_t n, cudaStream_t st);
+int launch_scan_only(const Geo& g, SpeciesDev& sp, int* err, void* scan_tmp, cudaStream_t st);
 
 int launch_halo_field(const Geo& g, const ChunkGeo* cg, void* uf, const PeerTabs& pt, const void* recvbuf,
                       cudaStream_t st, bool fp32);

@@ -192,6 +192,10 @@ int wire_unpack_chunk(Domain* nd, int k, const WireLayout& w, const unsigned cha
   for (size_t is = 0; is < nd->sp.size(); is++) {
     const WireSpecies& s  = w.sp[is];
     SpeciesDev&        sd = nd->sp[is];
+    // per-(cell, lane) counts as the sender's last count() left them (pcount rows [0, ncell) and row Ng)
+    const size_t nk = (size_t)nd->geo.ncell * LANES;
+    if (dev_copy(sd.hist + (size_t)k * nk, wire + s.pcount, nk * 4, nd->stream)) return 1;
+    if (dev_copy(sd.oob + (size_t)k * LANES, wire + s.pcount + cells * LANES * 4, LANES * 4, nd->stream)) return 1;
     if (s.np == 0) continue;
     if (dev_copy(nd->pack_dev, wire + s.xu, (size_t)s.np * NC * 8, nd->stream)) return 1;
     if (nd->fp32) {
@@ -393,6 +397,14 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
       NIX_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(s.xu) + ((size_t)c * s.cap + dst0) * d->esz,
                                reinterpret_cast<char*>(d->sp[is].xu) + ((size_t)c * d->sp[is].cap + src0) * d->esz,
                                (size_t)nkeep * d->esz, cudaMemcpyDeviceToDevice, d->stream));
+    // ... and their per-(cell, lane) counts and out-of-bounds rows (NOT a re-sort: the key of the reference's sort
+    // is cell * 8 + position % 8, so sorting a sorted container regroups the lanes)
+    const size_t nk = (size_t)d->geo.ncell * LANES;
+    if (launch_hist_from_start(d->sp[is].start + (size_t)(keep0 - b0) * nk, s.hist + (size_t)(keep0 - b1) * nk,
+                               (size_t)(keep1 - keep0) * nk, d->stream))
+      return 1;
+    NIX_CUDA(cudaMemcpyAsync(s.oob + (size_t)(keep0 - b1) * LANES, d->sp[is].oob + (size_t)(keep0 - b0) * LANES,
+                             sizeof(int32_t) * LANES * (keep1 - keep0), cudaMemcpyDeviceToDevice, d->stream));
   }
   for (int which = 0; which < 2; which++) { // kept chunks: E/B and J
     const size_t cb_ = d->cells_per_chunk * (which == 0 ? d->fcs : 4) * d->esz;
@@ -412,6 +424,12 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
       if (wire_unpack_chunk(nd, id - b1, wr[j], rbuf + off, first.data())) return 1;
       off += wr[j].total;
     }
+  }
+  // scan of the counts -> start / chunk bases of the new domain (the particles are where they belong already)
+  for (int is = 0; is < ns; is++) {
+    SpeciesDev& s = nd->sp[is];
+    if (launch_scan_only(nd->geo, s, nd->err_dev, nd->scan_tmp, d->stream)) return 1;
+    std::swap(s.cbase, s.cbase_new); // (equal to the bases laid out above)
   }
   NIX_CUDA(cudaStreamSynchronize(d->stream));
   cudaFree(sbuf);
@@ -434,9 +452,7 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
   d->particles_set = true;
   if (nixb200_domain_set_ranks(dd, nrank, boundary, rank)) return 1;
   if (comm && peer_give_comm(d, comm, own)) return 1;
-  // ghosts of the arrived chunks' neighbours, and the count / scan tables of every chunk
-  if (nixb200_domain_exchange_field(dd)) return 1;
-  return nixb200_domain_sort(dd);
+  return 0;
 }
 
 } // extern "C"

@@ -601,6 +601,41 @@ int launch_mig_recv(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, const Peer
   return 0;
 }
 
+// counts of a key range recovered from a scan (rebalance.cu: the chunks that stay keep their per-(cell, lane)
+// counts; re-sorting them would regroup the lanes, the reference's key being cell * 8 + position % 8)
+__global__ void k_hist_from_start(const int32_t* __restrict__ start, int32_t* __restrict__ hist, size_t n)
+{
+  for (size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (size_t)gridDim.x * blockDim.x)
+    hist[j] = start[j + 1] - start[j];
+}
+
+int launch_hist_from_start(const int32_t* start, int32_t* hist, size_t n, cudaStream_t st)
+{
+  if (n == 0) return 0;
+  k_hist_from_start<<<grid_for(n, 256), 256, 0, st>>>(start, hist, n);
+  NIX_LAUNCHED();
+  return 0;
+}
+
+// hist -> start and the chunk bases only (no particle moves); hist is cleared afterwards, as a sort leaves it
+int launch_scan_only(const Geo& g, SpeciesDev& sp, int* err, void* scan_tmp, cudaStream_t st)
+{
+  const size_t n     = (size_t)g.nchunk * g.ncell * LANES;
+  const int    nblk  = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+  int32_t*     bsum  = reinterpret_cast<int32_t*>(scan_tmp);
+  int32_t*     total = bsum + nblk;
+  k_scan_reduce<<<nblk, SCAN_THREADS, 0, st>>>(sp.hist, n, bsum);
+  NIX_LAUNCHED();
+  k_scan_bsum<<<1, 1024, 0, st>>>(bsum, nblk, total);
+  NIX_LAUNCHED();
+  k_scan_apply<<<nblk, SCAN_THREADS, 0, st>>>(sp.hist, n, bsum, sp.start);
+  NIX_LAUNCHED();
+  k_chunk_bases<<<(g.nchunk + 1 + 255) / 256, 256, 0, st>>>(g, sp, total, err);
+  NIX_LAUNCHED();
+  NIX_CUDA(cudaMemsetAsync(sp.hist, 0, sizeof(int32_t) * n, st));
+  return 0;
+}
+
 // hist -> start, place, scatter; leaves the sorted particles in sp.xv and the new chunk bases in
 // sp.cbase_new (the caller swaps, xtensor_particle.hpp:317)
 int launch_sort(const Geo& g, const ChunkGeo* cg, SpeciesDev& sp, int* err, void* scan_tmp,
