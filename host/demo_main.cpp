@@ -10,6 +10,7 @@
 //
 // tests/test_host_cpp.py compares the outputs with the CPU oracle (bit-exact particles).
 #include "nixb200_host.hpp"
+#include "balancer.hpp"
 
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +45,26 @@ int main(int argc, char** argv)
       auto [cz, cy, cx] = cm.get_coordinate(id);
       std::printf("%d %d %d\n", cz, cy, cx);
     }
+    return 0;
+  }
+  if (argc >= 4 && std::string(argv[1]) == "assign") {
+    // demo assign <nrank> <initial|step> load0 load1 ... [-- b0 b1 ... b_nrank]: the reference's own Balancer
+    // (balancer.cpp:8-132) on a load vector -> the new rank boundaries (golden vectors for nix_b200/balancer.py)
+    const int            nrank = atoi(argv[2]);
+    const bool           init  = std::string(argv[3]) == "initial";
+    std::vector<double>  load;
+    std::vector<int>     boundary;
+    bool                 second = false;
+    for (int i = 4; i < argc; i++) {
+      if (std::string(argv[i]) == "--") second = true;
+      else if (second) boundary.push_back(atoi(argv[i]));
+      else load.push_back(atof(argv[i]));
+    }
+    nix::Balancer bal((int)load.size());
+    for (size_t i = 0; i < load.size(); i++) bal.load(i) = load[i];
+    std::vector<int> out = init ? bal.assign_initial(nrank) : bal.assign(boundary);
+    for (int b : out) std::printf("%d ", b);
+    std::printf("\n");
     return 0;
   }
   if (argc < 12 || std::string(argv[1]) != "run") {
