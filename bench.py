@@ -57,6 +57,13 @@ CONFIGS = {
                  q=(-1.0, -1.0), m=(1.0, 1.0),
                  label="Weibel: 256^3 cells per GPU as 512 chunks of 32^3, two counter-streaming electron species "
                        "u_z = +-0.5 c, 48 ppc (2 x 24), order 3, nb 3, fp64"),
+    # configs[4]: weak scaling with a non-uniform density n(x) = 1 + 0.8 sin(2 pi x / Lx) and SFC rebalancing
+    # (Balancer::assign, balancer.cpp:8-72,126-132; chunks shipped GPU to GPU by nixb200_domain_rebalance).
+    # 16 ppc on average instead of 32: the rank in the dense half starts with 1.5x the mean and a rebalance
+    # holds the old and the new arrays at once
+    "cfg5": dict(cdims=(8, 8, 8), dims=(32, 32, 32), order=2, ppc=8, ns=2, vth=(0.1, 0.02), drift=None, sine=0.8,
+                 label="256^3 cells per GPU as 512 chunks of 32^3, density 1 + 0.8 sin(2 pi x / Lx), 16 ppc on average "
+                       "(2 species x 8), order 2, fp64, rank boundaries rebalanced along the Gilbert curve"),
 }
 
 
@@ -100,16 +107,27 @@ def global_box(cd, world):
     return gcd, chunk_coords(gcd)
 
 
+def chunk_counts(prob, w, ids):
+    """particles per chunk and species: uniform, or following 1 + a sin(2 pi x / Lx) at the chunk's centre"""
+    n = prob.ncell() * prob.ppc
+    if not w.get("sine"):
+        return np.full(len(ids), n, dtype=np.int64)
+    xc = np.array([(prob.coord[k][2] + 0.5) / prob.cdims[2] for k in ids])
+    return np.maximum(1, np.rint(n * (1.0 + w["sine"] * np.sin(2 * np.pi * xc)))).astype(np.int64)
+
+
 def device_particles(torch, prob, w, ids, s, seed):
     """Synthetic particles of species s for the chunks `ids`, generated on the device (the large configs would
     spend minutes in numpy): uniform positions inside each chunk, Gaussian momenta, optional drift along z."""
     gen = torch.Generator(device="cuda")
     gen.manual_seed(seed * 1000 + s)
-    n = prob.ncell() * prob.ppc
     dims = torch.tensor(prob.dims, dtype=torch.float64, device="cuda")
-    out = torch.empty((len(ids) * n, 7), dtype=torch.float64, device="cuda")
+    counts = chunk_counts(prob, w, ids)
+    first = np.concatenate([[0], np.cumsum(counts)])
+    out = torch.empty((int(first[-1]), 7), dtype=torch.float64, device="cuda")
     for j, k in enumerate(ids):
-        o = out[j * n:(j + 1) * n]
+        n = int(counts[j])
+        o = out[int(first[j]):int(first[j + 1])]
         lo = torch.tensor([float(prob.coord[k][a] * prob.dims[a]) for a in range(3)], dtype=torch.float64, device="cuda")
         u = torch.rand((n, 3), dtype=torch.float64, device="cuda", generator=gen) * (1.0 - 1e-12)
         o[:, 0] = lo[2] + u[:, 0] * dims[2]
@@ -320,7 +338,7 @@ def run_gpu(args):
             else:
                 t = device_particles(torch, prob, w, ids, s, seed=2024)
                 torch.cuda.synchronize()
-                dm.set_particles_ptr(s, t.data_ptr(), np.full(nchunk, npc, dtype=np.int64))
+                dm.set_particles_ptr(s, t.data_ptr(), chunk_counts(prob, w, ids))
                 del t
                 torch.cuda.empty_cache()
         dm.sort()
@@ -345,6 +363,11 @@ def run_gpu(args):
     if err:
         raise SystemExit(f"bench.py: device error bits {err} during warm-up")
 
+    rebal = None
+    skip_e2e = False
+    if w["name"] == "cfg5":
+        args.no_fp32 = True
+
     def timed_steps(nsteps, fn):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -354,6 +377,50 @@ def run_gpu(args):
         e1.record(stream)
         barrier()
         return e0.elapsed_time(e1)
+
+    if w["name"] == "cfg5" and world > 1:
+        # imbalanced start (uniform boundaries over a non-uniform density), then rounds of
+        # Balancer::assign on the per-chunk particle counts + device-to-device chunk shipping
+        from nix_b200 import balancer
+        ms_before = timed_steps(args.steps, lambda: dom.step(dt))
+        n_before = dom.total_particles()
+        bnow = [int(v) for v in bd]
+        rounds, moved = 0, 0
+        tr0 = time.perf_counter()
+        for _ in range(12):
+            mine = torch.zeros(prob.nchunk, dtype=torch.float64, device="cuda")
+            mine[bnow[rank]:bnow[rank + 1]] = torch.tensor(sum(dom.get_np(s) for s in range(prob.ns)), dtype=torch.float64)
+            dist.all_reduce(mine)
+            bnew = balancer.assign(mine.cpu().numpy(), bnow)
+            if bnew == bnow:
+                break
+            moved += sum(abs(a - b) for a, b in zip(bnew, bnow))
+            dom.rebalance(bnew, rank)
+            bnow = bnew
+            rounds += 1
+        torch.cuda.synchronize()
+        t_rebal = time.perf_counter() - tr0
+        nchunk = dom.nchunk
+        ids = list(range(bnow[rank], bnow[rank + 1]))
+        for _ in range(2):
+            dom.step(dt)
+        nmax = torch.tensor([float(n_before), float(dom.total_particles())], dtype=torch.float64, device="cuda")
+        nmin = nmax.clone()
+        dist.all_reduce(nmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nmin, op=dist.ReduceOp.MIN)
+        tb = torch.tensor([ms_before], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        rebal = {"rounds": rounds, "chunks_moved": int(moved), "seconds": t_rebal, "boundary": bnow,
+                 "ms_per_step_before": float(tb[0]) / args.steps,
+                 "particles_per_rank_before": [float(nmin[0]), float(nmax[0])],
+                 "particles_per_rank_after": [float(nmin[1]), float(nmax[1])]}
+        ntot = dom.total_particles()
+        # the pinned host mirrors follow the new chunk count; they start from the fields the device holds
+        ufi_host = torch.empty((nchunk, icells, 6), dtype=torch.float64, pin_memory=True)
+        uji_host = torch.empty((nchunk, icells, 4), dtype=torch.float64, pin_memory=True)
+        dom.interior_download_overlapped(core.FIELD_UF, ufi_host.data_ptr())
+        dom.copy_synchronize()
+        skip_e2e = True  # (= do not reset the host mirror from the initial condition)
 
     # ---- timed region: K device-resident steps ----
     try:
@@ -411,8 +478,9 @@ def run_gpu(args):
 
     # ---- the round-1 flavour for comparison: HOST-side field solver, interior E/B up and interior J down
     #      every step on a second stream (what the device-side solver removes) ----
-    ufi_host.numpy()[...] = ufn.reshape((nchunk,) + tuple(prob.M) + (6,))[
-        :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
+    if not skip_e2e:
+        ufi_host.numpy()[...] = ufn.reshape((nchunk,) + tuple(prob.M) + (6,))[
+            :, nbh:nbh + prob.dims[0], nbh:nbh + prob.dims[1], nbh:nbh + prob.dims[2]].reshape(nchunk, icells, 6)
     barrier()
     e4, e5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e4.record(stream)
@@ -564,6 +632,7 @@ def run_gpu(args):
                                  "and issue latency and k_push by the shared-memory data pipe, not by HBM "
                                  "(DESIGN.md 3.2, SURVEY.md 8d): fp64_frac = fp64 warp instructions x 32 / time / "
                                  "measured DFMA peak"},
+            "rebalance": rebal,
             "phases_ms_per_step": {k: (v[0] / args.steps) for k, v in phases.items()},
             "phases_ms_per_step_e2e": {k: (v[0] / args.steps) for k, v in phases_e2e.items()},
             "field_energy_last": [float(energies[-1, :, 0].sum()), float(energies[-1, :, 1].sum())],
