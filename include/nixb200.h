@@ -165,6 +165,10 @@ int nixb200_domain_push_bfd(nixb200_domain* d, double delt, int ext);
 int nixb200_domain_push_efd(nixb200_domain* d, double delt, double cfj);
 int nixb200_domain_step_em(nixb200_domain* d, double delt, double cfj);
 int nixb200_domain_field_energy(nixb200_domain* d, double* host_e2b2);
+/* the per-step history read-back without stalling the device: field energies [nchunk][2] and particle counts
+ * [ns][nchunk] (int64) arrive in caller-provided PINNED host memory in stream order (either pointer may be NULL);
+ * read them after nixb200_domain_synchronize or any later call that synchronises */
+int nixb200_domain_history_async(nixb200_domain* d, double* host_e2b2, int64_t* host_np);
 /* 1: push arithmetic without FMA contraction (bit-identical to the reference's scalar templates), 0: contracted */
 int nixb200_domain_set_strict_fp(nixb200_domain* d, int on);
 

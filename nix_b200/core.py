@@ -37,7 +37,7 @@ SYMBOLS = [
     "nixb200_domain_field_energy", "nixb200_domain_set_strict_fp", "nixb200_comm_create", "nixb200_comm_destroy",
     "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
-    "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance",
+    "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance", "nixb200_domain_history_async",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -139,6 +139,7 @@ def load_library():
     sig("nixb200_domain_step_em", I, P, D, D)
     sig("nixb200_domain_field_energy", I, P, PD)
     sig("nixb200_domain_set_strict_fp", I, P, I)
+    sig("nixb200_domain_history_async", I, P, P, P)
     sig("nixb200_domain_deposit_moment", I, P)
     sig("nixb200_chunk_moment_download", I, P, I, PD)
     sig("nixb200_chunk_pack_field", I, P, I, I, PD, PL)
@@ -439,6 +440,11 @@ class Domain:
         out = np.zeros((self.nchunk, 2), dtype=np.float64)
         self._ck(self.lib.nixb200_domain_field_energy(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
+
+    def history_async(self, e2b2_ptr, np_ptr):
+        """field energies [nchunk][2] f64 and particle counts [ns][nchunk] i64 into PINNED host memory, in stream
+        order, without synchronising (addresses; 0 / None skips one)"""
+        self._ck(self.lib.nixb200_domain_history_async(self.h, C.c_void_p(int(e2b2_ptr or 0)), C.c_void_p(int(np_ptr or 0))))
 
     def set_strict_fp(self, on):
         self._ck(self.lib.nixb200_domain_set_strict_fp(self.h, int(bool(on))))

@@ -315,6 +315,7 @@ int launch_aos_to_soa_f32(const double* aos, float* soa_base, size_t cap, size_t
 int launch_soa_to_aos_f32(const float* soa_base, double* aos, size_t cap, size_t first, size_t n, const double* origin3,
                           cudaStream_t st);
 int launch_cells_convert(bool to_dev, double* host_layout, float* dev_layout, size_t ncell, int nc, int fc, cudaStream_t st);
+int launch_np_from_cbase(const int32_t* cbase, int nch, int64_t* np, cudaStream_t st);
 int launch_interior_f32(bool pack, float* full, double* dense, const Geo& g, int ncomp, int fc, cudaStream_t st);
 int launch_aos_to_soa(const double* aos, double* soa_base, size_t cap, size_t first, size_t n,
                       cudaStream_t st);

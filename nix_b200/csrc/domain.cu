@@ -552,6 +552,7 @@ int nixb200_domain_destroy(nixb200_domain* dd)
   if (d->err_dev) cudaFree(d->err_dev);
   if (d->stat_dev) cudaFree(d->stat_dev);
   if (d->energy_dev) cudaFree(d->energy_dev);
+  if (d->np_dev) cudaFree(d->np_dev);
   if (d->origin_dev) cudaFree(d->origin_dev);
   if (d->um) cudaFree(d->um);
   if (d->pack_dev) cudaFree(d->pack_dev);
@@ -1083,6 +1084,28 @@ int nixb200_domain_field_energy(nixb200_domain* dd, double* host_e2b2)
   if (launch_field_energy(d->geo, d->uf, d->energy_dev, d->stream, d->fp32)) return 1;
   NIX_CUDA(cudaMemcpyAsync(host_e2b2, d->energy_dev, sizeof(double) * 2 * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
   NIX_CUDA(cudaStreamSynchronize(d->stream));
+  return 0;
+}
+
+// History diagnostics without a host round trip per step: field energies [nchunk][2] and particle counts
+// [ns][nchunk] (int64) are written to caller-provided PINNED host memory in stream order; the caller reads them
+// after nixb200_domain_synchronize (or any later synchronising call).
+int nixb200_domain_history_async(nixb200_domain* dd, double* host_e2b2, int64_t* host_np)
+{
+  NIX_ENTER(dd);
+  if (host_e2b2) {
+    if (wait_copy(d, 0)) return 1;
+    if (!d->energy_dev) NIX_CUDA(cudaMalloc(&d->energy_dev, sizeof(double) * 2 * d->geo.nchunk));
+    if (launch_field_energy(d->geo, d->uf, d->energy_dev, d->stream, d->fp32)) return 1;
+    NIX_CUDA(cudaMemcpyAsync(host_e2b2, d->energy_dev, sizeof(double) * 2 * d->geo.nchunk, cudaMemcpyDeviceToHost, d->stream));
+  }
+  if (host_np) {
+    const int nch = d->geo.nchunk;
+    if (!d->np_dev) NIX_CUDA(cudaMalloc(&d->np_dev, sizeof(int64_t) * nch * d->sp.size()));
+    for (size_t is = 0; is < d->sp.size(); is++)
+      if (launch_np_from_cbase(d->sp[is].cbase, nch, d->np_dev + is * nch, d->stream)) return 1;
+    NIX_CUDA(cudaMemcpyAsync(host_np, d->np_dev, sizeof(int64_t) * nch * d->sp.size(), cudaMemcpyDeviceToHost, d->stream));
+  }
   return 0;
 }
 

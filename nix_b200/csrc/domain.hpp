@@ -39,6 +39,7 @@ struct Domain {
   int32_t*                stat_host    = nullptr; // pinned [ns][4]
   int32_t*                stat_dev     = nullptr; // device [ns][4]
   double*                 energy_dev   = nullptr; // device [nchunk][2]
+  int64_t*                np_dev       = nullptr; // device [ns][nchunk]
   cudaEvent_t             ev_stat      = nullptr;
   bool                    stat_pending = false;
   CUtensorMap             tmap;

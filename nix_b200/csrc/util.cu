@@ -223,6 +223,22 @@ int launch_interior_f32(bool pack, float* full, double* dense, const Geo& g, int
   return 0;
 }
 
+namespace
+{
+__global__ void k_np_from_cbase(const int32_t* __restrict__ cbase, int nch, int64_t* __restrict__ np)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < nch) np[k] = (int64_t)cbase[k + 1] - cbase[k];
+}
+} // namespace
+
+int launch_np_from_cbase(const int32_t* cbase, int nch, int64_t* np, cudaStream_t st)
+{
+  k_np_from_cbase<<<(nch + 255) / 256, 256, 0, st>>>(cbase, nch, np);
+  NIX_LAUNCHED();
+  return 0;
+}
+
 int launch_interior(bool pack, double* full, double* dense, const Geo& g, int ncomp, cudaStream_t st)
 {
   const int    nc2 = ncomp / 2;

@@ -97,3 +97,24 @@ def test_gauss_law_and_div_b_at_scale(gpu_lib):
         prev = res
     assert gd.total_particles() == ntot
     gd.close()
+
+
+def test_history_read_back_without_synchronising(gpu_lib):
+    """nixb200_domain_history_async: field energies and per-chunk particle counts of every step arrive in pinned
+    host memory in stream order; after one synchronise they equal what the blocking calls return."""
+    import torch
+    prob = Problem((2, 2, 2), (8, 8, 8), 2, ppc=6, seed=3, vth=(0.3, 0.05))
+    gd = gpu_domain(prob, strict=True)
+    steps = 3
+    e = torch.zeros((steps, gd.nchunk, 2), dtype=torch.float64, pin_memory=True)
+    n = torch.zeros((steps, prob.ns, gd.nchunk), dtype=torch.int64, pin_memory=True)
+    for k in range(steps):
+        gd.step_em(0.5, 0.05)
+        gd.history_async(e[k].data_ptr(), n[k].data_ptr())
+    gd.synchronize()
+    assert np.array_equal(e[-1].numpy(), gd.field_energy())
+    for s in range(prob.ns):
+        assert np.array_equal(n[-1, s].numpy(), gd.get_np(s))
+    assert (n.sum(dim=(1, 2)) == prob.total_particles()).all()
+    assert (e[0] != e[1]).any()
+    gd.close()
