@@ -113,17 +113,36 @@ static int alloc_leavers(Domain* d, SpeciesDev& s, int64_t lcap)
   return 0;
 }
 
-int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
+// everything of a species that carries no state between steps (the temporary array, keys, member lists,
+// migration buffers): a rebalance frees it first and re-creates it last to keep its peak memory down
+void free_species_scratch(SpeciesDev& s)
 {
-  void* old[] = {s.xu, s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.paysend, s.payrecv};
+  void* old[] = {s.xv, s.key, s.ordl, s.lrec, s.msg, s.msgkey, s.paysend, s.payrecv};
   for (void* p : old)
     if (p) cudaFree(p);
-  s.xu = s.xv = nullptr;
+  s.xv = nullptr;
   s.key = s.ordl = nullptr;
   s.lrec = nullptr;
   s.msg = nullptr;
   s.msgkey = nullptr;
   s.paysend = s.payrecv = nullptr;
+}
+
+int alloc_species_scratch(Domain* d, SpeciesDev& s)
+{
+  free_species_scratch(s);
+  NIX_CUDA(cudaMalloc(&s.xv, d->esz * d->nct * s.cap));
+  NIX_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * s.cap));
+  NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * s.cap));
+  NIX_CUDA(cudaMemset(s.xv, 0, d->esz * d->nct * s.cap));
+  return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, s.cap / 16))); // regrown on demand (ensure_capacity)
+}
+
+int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot, bool with_scratch)
+{
+  free_species_scratch(s);
+  if (s.xu) cudaFree(s.xu);
+  s.xu = nullptr;
   double f = d->desc.capacity_factor > 0 ? d->desc.capacity_factor : 1.25;
   if (f < 1.0) f = 1.0;
   int64_t cap = round_cap((int64_t)((double)ntot * f) + 1024);
@@ -133,12 +152,8 @@ int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot)
   }
   s.cap = cap;
   NIX_CUDA(cudaMalloc(&s.xu, d->esz * d->nct * cap));
-  NIX_CUDA(cudaMalloc(&s.xv, d->esz * d->nct * cap));
-  NIX_CUDA(cudaMalloc(&s.key, sizeof(int32_t) * cap));
-  NIX_CUDA(cudaMalloc(&s.ordl, sizeof(int32_t) * cap));
   NIX_CUDA(cudaMemset(s.xu, 0, d->esz * d->nct * cap));
-  NIX_CUDA(cudaMemset(s.xv, 0, d->esz * d->nct * cap));
-  return alloc_leavers(d, s, round_cap(std::max<int64_t>(4096, cap / 16))); // regrown on demand (ensure_capacity)
+  return with_scratch ? alloc_species_scratch(d, s) : 0;
 }
 
 // fp32 mode: fp64 AoS scratch for the particle boundary

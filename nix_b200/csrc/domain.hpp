@@ -107,7 +107,9 @@ int grow_particles(Domain* d, SpeciesDev& s, int64_t newcap);           // keeps
 int grow_leavers(Domain* d, SpeciesDev& s, int64_t newlcap, bool keep); // keep: lrec survives
 int record_stats(Domain* d);
 
-int alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot); // (re)sizes the stores of one species
+int  alloc_species_particles(Domain* d, SpeciesDev& s, int64_t ntot, bool with_scratch = true); // (re)sizes the stores of one species
+int  alloc_species_scratch(Domain* d, SpeciesDev& s);
+void free_species_scratch(SpeciesDev& s);
 int pack_scratch(Domain* d, size_t bytes);                           // d->pack_dev, grown on demand
 
 // peer.cu: raw transport for rebalance.cu

@@ -363,7 +363,11 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
     if (peer_sendrecv_bytes(peer_comm(d), d->stream, 2, ranks, sb, tot_s, rb, tot_r)) return 1;
   }
 
-  // 3. the re-sized domain: same streams and communicator, new id range
+  // 3. the re-sized domain: same streams and communicator, new id range.  Peak memory = the old and the new
+  //    particle arrays (xu) + the wire buffers: everything that carries no state between steps (temporary array,
+  //    keys, member lists, migration buffers) is freed first and re-created last
+  NIX_CUDA(cudaStreamSynchronize(d->stream));
+  for (auto& s : d->sp) free_species_scratch(s);
   nixb200_domain_desc nd_desc = d->desc;
   nd_desc.id_begin            = b1;
   nd_desc.id_end              = e1;
@@ -388,7 +392,7 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
       nb[id - b1 + 1] = nb[id - b1] + n;
     }
     SpeciesDev& s = nd->sp[is];
-    if (alloc_species_particles(nd, s, nb[nch1])) return 1;
+    if (alloc_species_particles(nd, s, nb[nch1], /*with_scratch=*/false)) return 1;
     NIX_CUDA(cudaMemcpyAsync(s.cbase, nb.data(), sizeof(int32_t) * (nch1 + 1), cudaMemcpyHostToDevice, d->stream));
     NIX_CUDA(cudaStreamSynchronize(d->stream)); // (nb is a local)
     // kept chunks: one contiguous particle range per component, device to device
@@ -449,6 +453,8 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
     std::swap(d->ev_copy_done[w], nd->ev_copy_done[w]);
   }
   nixb200_domain_destroy(reinterpret_cast<nixb200_domain*>(nd)); // frees the old arrays
+  for (auto& s : d->sp)
+    if (alloc_species_scratch(d, s)) return 1;
   d->particles_set = true;
   if (nixb200_domain_set_ranks(dd, nrank, boundary, rank)) return 1;
   if (comm && peer_give_comm(d, comm, own)) return 1;
