@@ -90,7 +90,7 @@ def make_problem(w, seed=2024, cdims=None, coord=None):
                    vth=w["vth"], coord=coord, q=w.get("q", (-1.0, 1.0)), m=w.get("m", (1.0, 25.0)))
 
 
-def global_box(cd, world):
+def global_box(cd, world, first_axis=0):
     """Weak scaling: the per-GPU block of cd chunks is repeated world times (z first, then y, then x).  Chunk
     ids follow the reference's Gilbert curve over the WHOLE box (sfc.cpp:97-169 via nix_b200/sfc.py) and every
     rank owns one contiguous segment of it (Balancer::assign_initial with uniform loads, balancer.cpp:101-124)."""
@@ -100,7 +100,7 @@ def global_box(cd, world):
     while n > 1:
         if n % 2:
             raise SystemExit("bench.py: --gpus must be a power of two")
-        rep[a % 3] *= 2
+        rep[(first_axis + a) % 3 if first_axis == 0 else (first_axis - a) % 3] *= 2
         n //= 2
         a += 1
     gcd = tuple(cd[i] * rep[i] for i in range(3))
@@ -297,7 +297,8 @@ def run_gpu(args):
 
     w = workload(args)
     peak64 = fp64_peak() if rank == 0 else None  # before the timed regions, GPU otherwise idle
-    gcd, gcoord = global_box(w["cdims"], world)
+    # (cfg5: the box grows along x first, the axis the density varies along, so that already two ranks are imbalanced)
+    gcd, gcoord = global_box(w["cdims"], world, first_axis=2 if w.get("sine") else 0)
     prob = make_problem(w, seed=2024, cdims=gcd, coord=gcoord)
     bd = core.uniform_boundary(prob.nchunk, world)
     ids = list(range(int(bd[rank]), int(bd[rank + 1])))
