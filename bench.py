@@ -389,8 +389,12 @@ def run_gpu(args):
         rounds, moved = 0, 0
         tr0 = time.perf_counter()
         for _ in range(12):
+            # Chunk::load (chunk.hpp:177-192) of a GPU chunk: particles + a per-cell term.  Measured on this
+            # workload (profiles/r02p_cfg5_n2.json): a bin costs the kernels about as much as 12 particles
+            # (per-bin reduction and flush of the deposit, the 8 keys per cell of the sort)
             mine = torch.zeros(prob.nchunk, dtype=torch.float64, device="cuda")
-            mine[bnow[rank]:bnow[rank + 1]] = torch.tensor(sum(dom.get_np(s) for s in range(prob.ns)), dtype=torch.float64)
+            mine[bnow[rank]:bnow[rank + 1]] = torch.tensor(
+                sum(dom.get_np(s) for s in range(prob.ns)) + 12.0 * prob.ncell() * prob.ns, dtype=torch.float64)
             dist.all_reduce(mine)
             bnew = balancer.assign(mine.cpu().numpy(), bnow)
             if bnew == bnow:
