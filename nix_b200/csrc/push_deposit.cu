@@ -57,6 +57,9 @@ namespace
 #ifndef NIX_MAXMOV
 #define NIX_MAXMOV 20
 #endif
+#ifndef NIX_MOVER_AGGREGATE
+#define NIX_MOVER_AGGREGATE 1 // sum the lanes of a mover flush that target the same nodes before the atomics
+#endif
 #ifndef NIX_MOV_FLUSH
 #define NIX_MOV_FLUSH NIX_MAXMOV // flush whole groups of XGROUP records: the expansion and face-node lanes stay busy
 #endif
@@ -368,13 +371,19 @@ __device__ __forceinline__ void flush_group(T* s_j, const T* myrec, int* myml, i
     wz  = -qdz * ((s0x + A * dsx) * s0y + (A * s0x + B * dsx) * dsy);
   };
   for (int it0 = 0; it0 < nsingle * N1 * N1; it0 += 32) {
-    const int gi = it0 + lane;
-    if (gi < nsingle * N1 * N1) {
+    const int  gi     = it0 + lane;
+    const bool active = gi < nsingle * N1 * N1;
+    T*         dst    = s_j;
+    T          val[5] = {T(0.0), T(0.0), T(0.0), T(0.0), T(0.0)};
+    int        ax = 0, key = -1 - lane; // (a key of its own for an idle lane)
+    bool       low = false;
+    if (active) {
       const int     m  = myml[gi / (N1 * N1)];
       const int     uv = gi % (N1 * N1);
       const T* r  = myrec + m * C::REC;
       const int*    ri = reinterpret_cast<const int*>(r + 9 * NS);
-      const int     cbase = ri[0], ax = ri[1] >> 1, o = (ri[1] & 1) ? NS - 1 : 0;
+      const int     cbase = ri[0], o = (ri[1] & 1) ? NS - 1 : 0;
+      ax = ri[1] >> 1;
       // mesh slots z,y,x: the moving axis sits on its outer slot, the two in-plane axes (ascending
       // axis order) run over the central slots
       const int u = uv / N1 + 1, v = uv % N1 + 1;
@@ -383,14 +392,40 @@ __device__ __forceinline__ void flush_group(T* s_j, const T* myrec, int* myml, i
       const int jx = (ax == 2) ? o : v;
       T    rho, wx, wy, wz;
       node(r, jz, jy, jx, rho, wx, wy, wz);
-      T*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
-      const T vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+      const int nd = cbase + (jz * JY + jy) * JX + jx;
+      dst = s_j + nd;
+      low = o == 0;
+      val[0] = rho, val[1] = wx * r[8 * NS + jx], val[2] = wy * r[5 * NS + jy], val[3] = wz * r[2 * NS + jz];
       // low-side mover: the current through the first central face (slot 1) is carried by DS[0]
-      const int     st = (ax == 0) ? JY * JX : ((ax == 1) ? JX : 1);
-      const T  w1 = (ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]);
-      T* const ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
-      const T  val[5]  = {rho, vx, vy, vz, w1};
-      bool          todo[5] = {rho != T(0.0), vx != T(0.0), vy != T(0.0), vz != T(0.0), o == 0 && w1 != T(0.0)};
+      val[4] = !low ? T(0.0) : ((ax == 0) ? wz * r[2 * NS + 1] : ((ax == 1) ? wy * r[5 * NS + 1] : wx * r[8 * NS + 1]));
+      key    = (nd * 4 + ax) * 2 + (low ? 1 : 0);
+    }
+#if NIX_MOVER_AGGREGATE
+    // Movers of one bin that leave through the same face add to the SAME nodes: compare-and-swap loops on one
+    // address serialise (profiles/r02f: 207 wavefronts where 49 would do).  Lanes with the same target are
+    // summed with shuffles first and one of them issues the atomics.
+    {
+      const unsigned peers  = __match_any_sync(FULL, key);
+      const int      cnt    = __popc(peers), leader = __ffs(peers) - 1;
+      const int      maxcnt = (int)__reduce_max_sync(FULL, (unsigned)cnt);
+      for (int k = 1; k < maxcnt; k++) {
+        const int src = (k < cnt) ? (int)__fns(peers, 0, k + 1) : lane;
+#pragma unroll
+        for (int c = 0; c < 5; c++) {
+          const T t = __shfl_sync(FULL, val[c], src);
+          if (lane == leader && k < cnt) val[c] += t;
+        }
+      }
+      if (lane != leader) {
+#pragma unroll
+        for (int c = 0; c < 5; c++) val[c] = T(0.0);
+      }
+    }
+#endif
+    if (active) {
+      const int st = (ax == 0) ? JY * JX : ((ax == 1) ? JX : 1);
+      T* const  ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
+      bool      todo[5] = {val[0] != T(0.0), val[1] != T(0.0), val[2] != T(0.0), val[3] != T(0.0), low && val[4] != T(0.0)};
       atomic_add_batch<5, T>(ad, val, todo);
     }
   }

@@ -238,3 +238,57 @@ def test_sort_is_stable_by_cell_and_lane(oracle_port):
         assert c.np(0) == inb.sum()
         assert np.array_equal(c.particles(0), exp)
         assert c.pindex(0)[ng] == inb.sum()
+
+
+# ---- XtensorPacker3D: the reference's own known answers (unittest/test_xtensor_packer3d.cpp) --------------
+def _chunk_with_pattern(lib, n, nb):
+    from oracle import nixoracle as no
+    c = no.Chunk(lib, (n, n, n), nb, 2, ns=1, np_required=[64])
+    iz, iy, ix, k = np.meshgrid(*[np.arange(m) for m in c.M], np.arange(6), indexing="ij")
+    c.uf[...] = iz * 1000.0 + iy * 100.0 + ix * 10.0 + k   # test_xtensor_packer3d.cpp:191-199
+    c.uj[...] = (iz * 100.0 + iy * 10.0 + ix)[..., :4]       # :235-242
+    return c
+
+
+def test_pack_field_colocates(oracle_port):
+    """test_xtensor_packer3d.cpp:188-230: every packed value is the average of the staggered neighbours"""
+    n, nb = 4, 2
+    c = _chunk_with_pattern(oracle_port, n, nb)
+    out = c.pack_field(1).reshape(n, n, n, 6)
+    x = c.uf
+    s = slice(nb, nb + n)
+    p = slice(nb + 1, nb + n + 1)
+    assert np.allclose(out[..., 0], 0.5 * (x[s, s, s, 0] + x[s, s, p, 0]))
+    assert np.allclose(out[..., 1], 0.5 * (x[s, s, s, 1] + x[s, p, s, 1]))
+    assert np.allclose(out[..., 2], 0.5 * (x[s, s, s, 2] + x[p, s, s, 2]))
+    assert np.allclose(out[..., 3], 0.25 * (x[s, s, s, 3] + x[p, p, s, 3] + x[s, p, s, 3] + x[p, s, s, 3]))
+    assert np.allclose(out[..., 4], 0.25 * (x[s, s, s, 4] + x[p, s, p, 4] + x[p, s, s, 4] + x[s, s, p, 4]))
+    assert np.allclose(out[..., 5], 0.25 * (x[s, s, s, 5] + x[s, p, p, 5] + x[s, s, p, 5] + x[s, p, s, 5]))
+
+
+def test_pack_moment_decimates_by_averaging_blocks(oracle_port):
+    """test_xtensor_packer3d.cpp:232-275: decimate = 2 on a 4^3 interior -> 2^3 block means; decimate >= size -> 1"""
+    n, nb = 4, 2
+    c = _chunk_with_pattern(oracle_port, n, nb)
+    out = c.pack_moment(0, 2).reshape(2, 2, 2, 4)
+    inner = c.uj[nb:nb + n, nb:nb + n, nb:nb + n]
+    want = inner.reshape(2, 2, 2, 2, 2, 2, 4).mean(axis=(1, 3, 5))
+    assert np.allclose(out, want)
+    assert c.pack_moment(0, 4).shape == (4,) and np.allclose(c.pack_moment(0, 4), inner.reshape(-1, 4).mean(axis=0))
+    assert len(c.pack_moment(0, 1)) == n ** 3 * 4
+
+
+def test_pack_tracer_packs_negative_ids_only(oracle_port):
+    """test_xtensor_packer3d.cpp:303-340"""
+    from oracle import nixoracle as no
+    c = no.Chunk(oracle_port, (4, 4, 4), 2, 2, ns=1, np_required=[16])
+    xu = np.zeros((6, 7))
+    xu[:, 0:3] = 1.5
+    xu[:, 3] = np.arange(6)
+    ids = np.array([5, -1, 7, -9, -3, 11], dtype=np.int64)
+    xu[:, 6] = ids.view(np.float64)
+    c.set_particles(0, xu)
+    t = c.pack_tracer(0)
+    assert t.shape == (3, 7)
+    assert np.ascontiguousarray(t[:, 6]).view(np.int64).tolist() == [-1, -9, -3]
+    assert t[:, 3].tolist() == [1.0, 3.0, 4.0]
