@@ -345,3 +345,34 @@ def test_single_rank_rebalance_and_wire_record(oracle_port, gpu_lib):
             assert np.array_equal(pidx, c.pindex(s))
             off += 175 + npt * 116 + (cells + 1) * 36
     gd.close()
+
+
+def test_two_domains_on_two_devices_in_one_process(oracle_port, gpu_lib):
+    """ADVICE r01 (push_deposit.cu:1172): kernel attributes are per device and every entry point must run on the
+    domain's device whatever the caller's current device is.  Two independent domains on cuda:0 and cuda:1,
+    stepped alternately from one thread while the current device points at the OTHER one."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from nix_b200 import core
+    from helpers import assert_particles_equal, oracle_domain
+    probs = [Problem((2, 2, 2), (8, 8, 8), 2, ppc=8, seed=11, vth=(0.3, 0.05)),
+             Problem((1, 2, 2), (8, 8, 8), 3, ppc=6, seed=12, vth=(0.3, 0.05))]
+    ods = [oracle_domain(oracle_port, p) for p in probs]
+    gds = []
+    for dev, p in enumerate(probs):
+        torch.cuda.set_device(1 - dev)  # deliberately the wrong current device
+        gd = core.Domain(p.cdims, p.dims, p.nb, p.order, p.q, p.m, coord=p.coord, device=dev, strict_fp=True)
+        _load(gd, p, list(range(p.nchunk)))
+        gds.append(gd)
+        assert torch.cuda.current_device() == 1 - dev, "the library must restore the caller's device"
+    for step in range(3):
+        for dev in (0, 1):
+            torch.cuda.set_device(1 - dev)
+            ods[dev].step(0.5, 1.0)
+            gds[dev].step(0.5)
+            assert gds[dev].check() == 0
+    for dev in (0, 1):
+        torch.cuda.set_device(1 - dev)
+        assert_particles_equal(ods[dev], gds[dev], f"device {dev}")
+        gds[dev].close()
