@@ -880,7 +880,7 @@ __global__ void __launch_bounds__(PTHREADS, NIX_P_MINB) k_push(const __grid_cons
 
 
 template <int O, bool S, typename T>
-__global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : NIX_D_MINB) k_deposit(const KparamsT<T> P)
+__global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : (sizeof(T) == 4 ? 4 : NIX_D_MINB)) k_deposit(const KparamsT<T> P)
 {
   using C          = Cfg<O>;
   constexpr int N1 = C::N1;
