@@ -255,6 +255,9 @@ int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int
 int nixb200_chunk_wire_size(nixb200_domain* d, int k, int64_t* bytes);
 int nixb200_chunk_wire_pack(nixb200_domain* d, int k, void* buffer, int64_t bytes);
 int nixb200_domain_rebalance(nixb200_domain* d, int nrank, const int* boundary, int rank);
+/* host logic of it (no device needed): a rank that owned [b0, e0) and will own [b1, e1) sends [out0, out1) to rank-1 and
+ * [out2, out3) to rank+1, receives [out4, out5) from rank-1 and [out6, out7) from rank+1, keeps [out8, out9) */
+int nixb200_rebalance_moves(int b0, int e0, int b1, int e1, int* out10);
 
 /* device-time accounting per phase (feeds Chunk::load; also bench.py's roofline).  Phases:
  * 0 push_deposit, 1 exchange_current, 2 exchange_field, 3 migrate+sort, 4 sort (count+sort only),

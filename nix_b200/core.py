@@ -38,6 +38,7 @@ SYMBOLS = [
     "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
     "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance", "nixb200_domain_history_async",
+    "nixb200_rebalance_moves",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -149,6 +150,7 @@ def load_library():
     sig("nixb200_chunk_wire_size", I, P, I, PL)
     sig("nixb200_chunk_wire_pack", I, P, I, P, C.c_int64)
     sig("nixb200_domain_rebalance", I, P, I, PI, I)
+    sig("nixb200_rebalance_moves", I, I, I, I, I, PI)
     sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
     sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib
@@ -210,6 +212,15 @@ class Plan:
 
 
 from .sfc import chunk_coords  # noqa: E402  (the reference's chunk order; re-exported)
+
+
+def rebalance_moves(old, new):
+    """(send_left, send_right, recv_left, recv_right, keep) id ranges of a rank whose range changes old -> new"""
+    lib = load_library()
+    out = (C.c_int * 10)()
+    rc = lib.nixb200_rebalance_moves(int(old[0]), int(old[1]), int(new[0]), int(new[1]), out)
+    v = list(out)
+    return rc, [(v[0], v[1]), (v[2], v[3]), (v[4], v[5]), (v[6], v[7]), (v[8], v[9])]
 
 
 def uniform_boundary(nchunk, nrank):

@@ -267,6 +267,19 @@ int nixb200_chunk_wire_pack(nixb200_domain* dd, int k, void* buffer, int64_t byt
   return rc;
 }
 
+// Pure host logic (no device): which chunk ids a rank that owned [b0, e0) and will own [b1, e1) sends to rank-1
+// ([sl0, sl1)) and to rank+1 ([sr0, sr1)), receives from rank-1 ([rl0, rl1)) and from rank+1 ([rr0, rr1)), and
+// keeps ([keep0, keep1)); out[10] in that order.  Returns non-zero when the two ranges do not overlap.
+int nixb200_rebalance_moves(int b0, int e0, int b1, int e1, int* out)
+{
+  out[0] = b0, out[1] = std::max(b0, std::min(b1, e0));  // leaving at the low end
+  out[2] = std::min(e0, std::max(e1, b0)), out[3] = e0;  // leaving at the high end
+  out[4] = b1, out[5] = std::max(b1, std::min(b0, e1));  // arriving at the low end (ids below b0)
+  out[6] = std::min(e1, std::max(e0, b1)), out[7] = e1;  // arriving at the high end
+  out[8] = std::max(b0, b1), out[9] = std::min(e0, e1);  // staying
+  return out[8] < out[9] ? 0 : 1;
+}
+
 // Collective: every rank of the communicator calls it with the same new boundaries.
 int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary, int rank)
 {
@@ -293,12 +306,11 @@ int nixb200_domain_rebalance(nixb200_domain* dd, int nrank, const int* boundary,
   }
   const int ns = (int)d->sp.size();
   // moving chunks, in ascending id order: [send to left][send to right], [recv from left][recv from right]
-  const int sl0 = b0, sl1 = std::max(b0, std::min(b1, e0)); // leaving at the low end
-  const int sr0 = std::min(e0, std::max(e1, b0)), sr1 = e0;  // leaving at the high end
-  const int rl0 = b1, rl1 = std::min(b0, e1);                // arriving at the low end (ids below b0)
-  const int rr0 = std::max(e0, b1), rr1 = e1;                // arriving at the high end
+  int mv[10];
+  nixb200_rebalance_moves(b0, e0, b1, e1, mv);
+  const int sl0 = mv[0], sl1 = mv[1], sr0 = mv[2], sr1 = mv[3], rl0 = mv[4], rl1 = mv[5], rr0 = mv[6], rr1 = mv[7];
   const int nsl = std::max(0, sl1 - sl0), nsr = std::max(0, sr1 - sr0), nrl = std::max(0, rl1 - rl0), nrr = std::max(0, rr1 - rr0);
-  const int keep0 = std::max(b0, b1), keep1 = std::min(e0, e1);
+  const int keep0 = mv[8], keep1 = mv[9];
 
   std::vector<std::vector<int32_t>> cb;
   if (read_cbase(d, cb)) return 1;
