@@ -306,6 +306,7 @@ protected:
   float64                    cfj          = 1.0;
   int                        pusher       = NIXB200_PUSH_BORIS;
   void*                      nccl_comm    = nullptr; ///< created once, handed to every rebuilt domain
+  float64                    cell_weight  = 12.0; ///< load of one cell and species in particle-equivalents
   long                       npush = 0, nrebuild = 0;
 
 public:
@@ -376,8 +377,10 @@ public:
     if (err & NIXB200_ERR_CFL) ERROR << tfm::format("step[%d] a particle moved more than one cell (c*delt > delh)", curstep);
     if (err & NIXB200_ERR_UNSORTED) ERROR << tfm::format("step[%d] particle container was not cell-sorted", curstep);
     assert_mpi((err & NIXB200_ERR_CAPACITY) == 0, "particle storage overflowed on the device (raise capacity_factor)");
-    // Chunk::load feeds the balancer (chunk.hpp:177-192): device time of the push, shared among
-    // the chunks in proportion to their particle counts
+    // Chunk::load feeds the balancer (chunk.hpp:177-192): device time of the push, shared among the chunks in
+    // proportion to (particles + cell_weight x cells x species): a bin costs the kernels about as much as 12
+    // particles (per-bin reduction and flush of the deposit, the 8 keys per cell of the sort; measured,
+    // profiles/r02p_cfg5_n2.json), which matters once there are fewer than ~30 particles per cell
     double ms = 0;
     nixb200_domain_get_load(domain->h, &ms);
     std::vector<int64_t> np(chunkvec.size());
@@ -386,8 +389,10 @@ public:
     for (size_t is = 0; is < species.size(); is++) {
       check(nixb200_domain_get_np(domain->h, (int)is, np.data()), "get_np");
       for (size_t k = 0; k < np.size(); k++) {
-        w[k] += (double)np[k];
-        total += (double)np[k];
+        auto         nd    = chunkvec[k]->get_dims();
+        const double cells = cell_weight * nd[0] * nd[1] * nd[2];
+        w[k] += (double)np[k] + cells;
+        total += (double)np[k] + cells;
       }
     }
     for (size_t k = 0; k < chunkvec.size(); k++) {
