@@ -186,3 +186,48 @@ def test_rebalance_moves_are_consistent_between_ranks():
             checked += old != new
             old = new
     assert checked > 20
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_plan_of_the_benchmarked_boxes(world):
+    """The boxes `bench.py --gpus N` runs (cfg2: 8x8x8 chunks of 16^3 per GPU, repeated z, y, x; ids along the
+    reference's Gilbert curve, one contiguous segment per rank): every rank's plan pairs up with its peers'
+    entry by entry, every slab that crosses a rank boundary appears exactly once, and the neighbour relation is
+    symmetric (host logic only -- the N = 4 box is not covered by any GPU test of its own)."""
+    saved = os.dup(1)  # (bench.py points file descriptor 1 at stderr when it is loaded: its stdout carries ONE line)
+    try:
+        import bench
+    finally:
+        os.dup2(saved, 1)
+        os.close(saved)
+    gcd, coord = bench.global_box((8, 8, 8), world)
+    assert int(np.prod(gcd)) == 512 * world
+    nchunk = 512 * world
+    bd = core.uniform_boundary(nchunk, world)
+    assert list(bd) == [512 * r for r in range(world + 1)]
+    dims, nb = (16, 16, 16), 2
+    plans = [core.Plan(gcd, dims, nb, coord, bd, r) for r in range(world)]
+    grid2id = {tuple(int(v) for v in c): i for i, c in enumerate(coord)}
+    assert len(grid2id) == nchunk  # the curve visits every chunk once
+    owner = np.searchsorted(bd, np.arange(nchunk), side="right") - 1
+    for r, pl in enumerate(plans):
+        ranks = [p["rank"] for p in pl.peers]
+        assert ranks == sorted(set(ranks)) and r not in ranks
+        expect = set()
+        for i in range(bd[r], bd[r + 1]):
+            c = coord[i]
+            for d in range(27):
+                if d == 13:
+                    continue
+                nid = grid2id[((int(c[0]) + d // 9 - 1) % gcd[0], (int(c[1]) + (d // 3) % 3 - 1) % gcd[1],
+                               (int(c[2]) + d % 3 - 1) % gcd[2])]
+                if owner[nid] != r:
+                    expect.add((int(owner[nid]), i, d))
+        assert {(p["rank"], i, d) for p in pl.peers for (i, d, _) in p["send"]} == expect
+        for p in pl.peers:
+            back = next(q for q in plans[p["rank"]].peers if q["rank"] == r)
+            assert len(p["send"]) == len(back["recv"]) and len(p["recv"]) == len(back["send"])
+            for (i, d, n), (j, e, m) in zip(p["send"], back["recv"]):
+                assert e == 26 - d and n == m
+                assert grid2id[((int(coord[i][0]) + d // 9 - 1) % gcd[0], (int(coord[i][1]) + (d // 3) % 3 - 1) % gcd[1],
+                                (int(coord[i][2]) + d % 3 - 1) % gcd[2])] == j
