@@ -50,6 +50,75 @@ def test_shape_mc_equals_analytic(oracle_port, order, dx):
         assert abs(s.sum() - 1) < 1e-14
 
 
+def _tp(n, x):
+    """(x)_+^n in extended precision"""
+    x = np.longdouble(x)
+    return x ** n if x > 0 else np.longdouble(0)
+
+
+def bspline(n, t):
+    """Centred cardinal B-spline of degree n (support n + 1), textbook truncated-power form
+    B_n(t) = 1/n! sum_k (-1)^k C(n+1, k) (t + (n+1)/2 - k)_+^n, evaluated in extended precision.  Independent of
+    the piecewise polynomials the reference's tests spell out (test_primitives.cpp:271-530) and equal to them."""
+    from math import comb, factorial
+    return float(sum(np.longdouble((-1) ** k * comb(n + 1, k)) * _tp(n, np.longdouble(t) + np.longdouble(n + 1) / 2 - k)
+                     for k in range(n + 2)) / np.longdouble(factorial(n)))
+
+
+def bspline_cumulative(m, t):
+    """integral of B_m from -inf to t"""
+    from math import comb, factorial
+    return sum(np.longdouble((-1) ** k * comb(m + 1, k)) * _tp(m + 1, np.longdouble(t) + np.longdouble(m + 1) / 2 - k)
+               for k in range(m + 2)) / np.longdouble(factorial(m + 1))
+
+
+def test_truncated_power_form_equals_the_piecewise_b_splines():
+    for order in (1, 2, 3):
+        for t in np.linspace(-2.6, 2.6, 521):
+            assert abs(bspline(order, t) - W(order, t)) < 1e-15
+
+
+@pytest.mark.parametrize("dx", [0.5, 1.0, 1.5])
+def test_shape_mc4_equals_analytic(oracle_port, dx):
+    # test_primitives.cpp:458-530 ("Fourth-order shape function"): 100 points, abs 1e-14
+    rdx = 1 / dx
+    for x in np.linspace(0, 3 * dx, 100):
+        ix = int(np.floor(x * rdx + 0.5))  # even order: nearest node (primitives.hpp:497-511)
+        s = np.zeros(5)
+        oracle_port.nixo_shape_mc(4, float(x), float(ix * dx), rdx, s.ctypes.data_as(PD))
+        for j in range(5):
+            assert abs(s[j] - bspline(4, (x - (ix - 2 + j) * dx) * rdx)) < 1e-14
+        assert abs(s.sum() - 1) < 1e-14
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("dt", [0.1, 0.2, 0.3, 0.4, 0.5])
+@pytest.mark.parametrize("dx", [0.5, 1.0, 1.5])
+def test_shape_wt_equals_analytic(oracle_port, order, dt, dx):
+    """test_primitives.cpp:532-822 ("... shape function for WT scheme", delt = 0.1 .. 0.5, 100 points, abs 1e-14).
+    The reference's tests spell the WT weights out as piecewise polynomials per order; all of them are ONE
+    statement: the order-n WT weight is the B-spline of degree n-1 averaged over the path of half-length dt
+    (in cells), W_n(t; dt) = [C_{n-1}(t + dt) - C_{n-1}(t - dt)] / (2 dt) with C the cumulative B-spline -- e.g.
+    order 1: (1 + 2 dt - 2|t|) / (4 dt) on 1/2 - dt < |t| <= 1/2 + dt, 1 inside, 0 outside (:541-551)."""
+    rdx = 1 / dx
+    if order == 1:  # the reference's own closed form for order 1, as a check of the statement above
+        for t in np.linspace(-1.2, 1.2, 49):
+            a = abs(t)
+            w1 = (1 + 2 * dt - 2 * a) / (4 * dt) if 0.5 - dt < a <= 0.5 + dt else (1.0 if a <= 0.5 - dt else 0.0)
+            w = float((bspline_cumulative(0, t + dt) - bspline_cumulative(0, t - dt)) / (2 * np.longdouble(dt)))
+            assert abs(w - w1) < 1e-15
+    for x in np.linspace(0, 3 * dx, 100):
+        ix = int(np.floor(x * rdx)) if order % 2 else int(np.floor(x * rdx + 0.5))
+        s = np.zeros(order + 1)
+        oracle_port.nixo_shape_wt(order, float(x), float(ix * dx), rdx, dt, 1 / dt, s.ctypes.data_as(PD))
+        first = ix - order // 2
+        for j in range(order + 1):
+            t = (np.longdouble(x) - (first + j) * np.longdouble(dx)) * np.longdouble(rdx)
+            w = float((bspline_cumulative(order - 1, t + dt) - bspline_cumulative(order - 1, t - dt)) / (2 * np.longdouble(dt)))
+            assert abs(s[j] - w) < 1e-14, (order, dt, dx, x, j)
+        assert abs(s.sum() - 1) < 1e-14
+
+
 @pytest.mark.parametrize("xmin,dx", [(-1.0, 0.5), (0.0, 1.0), (-1.0, 1.5), (0.0, 0.5)])
 def test_digitize(oracle_port, xmin, dx):
     # test_primitives.cpp:73-117
@@ -292,3 +361,52 @@ def test_pack_tracer_packs_negative_ids_only(oracle_port):
     assert t.shape == (3, 7)
     assert np.ascontiguousarray(t[:, 6]).view(np.int64).tolist() == [-1, -9, -3]
     assert t[:, 3].tolist() == [1.0, 3.0, 4.0]
+
+
+# ---- XtensorParticle: the reference's own container tests (unittest/test_xtensor_particle.cpp) ----------------
+@pytest.mark.parametrize("which", ["port", "ref"])
+def test_create_particle_sizes(which):
+    """test_xtensor_particle.cpp:210-232 "CreateParticle": Np = 1000 in an 8^3 chunk with one ghost layer ->
+    Ng = 10^3, Np_total = ((Np + 128) / 128) * 128 slots (particle.hpp:146-153), pindex [Ng + 1], pcount
+    [Ng + 1][8], everything zero."""
+    if not no.available(which):
+        pytest.skip(f"{which} library not built here")
+    lib = no.load(which)
+    c = no.Chunk(lib, (8, 8, 8), 1, 1, ns=1, np_required=[1000])
+    assert c.ng(0) == 10 * 10 * 10
+    assert c.np_total(0) == ((1000 + 128) // 128) * 128 == 1024
+    assert c.xu(0).shape == (1024, 7) and c.xv(0).shape == (1024, 7) and c.gindex(0).shape == (1024,)
+    assert c.pindex(0).shape == (1001,) and c.pcount(0).shape == (1001, 8)
+    assert not c.xu(0).any() and not c.xv(0).any()
+
+
+@pytest.mark.parametrize("npart", [100, 1000, 10000])
+@pytest.mark.parametrize("dims", [(8, 8, 8), (16, 8, 16), (16, 16, 16)])
+def test_sort_particle_3d(oracle_port, npart, dims):
+    """test_xtensor_particle.cpp:339-367 "SortParticle3D" with what that test MEANT to check (it never sets Np, so
+    the reference's own run is vacuous): positions uniform in the chunk plus one cell on every
+    side, count(order 1) + sort, then every particle between pindex[ii] and pindex[ii + 1] lies in cell ii
+    (check_sort3d, :190-207) and the out-of-bounds ones are gone."""
+    rng = np.random.default_rng(npart + dims[0])
+    nb = 1
+    c = no.Chunk(oracle_port, dims, nb, 1, ns=1, np_required=[npart])
+    x = np.zeros((npart, 7))
+    for a in range(3):  # x, y, z <- dims[2], dims[1], dims[0]
+        x[:, a] = rng.uniform(-1.0, dims[2 - a] + 1.0, npart)
+    c.set_particles(0, x)
+    c.count(0, 0, npart - 1, True, 1)
+    c.sort(0)
+    inside = np.ones(npart, dtype=bool)
+    for a in range(3):
+        inside &= (x[:, a] >= 0.0) & (x[:, a] < dims[2 - a])
+    assert c.np(0) == int(inside.sum())
+    xs, pin = c.particles(0), c.pindex(0)
+    # bins as count() computes them for an odd order: half a cell below the chunk (xtensor_particle.hpp:328-348)
+    ix = np.floor(xs[:, 0] + 0.5).astype(int)
+    iy = np.floor(xs[:, 1] + 0.5).astype(int)
+    iz = np.floor(xs[:, 2] + 0.5).astype(int)
+    cell = (iz * (dims[1] + 1) + iy) * (dims[2] + 1) + ix
+    assert (np.diff(cell) >= 0).all()
+    i = np.arange(len(cell))
+    assert (pin[cell] <= i).all() and (i < pin[cell + 1]).all()
+    assert sorted(map(tuple, xs[:, :3])) == sorted(map(tuple, x[inside][:, :3]))

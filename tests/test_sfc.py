@@ -35,3 +35,37 @@ def test_uniform_boundary_is_assign_initial():
     # unittest/test_balancer.cpp:41-44: boundary[i] == i * nchunk / nrank for equal loads
     assert rank_boundary(512, 8).tolist() == [0, 64, 128, 192, 256, 320, 384, 448, 512]
     assert rank_boundary(10, 4).tolist() == [0, 2, 5, 7, 10]
+
+
+def _locality(coord, distmax2):
+    """sfc::check_locality3d (sfc.cpp:206-227): consecutive ids at most sqrt(distmax2) apart"""
+    d = np.diff(coord.astype(np.int64), axis=0)
+    return bool(((d * d).sum(axis=1) <= distmax2).all())
+
+
+def _index_is_a_permutation(coord, cd):
+    """sfc::check_index (sfc.cpp:174-185): every cell of the box is visited exactly once"""
+    flat = (coord[:, 0].astype(np.int64) * cd[1] + coord[:, 1]) * cd[2] + coord[:, 2]
+    return bool(np.array_equal(np.sort(flat), np.arange(cd[0] * cd[1] * cd[2])))
+
+
+def test_reference_sfc3d_properties_even():
+    # unittest/test_sfc.cpp:58-70 "SFC3D even": sizes from {1, 4, 20, 100}, distance 1 between neighbours
+    # (100 is run against one other size here: pure-Python recursion)
+    sizes = [(z, y, x) for z in (1, 4, 20) for y in (1, 4, 20) for x in (1, 4, 20)] + [(1, 4, 100), (4, 100, 1), (100, 1, 20)]
+    for cd in sizes:
+        c = chunk_coords(cd)
+        assert c.shape == (cd[0] * cd[1] * cd[2], 3)
+        assert _locality(c, 1), cd
+        assert _index_is_a_permutation(c, cd), cd
+
+
+def test_reference_sfc3d_properties_odd():
+    # unittest/test_sfc.cpp:71-112 "SFC3D odd-x / odd-y / odd-z": one odd size, distance^2 <= 2
+    for odd in (3, 7, 9):
+        for a in (4, 8, 16):
+            for b in (4, 8, 16):
+                for cd in ((a, b, odd), (a, odd, b), (odd, a, b)):  # (Cz, Cy, Cx)
+                    c = chunk_coords(cd)
+                    assert _locality(c, 2), cd
+                    assert _index_is_a_permutation(c, cd), cd
