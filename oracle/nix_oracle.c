@@ -295,6 +295,26 @@ static void interp_shift_weights(int order, int shift, double* ww)
   }
 }
 
+void nixo_interp_shift_weights(int order, int shift, double* ww)
+{
+  interp_shift_weights(order, shift, ww);
+}
+
+/* esirkepov.hpp:241-258 (scalar branch): ss is [3][order+3]; a particle that moved one cell down (shift < 0)
+ * has its weights moved one slot to the left, one cell up (shift > 0) one slot to the right */
+void nixo_esirkepov_shift_weights(int order, const int* shift, double* ss)
+{
+  const int n = order + 3;
+  for (int dir = 0; dir < 3; dir++) {
+    double* w = ss + dir * n;
+    if (shift[dir] < 0) {
+      for (int ii = 0; ii < order + 2; ii++) w[ii] = w[ii + 1];
+    } else if (shift[dir] > 0) {
+      for (int ii = order + 2; ii > 0; ii--) w[ii] = w[ii - 1];
+    }
+  }
+}
+
 /* interp.hpp:95-113 (interp3d_impl_sorted, scalar) via :217-230 */
 double nixo_interp3d(int order, const double* eb, int my, int mx, int iz0, int iy0, int ix0, int ik,
                      const double* wz, const double* wy, const double* wx, double dt)

@@ -81,6 +81,10 @@ double nixo_lorentz_factor(double ux, double uy, double uz, double rc);  /* prim
 /* esirkepov::deposit3d<order> on ss[2][3][order+3] -> cur[(order+3)^3][4] (esirkepov.hpp:326-340) */
 void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs, double* ss,
                     double* cur);
+/* interp::shift_weights<Order> (interp.hpp:149-160), ww[order+2]; esirkepov::shift_weights<3, Order>
+ * (esirkepov.hpp:241-258), ss[3][order+3], shift[3] */
+void nixo_interp_shift_weights(int order, int shift, double* ww);
+void nixo_esirkepov_shift_weights(int order, const int* shift, double* ss);
 /* interp::interp3d<order> scalar (interp.hpp:95-113,217-230) on a [Mz][My][Mx][6] array */
 double nixo_interp3d(int order, const double* eb, int my, int mx, int iz0, int iy0, int ix0, int ik,
                      const double* wz, const double* wy, const double* wx, double dt);

@@ -588,6 +588,47 @@ void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs,
   }
 }
 
+void nixo_interp_shift_weights(int order, int shift, double* ww)
+{
+  switch (order) {
+  case 1:
+    interp::shift_weights<1>(shift, ww);
+    break;
+  case 2:
+    interp::shift_weights<2>(shift, ww);
+    break;
+  case 3:
+    interp::shift_weights<3>(shift, ww);
+    break;
+  case 4:
+    interp::shift_weights<4>(shift, ww);
+    break;
+  default:
+    break;
+  }
+}
+
+void nixo_esirkepov_shift_weights(int order, const int* shift, double* ss)
+{
+  int sh[3] = {shift[0], shift[1], shift[2]};
+  switch (order) {
+  case 1:
+    esirkepov::shift_weights<3, 1>(sh, reinterpret_cast<double(*)[4]>(ss));
+    break;
+  case 2:
+    esirkepov::shift_weights<3, 2>(sh, reinterpret_cast<double(*)[5]>(ss));
+    break;
+  case 3:
+    esirkepov::shift_weights<3, 3>(sh, reinterpret_cast<double(*)[6]>(ss));
+    break;
+  case 4:
+    esirkepov::shift_weights<3, 4>(sh, reinterpret_cast<double(*)[7]>(ss));
+    break;
+  default:
+    break;
+  }
+}
+
 double nixo_interp3d(int order, const double* eb, int my, int mx, int iz0, int iy0, int ix0, int ik,
                      const double* wz, const double* wy, const double* wx, double dt)
 {

@@ -410,3 +410,41 @@ def test_sort_particle_3d(oracle_port, npart, dims):
     i = np.arange(len(cell))
     assert (pin[cell] <= i).all() and (i < pin[cell + 1]).all()
     assert sorted(map(tuple, xs[:, :3])) == sorted(map(tuple, x[inside][:, :3]))
+
+
+# ---- shift_weights: the reference's own vectors (test_interp.cpp:52-115, test_esirkepov.cpp:100-202) ----------
+INTERP_WW = {1: [0.5, 0.5, 0.0], 2: [0.2, 0.6, 0.2, 0.0], 3: [0.1, 0.4, 0.4, 0.1, 0.0], 4: [0.1, 0.2, 0.4, 0.2, 0.1, 0.0]}
+ESIRKEPOV_WW = {1: [0.0, 0.5, 0.5, 0.0], 2: [0.0, 0.2, 0.6, 0.2, 0.0], 3: [0.0, 0.1, 0.4, 0.4, 0.1, 0.0],
+                4: [0.0, 0.1, 0.2, 0.4, 0.2, 0.1, 0.0]}
+
+
+def _libs():
+    return [no.load(w) for w in ("port", "ref") if no.available(w)]
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_interp_shift_weights(order):
+    """test_interp.cpp:52-115: shift 0 leaves the (order+2)-wide window alone, shift 1 moves it up one slot and
+    clears slot 0 (half-grid weights aligned to the common stencil, interp.hpp:149-160)."""
+    for lib in _libs():
+        for shift in (0, 1):
+            ww = np.array(INTERP_WW[order])
+            lib.nixo_interp_shift_weights(order, shift, ww.ctypes.data_as(PD))
+            want = INTERP_WW[order] if shift == 0 else [0.0] + INTERP_WW[order][:-1]
+            assert ww.tolist() == want
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+@pytest.mark.parametrize("shift", [(+1, -1, 0), (0, +1, +1), (+1, 0, -1), (-1, -1, -1), (0, 0, 0)])
+def test_esirkepov_shift_weights(order, shift):
+    """test_esirkepov.cpp:100-202: a particle that moved one cell down has its (order+3)-wide weights moved one slot
+    to the left, one cell up one slot to the right (esirkepov.hpp:241-258); the padded window keeps its sum."""
+    for lib in _libs():
+        ss = np.array([ESIRKEPOV_WW[order]] * 3)
+        sh = (C.c_int * 3)(*shift)
+        lib.nixo_esirkepov_shift_weights(order, sh, ss.ctypes.data_as(PD))
+        for d in range(3):
+            w = ESIRKEPOV_WW[order]
+            want = w if shift[d] == 0 else (w[1:] + [w[-1]] if shift[d] < 0 else [w[0]] + w[:-1])
+            assert ss[d].tolist() == want, (order, shift, d)
+            assert abs(ss[d].sum() - 1.0) < 1e-15
