@@ -404,6 +404,31 @@ void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs,
 #undef CUR
 }
 
+/* append_current3d<order>, scalar branch (primitives.hpp:786-797): uj is [mz][my][mx][4], cur [n][n][n][4],
+ * n = order + 3 */
+void nixo_append_current3d(int order, double* uj, int my, int mx, int iz0, int iy0, int ix0, const double* cur)
+{
+  const int n = order + 3;
+  for (int jz = 0, iz = iz0; jz < n; jz++, iz++)
+    for (int jy = 0, iy = iy0; jy < n; jy++, iy++)
+      for (int jx = 0, ix = ix0; jx < n; jx++, ix++)
+        for (int k = 0; k < 4; k++)
+          uj[(((size_t)iz * my + iy) * mx + ix) * 4 + k] += cur[(((jz * n) + jy) * n + jx) * 4 + k];
+}
+
+/* append_moment3d<order>, scalar branch (primitives.hpp:904-915): um is [mz][my][mx][ns][14], mom [n][n][n][14],
+ * n = order + 1 */
+void nixo_append_moment3d(int order, double* um, int my, int mx, int ns, int iz0, int iy0, int ix0, int is,
+                          const double* mom)
+{
+  const int n = order + 1;
+  for (int jz = 0, iz = iz0; jz < n; jz++, iz++)
+    for (int jy = 0, iy = iy0; jy < n; jy++, iy++)
+      for (int jx = 0, ix = ix0; jx < n; jx++, ix++)
+        for (int k = 0; k < 14; k++)
+          um[((((size_t)iz * my + iy) * mx + ix) * ns + is) * 14 + k] += mom[(((jz * n) + jy) * n + jx) * 14 + k];
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* chunk geometry                                                                             */
 /* ------------------------------------------------------------------------------------------ */

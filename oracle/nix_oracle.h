@@ -85,6 +85,12 @@ void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs,
  * (esirkepov.hpp:241-258), ss[3][order+3], shift[3] */
 void nixo_interp_shift_weights(int order, int shift, double* ww);
 void nixo_esirkepov_shift_weights(int order, const int* shift, double* ss);
+/* append_current3d<order> (primitives.hpp:778-834) on uj[mz][my][mx][4] with cur[(order+3)^3][4];
+ * append_moment3d<order> (primitives.hpp:896-930) on um[mz][my][mx][ns][14] with mom[(order+1)^3][14]; mz = the
+ * highest plane touched + 1 */
+void nixo_append_current3d(int order, double* uj, int my, int mx, int iz0, int iy0, int ix0, const double* cur);
+void nixo_append_moment3d(int order, double* um, int my, int mx, int ns, int iz0, int iy0, int ix0, int is,
+                          const double* mom);
 /* interp::interp3d<order> scalar (interp.hpp:95-113,217-230) on a [Mz][My][Mx][6] array */
 double nixo_interp3d(int order, const double* eb, int my, int mx, int iz0, int iy0, int ix0, int ik,
                      const double* wz, const double* wy, const double* wx, double dt);

@@ -120,6 +120,8 @@ def load(name="port"):
     sig("nixo_deposit3d", None, I, D, D, D, D, PD, PD)
     sig("nixo_interp3d", D, I, PD, I, I, I, I, I, I, PD, PD, PD, D)
     sig("nixo_interp_shift_weights", None, I, I, PD)
+    sig("nixo_append_current3d", None, I, PD, I, I, I, I, I, PD)
+    sig("nixo_append_moment3d", None, I, PD, I, I, I, I, I, I, I, PD)
     sig("nixo_esirkepov_shift_weights", None, I, C.POINTER(C.c_int), PD)
     sig("nixo_chunk_push_deposit", None, P, D, D, I)
     sig("nixo_chunk_halo_pack", None, P, I)

@@ -411,6 +411,29 @@ PackData pack_data(RefChunk& c)
 }
 } // namespace
 
+template <int Order>
+static void ref_append_current3d(double* uj, int my, int mx, int iz0, int iy0, int ix0, const double* cur)
+{
+  constexpr int n  = Order + 3;
+  size_t        mz = static_cast<size_t>(iz0 + n);
+  auto view = xt::adapt(uj, mz * my * mx * 4, xt::no_ownership(), std::vector<size_t>{mz, (size_t)my, (size_t)mx, 4ul});
+  double local[n][n][n][4];
+  std::memcpy(local, cur, sizeof(local));
+  primitives::append_current3d<Order>(view, iz0, iy0, ix0, local);
+}
+
+template <int Order>
+static void ref_append_moment3d(double* um, int my, int mx, int ns, int iz0, int iy0, int ix0, int is, const double* mom)
+{
+  constexpr int n  = Order + 1;
+  size_t        mz = static_cast<size_t>(iz0 + n);
+  auto view = xt::adapt(um, mz * my * mx * ns * 14, xt::no_ownership(),
+                        std::vector<size_t>{mz, (size_t)my, (size_t)mx, (size_t)ns, 14ul});
+  double local[n][n][n][14];
+  std::memcpy(local, mom, sizeof(local));
+  primitives::append_moment3d<Order>(view, iz0, iy0, ix0, is, local);
+}
+
 extern "C" {
 
 const char* nixo_impl_name(void)
@@ -585,6 +608,29 @@ void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs,
     break;
   default:
     break;
+  }
+}
+
+void nixo_append_current3d(int order, double* uj, int my, int mx, int iz0, int iy0, int ix0, const double* cur)
+{
+  switch (order) {
+  case 1: ref_append_current3d<1>(uj, my, mx, iz0, iy0, ix0, cur); break;
+  case 2: ref_append_current3d<2>(uj, my, mx, iz0, iy0, ix0, cur); break;
+  case 3: ref_append_current3d<3>(uj, my, mx, iz0, iy0, ix0, cur); break;
+  case 4: ref_append_current3d<4>(uj, my, mx, iz0, iy0, ix0, cur); break;
+  default: break;
+  }
+}
+
+void nixo_append_moment3d(int order, double* um, int my, int mx, int ns, int iz0, int iy0, int ix0, int is,
+                          const double* mom)
+{
+  switch (order) {
+  case 1: ref_append_moment3d<1>(um, my, mx, ns, iz0, iy0, ix0, is, mom); break;
+  case 2: ref_append_moment3d<2>(um, my, mx, ns, iz0, iy0, ix0, is, mom); break;
+  case 3: ref_append_moment3d<3>(um, my, mx, ns, iz0, iy0, ix0, is, mom); break;
+  case 4: ref_append_moment3d<4>(um, my, mx, ns, iz0, iy0, ix0, is, mom); break;
+  default: break;
   }
 }
 

@@ -448,3 +448,45 @@ def test_esirkepov_shift_weights(order, shift):
             want = w if shift[d] == 0 else (w[1:] + [w[-1]] if shift[d] < 0 else [w[0]] + w[:-1])
             assert ss[d].tolist() == want, (order, shift, d)
             assert abs(ss[d].sum() - 1.0) < 1e-15
+
+
+# ---- append_current3d / append_moment3d (test_primitives.cpp:1008-1100, 1236-1300, 1633-1657) -----------------
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_append_current3d_adds_the_local_mesh(order):
+    """test_primitives.cpp:1008-1100 via test_append_current3d_scalar (:1633-1657): five appends of a random
+    (order+3)^3 x 4 mesh at (2, 2, 2) of a zeroed 16^3 array leave 5 x the mesh there -- and nothing anywhere else
+    (the reference's check sums the error over the box only)."""
+    n, N = order + 3, 16
+    rng = np.random.default_rng(order)
+    cur = rng.uniform(0, 1, (n, n, n, 4))
+    out = []
+    for lib in _libs():
+        uj = np.zeros((N, N, N, 4))
+        for _ in range(5):
+            lib.nixo_append_current3d(order, uj.ctypes.data_as(PD), N, N, 2, 2, 2, cur.ctypes.data_as(PD))
+        box = uj[2:2 + n, 2:2 + n, 2:2 + n]
+        assert np.abs(box - 5 * cur).sum() <= 1e-14 * np.abs(box).sum()
+        uj[2:2 + n, 2:2 + n, 2:2 + n] = 0
+        assert not uj.any()
+        out.append(box.copy())
+    assert all(np.array_equal(out[0], o) for o in out)  # port == reference, bit for bit
+
+
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
+def test_append_moment3d_adds_the_local_mesh(order):
+    """test_primitives.cpp:1236-1300: the same for the 14 moments of one species on the (order+1)^3 mesh."""
+    n, N, ns = order + 1, 16, 2
+    rng = np.random.default_rng(10 + order)
+    mom = rng.uniform(0, 1, (n, n, n, 14))
+    out = []
+    for lib in _libs():
+        um = np.zeros((N, N, N, ns, 14))
+        for _ in range(5):
+            lib.nixo_append_moment3d(order, um.ctypes.data_as(PD), N, N, ns, 3, 2, 4, 1, mom.ctypes.data_as(PD))
+        box = um[3:3 + n, 2:2 + n, 4:4 + n, 1]
+        assert np.abs(box - 5 * mom).sum() <= 1e-14 * np.abs(box).sum()
+        assert not um[..., 0, :].any()
+        um[3:3 + n, 2:2 + n, 4:4 + n, 1] = 0
+        assert not um.any()
+        out.append(box.copy())
+    assert all(np.array_equal(out[0], o) for o in out)
