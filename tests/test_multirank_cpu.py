@@ -48,13 +48,20 @@ def test_uniform_boundary_matches_balancer_known_answer():
     assert list(core.uniform_boundary(160, 8)) == [20 * i for i in range(9)]
 
 
-@pytest.mark.parametrize("cdims,nrank", [((2, 2, 4), 2), ((3, 2, 2), 3), ((4, 4, 4), 8), ((2, 1, 2), 2), ((1, 1, 2), 2)])
+@pytest.mark.parametrize("cdims,nrank", [((2, 2, 4), 2), ((3, 2, 2), 3), ((4, 4, 4), 8), ((2, 1, 2), 2), ((1, 1, 2), 2),
+                                         ((2, 2, 4), [0, 4, 9, 14, 16])])
 def test_plan_pairs_up(cdims, nrank):
     """What rank r sends to rank p is, entry by entry, what p expects from r; every slab whose
-    neighbour lives elsewhere is listed exactly once."""
+    neighbour lives elsewhere is listed exactly once.  The last case is the uneven boundary array of the
+    reference's own ChunkMap tests (unittest/test_chunkmap.cpp:127-160: Cz, Cy, Cx = 2, 2, 4, boundary
+    {0, 4, 9, 14, 16}; an id belongs to the rank whose range holds it, chunkmap.cpp:156-164)."""
     prob = Problem(cdims, (8, 6, 4), 2, ppc=1)
     nchunk = int(np.prod(cdims))
-    bd = core.uniform_boundary(nchunk, nrank)
+    if isinstance(nrank, list):
+        bd, nrank = np.array(nrank), len(nrank) - 1
+        assert [int(np.searchsorted(bd, i, side="right") - 1) for i in (0, 3, 4, 8, 9, 13, 14, 15)] == [0, 0, 1, 1, 2, 2, 3, 3]
+    else:
+        bd = core.uniform_boundary(nchunk, nrank)
     plans = [core.Plan(cdims, prob.dims, prob.nb, prob.coord, bd, r) for r in range(nrank)]
     owner = lambda i: int(np.searchsorted(bd, i, side="right") - 1)  # noqa: E731  ChunkMap::get_rank
     grid2id = {tuple(int(v) for v in c): i for i, c in enumerate(prob.coord)}
