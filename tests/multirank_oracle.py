@@ -92,6 +92,56 @@ class RankOracle:
                     rb[addr[e]:addr[e] + len(m)] = np.frombuffer(m, dtype=np.uint8)
             c.halo_unpack(mode)
 
+    def rebalance(self, new_boundary):
+        """Move to new rank boundaries the way nixb200_domain_rebalance does (host logic: nixb200_rebalance_moves):
+        what leaves at the low end goes to rank-1, at the high end to rank+1 (Balancer::sendrecv_chunk,
+        balancer.hpp:122-332); a chunk travels as its state between steps -- E/B, J and the cell-sorted particles
+        of every species."""
+        import pickle
+        nrank = len(self.boundary) - 1
+        new_boundary = np.asarray(new_boundary)
+        old = (int(self.boundary[self.rank]), int(self.boundary[self.rank + 1]))
+        new = (int(new_boundary[self.rank]), int(new_boundary[self.rank + 1]))
+        rc, (sl, sr, rl, rr, keep) = core.rebalance_moves(old, new)
+        assert rc == 0, "old and new range of a rank must overlap"
+        prob = self.prob
+
+        def state(i):
+            c = self.chunks[i]
+            return (i, c.uf.copy(), c.uj.copy(), [c.particles(s) for s in range(prob.ns)])
+
+        for peer, send, recv in ((self.rank - 1, sl, rl), (self.rank + 1, sr, rr)):
+            if peer < 0 or peer >= nrank:
+                assert send[1] <= send[0] and recv[1] <= recv[0]
+                continue
+            out = pickle.dumps([state(i) for i in range(send[0], max(send))])
+            osz, isz = torch.tensor([len(out)], dtype=torch.int64), torch.zeros(1, dtype=torch.int64)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, osz, peer), dist.P2POp(dist.irecv, isz, peer)]):
+                q.wait()
+            obuf = torch.frombuffer(bytearray(out), dtype=torch.uint8)
+            ibuf = torch.zeros(int(isz), dtype=torch.uint8)
+            for q in dist.batch_isend_irecv([dist.P2POp(dist.isend, obuf, peer), dist.P2POp(dist.irecv, ibuf, peer)]):
+                q.wait()
+            got = pickle.loads(ibuf.numpy().tobytes())
+            assert [g[0] for g in got] == list(range(recv[0], max(recv)))
+            cd = prob.cdims
+            gdims = tuple(cd[a] * prob.dims[a] for a in range(3))
+            for i, uf, uj, parts in got:
+                off = tuple(int(prob.coord[i][a]) * prob.dims[a] for a in range(3))
+                c = no.Chunk(self.lib, prob.dims, prob.nb, prob.order, prob.ns, [max(1, len(x)) for x in parts], prob.q,
+                             prob.m, off, gdims, prob.delh)
+                c.uf[...] = uf
+                c.uj[...] = uj
+                for s2, x in enumerate(parts):
+                    c.set_particles(s2, x)
+                self.chunks[i] = c
+            for i in range(send[0], max(send)):
+                del self.chunks[i]
+        self.boundary = new_boundary
+        self.ids = list(range(new[0], new[1]))
+        assert sorted(self.chunks) == self.ids and (keep[1] - keep[0]) > 0
+        self.plan = core.Plan(prob.cdims, prob.dims, prob.nb, prob.coord, new_boundary, self.rank)
+
     def step(self, delt, cc):
         for c in self.chunks.values():
             c.uj[...] = 0.0

@@ -238,3 +238,68 @@ def test_plan_of_the_benchmarked_boxes(world):
                 assert e == 26 - d and n == m
                 assert grid2id[((int(coord[i][0]) + d // 9 - 1) % gcd[0], (int(coord[i][1]) + (d // 3) % 3 - 1) % gcd[1],
                                 (int(coord[i][2]) + d % 3 - 1) % gcd[2])] == j
+
+
+def _rebalance_worker(rank, world, port, q):
+    try:
+        import torch.distributed as dist
+        from oracle import nixoracle as no
+        from helpers import bits, oracle_domain
+        from multirank_oracle import RankOracle
+        from nix_b200 import balancer
+        dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+        lib = no.load("port")
+        # density rising along x: the uniform boundaries are not the balanced ones
+        prob = Problem((1, 2, 6), (8, 8, 8), 2, ppc=4, seed=55, vth=(0.35, 0.08),
+                       density=lambda c, cd: 0.4 + 1.6 * c[2] / (cd[2] - 1))
+        bd = [int(v) for v in core.uniform_boundary(prob.nchunk, world)]
+        ro = RankOracle(lib, prob, bd, rank)
+        ro.load()
+        ro.exchange(no.MODE_FIELD)
+        ro.sort_only()
+        full = oracle_domain(lib, prob)
+        history = [list(bd)]
+        for rnd in range(3):
+            for _ in range(2):
+                ro.step(0.5, 1.0)
+                full.step(0.5, 1.0)
+            # Chunk::load = particles per chunk (what GpuApplication::push() reports), all-gathered like
+            # Balancer::assign's input (balancer.hpp:116)
+            load = np.array([sum(full.chunks[i].np(s) for s in range(prob.ns)) for i in range(prob.nchunk)], dtype=np.float64)
+            new = balancer.assign(load, bd)
+            if new != bd:
+                ro.rebalance(new)
+                bd = new
+                history.append(list(bd))
+        for i in ro.ids:
+            a, b = ro.chunks[i], full.chunks[i]
+            assert np.array_equal(a.uf, b.uf), f"rank {rank} chunk {i}: E/B differ"
+            assert np.array_equal(bits(a.uj), bits(b.uj)), f"rank {rank} chunk {i}: J differs"
+            for s in range(prob.ns):
+                pa, pb = a.particles(s), b.particles(s)
+                assert pa.shape == pb.shape and np.array_equal(bits(pa), bits(pb)), f"rank {rank} chunk {i} sp {s}"
+        dist.barrier()
+        dist.destroy_process_group()
+        q.put((rank, "ok", len(history) - 1))
+    except Exception as exc:  # noqa: BLE001
+        import traceback
+        q.put((rank, "fail: " + "".join(traceback.format_exception(exc)), 0))
+
+
+def test_rank_split_oracle_with_rebalancing_equals_single_process(oracle_port):
+    """world_size-3 `gloo` run of the REBALANCE path's host logic: Balancer::assign (nix_b200/balancer.py) on the
+    per-chunk particle counts of a non-uniform box moves the rank boundaries between steps, chunks travel to
+    rank-1 / rank+1 as nixb200_rebalance_moves says, the plan is rebuilt -- and every rank still equals the
+    single-process oracle bit for bit afterwards."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    world = 3
+    procs = [ctx.Process(target=_rebalance_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = _collect(q, procs, 300)
+    for rank, status, _ in res:
+        assert status == "ok", f"rank {rank}: {status}"
+    assert all(m >= 1 for _, _, m in res), "the boundaries never moved: the rebalance path was not exercised"
