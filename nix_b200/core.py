@@ -151,6 +151,9 @@ def load_library():
     sig("nixb200_chunk_wire_pack", I, P, I, P, C.c_int64)
     sig("nixb200_domain_rebalance", I, P, I, PI, I)
     sig("nixb200_rebalance_moves", I, I, I, I, I, PI)
+    sig("nixb200_comm_create", I, I, I, P, I, C.POINTER(C.c_void_p))
+    sig("nixb200_comm_destroy", I, P)
+    sig("nixb200_device_count", I, PI)
     sig("nixb200_domain_reserve", I, P, I, C.c_int64, C.c_int64)
     sig("nixb200_domain_get_capacity", I, P, I, PL, PL)
     _lib = lib

@@ -272,6 +272,10 @@ int nixb200_chunk_wire_pack(nixb200_domain* dd, int k, void* buffer, int64_t byt
 // keeps ([keep0, keep1)); out[10] in that order.  Returns non-zero when the two ranges do not overlap.
 int nixb200_rebalance_moves(int b0, int e0, int b1, int e1, int* out)
 {
+  if (!out) {
+    set_error("rebalance_moves: null output");
+    return 1;
+  }
   out[0] = b0, out[1] = std::max(b0, std::min(b1, e0));  // leaving at the low end
   out[2] = std::min(e0, std::max(e1, b0)), out[3] = e0;  // leaving at the high end
   out[4] = b1, out[5] = std::max(b1, std::min(b0, e1));  // arriving at the low end (ids below b0)

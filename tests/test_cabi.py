@@ -58,3 +58,40 @@ def test_no_cpu_fallback():
     x = np.zeros(4)
     with pytest.raises(core.NixB200Error):
         core.shape_eval(0, 2, x, x, 1.0)
+
+
+_NULL_CALLS = r"""
+import ctypes as C, sys
+sys.path.insert(0, sys.argv[1])
+from nix_b200 import core
+lib = core.load_library()
+def default(t):
+    if t in (C.c_int, C.c_int64): return 0
+    if t is C.c_double: return 0.0
+    return None
+for name in core.SYMBOLS:
+    f = getattr(lib, name)
+    assert f.argtypes is not None or name in ("nixb200_last_error", "nixb200_version", "nixb200_launch_count"), name
+    print("CALL", name, flush=True)
+    r = f(*[default(t) for t in (f.argtypes or [])])
+    print("RET", name, r if not isinstance(r, bytes) else 0, flush=True)
+"""
+
+
+def test_null_arguments_are_refused_not_dereferenced(tmp_path):
+    """Error behaviour of the boundary (status codes, no exception, no crash crosses it): every entry
+    point called with a NULL handle / NULL pointers returns non-zero (or -1 for the counting getters) and leaves a
+    message; nothing dereferences the NULL.  Runs in a child process so that a fault would be reported, not fatal."""
+    import subprocess
+    import sys
+    script = tmp_path / "null_calls.py"
+    script.write_text(_NULL_CALLS)
+    p = subprocess.run([sys.executable, str(script), ROOT], capture_output=True, text=True, timeout=300)
+    lines = p.stdout.strip().splitlines()
+    assert p.returncode == 0, f"crashed in {lines[-1] if lines else '?'}: {p.stderr[-400:]}"
+    ret = {ln.split()[1]: int(ln.split()[2]) for ln in lines if ln.startswith("RET")}
+    assert set(ret) == set(core.SYMBOLS)
+    ok_with_null = {"nixb200_last_error", "nixb200_version", "nixb200_launch_count",
+                    "nixb200_domain_destroy", "nixb200_plan_destroy"}  # (destroying nothing is not an error)
+    wrong = {n: r for n, r in ret.items() if n not in ok_with_null and r == 0}
+    assert not wrong, wrong
