@@ -353,24 +353,7 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
     return 1;
   }
   *out = nullptr;
-  int ndev = 0;
-  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-    set_error("no CUDA device: libnixb200 has no CPU fallback");
-    return 1;
-  }
-  DeviceGuard dev_guard(desc->device);
-  int         cur = -1;
-  if (cudaGetDevice(&cur) != cudaSuccess || cur != desc->device) {
-    set_error("cannot select CUDA device " + std::to_string(desc->device));
-    return 1;
-  }
-  cudaDeviceProp prop;
-  NIX_CUDA(cudaGetDeviceProperties(&prop, desc->device));
-  if (prop.major != 10) {
-    set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
-              "; this library is built for sm_100a only");
-    return 1;
-  }
+  // the descriptor first (host only), then the device: a bad descriptor is reported as such on any machine
   if (desc->pusher < NIXB200_PUSH_BORIS || desc->pusher > NIXB200_PUSH_HIGUERA_CARY) {
     set_error("pusher must be NIXB200_PUSH_BORIS, _VAY or _HIGUERA_CARY");
     return 1;
@@ -392,8 +375,38 @@ int nixb200_domain_create(const nixb200_domain_desc* desc, const int* coord, con
       set_error("chunk dims must be >= boundary margin and cdims >= 1");
       return 1;
     }
+    if (!(desc->del[a] > 0.0)) {
+      set_error("cell sizes must be positive");
+      return 1;
+    }
+  }
+  if (!(desc->cc > 0.0)) {
+    set_error("the speed of light must be positive");
+    return 1;
+  }
+  if (desc->id_begin < 0 || desc->id_end > desc->cdims[0] * desc->cdims[1] * desc->cdims[2]) {
+    set_error("chunk id range outside the box");
+    return 1;
   }
 
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: libnixb200 has no CPU fallback");
+    return 1;
+  }
+  DeviceGuard dev_guard(desc->device);
+  int         cur = -1;
+  if (cudaGetDevice(&cur) != cudaSuccess || cur != desc->device) {
+    set_error("cannot select CUDA device " + std::to_string(desc->device));
+    return 1;
+  }
+  cudaDeviceProp prop;
+  NIX_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) {
+    set_error(std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) +
+              "; this library is built for sm_100a only");
+    return 1;
+  }
   Domain* d = new Domain();
   d->desc   = *desc;
   d->fp32   = desc->fp32 != 0;

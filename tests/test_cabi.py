@@ -95,3 +95,29 @@ def test_null_arguments_are_refused_not_dereferenced(tmp_path):
                     "nixb200_domain_destroy", "nixb200_plan_destroy"}  # (destroying nothing is not an error)
     wrong = {n: r for n, r in ret.items() if n not in ok_with_null and r == 0}
     assert not wrong, wrong
+
+
+def test_descriptor_is_validated_before_the_device():
+    """A bad nixb200_domain_desc is reported as such on any machine (the checks are host logic and run before the
+    device is looked for); a GOOD one still fails here, loudly, for want of a device (test_no_cpu_fallback)."""
+    q, m = [-1.0, 1.0], [1.0, 25.0]
+    bad = [
+        (dict(order=4, nb=3), "order"),
+        (dict(order=0, nb=2), "order"),
+        (dict(order=3, nb=2), "boundary margin"),  # stencil of order 3 needs three ghost layers
+        (dict(order=2, nb=1), "boundary margin"),
+        (dict(order=2, nb=2, dims=(8, 1, 8)), "chunk dims"),
+        (dict(order=2, nb=2, cdims=(2, 0, 2), id_range=(0, 1)), "cdims"),
+        (dict(order=2, nb=2, delh=(1.0, 0.0, 1.0)), "cell sizes"),
+        (dict(order=2, nb=2, cc=0.0), "speed of light"),
+        (dict(order=2, nb=2, pusher=7), "pusher"),
+        (dict(order=2, nb=2, id_range=(3, 3)), "empty domain"),
+        (dict(order=2, nb=2, id_range=(0, 9)), "chunk id range"),
+        (dict(order=2, nb=2, q=[], m=[]), "empty domain"),
+    ]
+    for kw, msg in bad:
+        kw = dict(kw)
+        args = dict(cdims=kw.pop("cdims", (2, 2, 2)), dims=kw.pop("dims", (8, 8, 8)), nb=kw.pop("nb"), order=kw.pop("order"),
+                    q=kw.pop("q", q), m=kw.pop("m", m))
+        with pytest.raises(core.NixB200Error, match=msg):
+            core.Domain(args["cdims"], args["dims"], args["nb"], args["order"], args["q"], args["m"], **kw)
