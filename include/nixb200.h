@@ -198,6 +198,8 @@ int nixb200_shape_eval(int device, int kind, int order, int n, const double* x, 
 /* ---- per-chunk halo buffers in the reference's MpiBuffer layout (chunk.cpp:257-286), for
  *      neighbours that live on another rank and for drop-in use behind Chunk::set_boundary_* ---- */
 int nixb200_halo_layout(nixb200_domain* d, int mode, int* bufsize27, int* bufaddr27);
+/* the same from the chunk shape alone (host logic, no device): dims = (Nz, Ny, Nx) */
+int nixb200_halo_layout_dims(const int* dims3, int nb, int mode, int* bufsize27, int* bufaddr27);
 int nixb200_chunk_halo_pack(nixb200_domain* d, int k, int mode, void* host_sendbuf);
 int nixb200_chunk_halo_unpack(nixb200_domain* d, int k, int mode, const void* host_recvbuf,
                               const int* nbvalid27);

@@ -38,7 +38,7 @@ SYMBOLS = [
     "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
     "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance", "nixb200_domain_history_async",
-    "nixb200_rebalance_moves",
+    "nixb200_rebalance_moves", "nixb200_halo_layout_dims",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -112,6 +112,7 @@ def load_library():
     sig("nixb200_domain_push_deposit", I, P, D)
     sig("nixb200_domain_step", I, P, D)
     sig("nixb200_halo_layout", I, P, I, PI, PI)
+    sig("nixb200_halo_layout_dims", I, PI, I, I, PI, PI)
     sig("nixb200_chunk_halo_pack", I, P, I, I, P)
     sig("nixb200_chunk_halo_unpack", I, P, I, I, P, PI)
     sig("nixb200_domain_field_upload_async", I, P, I, P)
@@ -224,6 +225,16 @@ def rebalance_moves(old, new):
     rc = lib.nixb200_rebalance_moves(int(old[0]), int(old[1]), int(new[0]), int(new[1]), out)
     v = list(out)
     return rc, [(v[0], v[1]), (v[2], v[3]), (v[4], v[5]), (v[6], v[7]), (v[8], v[9])]
+
+
+def halo_layout_dims(dims, nb, mode):
+    """(bufsize[27], bufaddr[27]) of a chunk's MpiBuffer (Chunk::set_mpi_buffer, chunk.cpp:257-286) from its shape"""
+    lib = load_library()
+    d = (C.c_int * 3)(*[int(v) for v in dims])
+    bs, ba = (C.c_int * 27)(), (C.c_int * 27)()
+    if lib.nixb200_halo_layout_dims(d, int(nb), int(mode), bs, ba):
+        raise NixB200Error(lib.nixb200_last_error().decode())
+    return np.array(bs, dtype=np.int32), np.array(ba, dtype=np.int32)
 
 
 def uniform_boundary(nchunk, nrank):

@@ -1271,18 +1271,19 @@ int nixb200_shape_eval(int device, int kind, int order, int n, const double* x, 
   return rc;
 }
 
-int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufaddr27)
+// Chunk::set_mpi_buffer, chunk.cpp:257-286 (headbyte 0, elembyte 8 * ncomp): host logic, no device needed
+int nixb200_halo_layout_dims(const int* dims, int nb, int mode, int* bufsize27, int* bufaddr27)
 {
-  NIX_ENTER(dd);
-  if (!d || !bufsize27 || !bufaddr27) return 1;
+  if (!dims || !bufsize27 || !bufaddr27 || nb < 1 || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) {
+    set_error("halo_layout: bad argument");
+    return 1;
+  }
   if (mode != NIXB200_MODE_FIELD && mode != NIXB200_MODE_CURRENT) {
     set_error("halo_layout: fixed layouts exist for field and current only");
     return 1;
   }
-  // Chunk::set_mpi_buffer, chunk.cpp:257-286 (headbyte 0, elembyte 8*ncomp)
-  const Geo& g    = d->geo;
-  const int  elem = 8 * ((mode == NIXB200_MODE_FIELD) ? 6 : 4);
-  int        size = 0;
+  const int elem = 8 * ((mode == NIXB200_MODE_FIELD) ? 6 : 4);
+  int       size = 0;
   for (int s = 0; s < 27; s++) {
     bufaddr27[s] = size;
     if (s == 13) {
@@ -1291,11 +1292,17 @@ int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufad
     }
     int e[3] = {s / 9, (s / 3) % 3, s % 3};
     int cnt  = 1;
-    for (int a = 0; a < 3; a++) cnt *= (e[a] == 1) ? g.N[a] : g.nb;
+    for (int a = 0; a < 3; a++) cnt *= (e[a] == 1) ? dims[a] : nb;
     bufsize27[s] = elem * cnt;
     size += bufsize27[s];
   }
   return 0;
+}
+
+int nixb200_halo_layout(nixb200_domain* dd, int mode, int* bufsize27, int* bufaddr27)
+{
+  NIX_ENTER(dd);
+  return nixb200_halo_layout_dims(d->geo.N, d->geo.nb, mode, bufsize27, bufaddr27);
 }
 
 int nixb200_chunk_halo_pack(nixb200_domain* dd, int k, int mode, void* host_sendbuf)

@@ -121,3 +121,26 @@ def test_descriptor_is_validated_before_the_device():
                     q=kw.pop("q", q), m=kw.pop("m", m))
         with pytest.raises(core.NixB200Error, match=msg):
             core.Domain(args["cdims"], args["dims"], args["nb"], args["order"], args["q"], args["m"], **kw)
+
+
+@pytest.mark.parametrize("dims,nb", [((8, 8, 8), 1), ((8, 8, 8), 2), ((16, 16, 16), 2), ((32, 32, 32), 3), ((6, 8, 10), 2)])
+def test_halo_buffer_layout_equals_the_reference_mpibuffer(dims, nb):
+    """a12 on the CPU: the library's MpiBuffer layout (27 slots in z, y, x order, running-sum addresses, empty centre
+    slot) equals what the reference's Chunk::set_mpi_buffer (chunk.cpp:257-286) builds -- read from the oracle port
+    and, where it is built, from the reference's own class -- for E/B (48 B per cell) and J (32 B per cell).
+    SURVEY.md 8a quotes 666 624 / 444 416 bytes per exchange for 32^3 cells and two ghost layers."""
+    from oracle import nixoracle as no
+    for which in ("port", "ref"):
+        if not no.available(which):
+            continue
+        c = no.Chunk(no.load(which), dims, nb, 2 if nb >= 2 else 1)
+        for mode, omode in ((core.MODE_FIELD, no.MODE_FIELD), (core.MODE_CURRENT, no.MODE_CURRENT)):
+            bs, ba = core.halo_layout_dims(dims, nb, mode)
+            assert np.array_equal(bs, c.bufsize(omode)), (which, mode)
+            assert np.array_equal(ba, c.bufaddr(omode)), (which, mode)
+    bs, _ = core.halo_layout_dims((32, 32, 32), 2, core.MODE_FIELD)
+    assert int(bs.sum()) == 666624
+    bs, _ = core.halo_layout_dims((32, 32, 32), 2, core.MODE_CURRENT)
+    assert int(bs.sum()) == 444416
+    with pytest.raises(core.NixB200Error, match="field and current"):
+        core.halo_layout_dims((8, 8, 8), 2, core.MODE_PARTICLE)
