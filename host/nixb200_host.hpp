@@ -234,6 +234,51 @@ public:
   bool set_boundary_probe(int, bool) override { return true; }
 };
 
+/// XtensorPacker3D (xtensor_packer3d.hpp:15-140) for chunks whose data live on the device: what a downstream
+/// Packer functor of nix::ChunkWriter (diag/chunk_writer.hpp:118-146) calls instead of sync_host() + the host
+/// packer.  Same conventions -- the return value is `address + bytes`, buffer == nullptr only queries -- and the
+/// same bytes: the device packers (csrc/diag.cu) reproduce the reference's colocation, block averages and
+/// rounding bit for bit, so only the PACKED output crosses PCIe.  The chunk must be resident in its rank's
+/// domain (after the first push(), or after an explicit GpuApplication::ensure_domain()).
+class GpuPacker3D
+{
+  static nixb200_domain* handle(GpuChunk& c)
+  {
+    if (!c.domain || c.local < 0 || c.host_is_newer)
+      throw std::runtime_error("GpuPacker3D: chunk is not resident on the device (call ensure_domain() first)");
+    return c.domain->h;
+  }
+
+public:
+  /// pack_field (xtensor_packer3d.hpp:62-82): E/B colocated at the cell centres, block-averaged by `decimate`
+  size_t pack_field(GpuChunk& c, int decimate, uint8_t* buffer, int address)
+  {
+    int64_t n = 0;
+    check(nixb200_chunk_pack_field(handle(c), c.local, decimate, nullptr, &n), "pack_field");
+    if (buffer) check(nixb200_chunk_pack_field(handle(c), c.local, decimate, reinterpret_cast<double*>(buffer + address), &n), "pack_field");
+    return sizeof(float64) * (size_t)n + address;
+  }
+
+  /// pack_moment (:84-104): block averages of uj (which = 0) or of the ns x 14 moments (which = 1; after
+  /// nixb200_domain_deposit_moment)
+  size_t pack_moment(GpuChunk& c, int which, int decimate, uint8_t* buffer, int address)
+  {
+    int64_t n = 0;
+    check(nixb200_chunk_pack_moment(handle(c), c.local, which, decimate, nullptr, &n), "pack_moment");
+    if (buffer) check(nixb200_chunk_pack_moment(handle(c), c.local, which, decimate, reinterpret_cast<double*>(buffer + address), &n), "pack_moment");
+    return sizeof(float64) * (size_t)n + address;
+  }
+
+  /// pack_tracer (:122-140): the particles of species `is` with a negative 64-bit id, in container order
+  size_t pack_tracer(GpuChunk& c, int is, uint8_t* buffer, int address)
+  {
+    int64_t np = 0;
+    check(nixb200_chunk_pack_tracer(handle(c), c.local, is, nullptr, 0, &np), "pack_tracer");
+    if (buffer && np > 0) check(nixb200_chunk_pack_tracer(handle(c), c.local, is, reinterpret_cast<double*>(buffer + address), np, &np), "pack_tracer");
+    return sizeof(float64) * 7 * (size_t)np + address;
+  }
+};
+
 /// Application::Interface whose factory makes GpuChunks (application.hpp:45-48); used at set-up, on
 /// rebalance receive (balancer.hpp:216) and on checkpoint load (statehandler.hpp:297)
 class GpuInterface : public nix::Application::Interface
