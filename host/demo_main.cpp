@@ -67,6 +67,29 @@ int main(int argc, char** argv)
     std::printf("\n");
     return 0;
   }
+  if (argc >= 8 && std::string(argv[1]) == "wiresize") {
+    // demo wiresize Nz Ny Nx nb order np_0 [np_1 ...] : bytes a PIC chunk appends to nix::Chunk::pack's own header,
+    // measured by the reference's OWN pack() in query mode (chunk.cpp:18-60, xtensor_particle.hpp:128-169) on
+    // containers sized for exactly np particles.  Host only: no device, no domain.
+    const int dz = atoi(argv[2]), dy = atoi(argv[3]), dx = atoi(argv[4]), nb = atoi(argv[5]), order = atoi(argv[6]);
+    GpuInterface factory;
+    auto         c = factory.create_chunk(nix::Dims3D{dz, dy, dx}, nix::Bool3D{true, true, true}, 0);
+    auto*        g = static_cast<GpuChunk*>(c.get());
+    int          offset[3] = {0, 0, 0}, gdims[3] = {dz, dy, dx};
+    g->set_boundary_margin(nb);
+    g->set_global_context(offset, gdims);
+    g->set_coordinate(1.0, 1.0, 1.0);
+    g->allocate_staging(order, nb, {}, 0);
+    for (int i = 7; i < argc; i++) {
+      const int np = atoi(argv[i]);
+      auto      p  = std::make_shared<nix::XtensorParticle>(np, *g);
+      p->Np        = np;
+      g->up.push_back(p);
+    }
+    const int all = g->pack(nullptr, 0), hdr = g->nix::Chunk::pack(nullptr, 0);
+    std::printf("%d %d\n", hdr, all - hdr);
+    return 0;
+  }
   if (argc < 12 || std::string(argv[1]) != "run") {
     std::fprintf(stderr, "usage: demo coord Cz Cy Cx | demo run dir Cz Cy Cx N order nb ns ppc_max steps\n");
     return 2;

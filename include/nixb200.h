@@ -255,6 +255,9 @@ int nixb200_domain_peer_traffic(nixb200_domain* d, int64_t* halo_cells_sent, int
  *   re-sized arrays.  On return the handle covers [boundary[rank], boundary[rank+1]), rank tables and communicator
  *   are in place, counts are rebuilt.  Needs old + new arrays at once. */
 int nixb200_chunk_wire_size(nixb200_domain* d, int k, int64_t* bytes);
+/* the payload size from the chunk shape (Nz, Ny, Nx), the margin and the particle count of every species alone
+ * (host logic, no device) */
+int nixb200_wire_size_dims(const int* dims3, int nb, int ns, const int* np, int64_t* bytes);
 int nixb200_chunk_wire_pack(nixb200_domain* d, int k, void* buffer, int64_t bytes);
 int nixb200_domain_rebalance(nixb200_domain* d, int nrank, const int* boundary, int rank);
 /* host logic of it (no device needed): a rank that owned [b0, e0) and will own [b1, e1) sends [out0, out1) to rank-1 and

@@ -38,7 +38,7 @@ SYMBOLS = [
     "nixb200_device_count", "nixb200_domain_deposit_moment", "nixb200_chunk_moment_download",
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
     "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance", "nixb200_domain_history_async",
-    "nixb200_rebalance_moves", "nixb200_halo_layout_dims",
+    "nixb200_rebalance_moves", "nixb200_halo_layout_dims", "nixb200_wire_size_dims",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -149,6 +149,7 @@ def load_library():
     sig("nixb200_chunk_pack_tracer", I, P, I, I, PD, C.c_int64, PL)
     sig("nixb200_shape_eval", I, I, I, I, I, PD, PD, D, D, D, PD)
     sig("nixb200_chunk_wire_size", I, P, I, PL)
+    sig("nixb200_wire_size_dims", I, PI, I, I, PI, PL)
     sig("nixb200_chunk_wire_pack", I, P, I, P, C.c_int64)
     sig("nixb200_domain_rebalance", I, P, I, PI, I)
     sig("nixb200_rebalance_moves", I, I, I, I, I, PI)
@@ -235,6 +236,17 @@ def halo_layout_dims(dims, nb, mode):
     if lib.nixb200_halo_layout_dims(d, int(nb), int(mode), bs, ba):
         raise NixB200Error(lib.nixb200_last_error().decode())
     return np.array(bs, dtype=np.int32), np.array(ba, dtype=np.int32)
+
+
+def wire_size_dims(dims, nb, np_species):
+    """bytes of a chunk's payload in the reference's wire format (what follows nix::Chunk::pack's own header)"""
+    lib = load_library()
+    d = (C.c_int * 3)(*[int(v) for v in dims])
+    n = (C.c_int * len(np_species))(*[int(v) for v in np_species])
+    out = C.c_int64(0)
+    if lib.nixb200_wire_size_dims(d, int(nb), len(np_species), n, C.byref(out)):
+        raise NixB200Error(lib.nixb200_last_error().decode())
+    return out.value
 
 
 def uniform_boundary(nchunk, nrank):

@@ -37,21 +37,26 @@ struct WireLayout {
   std::vector<WireSpecies> sp;
 };
 
+WireLayout wire_layout(size_t cells, size_t ns, const int32_t* np);
+inline WireLayout wire_layout(const Domain* d, const int32_t* np)
+{
+  return wire_layout(d->cells_per_chunk, d->sp.size(), np);
+}
+
 int round_up_alloc(int np)
 {
   return ((np + 128) / 128) * 128; // particle.hpp:146-153
 }
 
-WireLayout wire_layout(const Domain* d, const int32_t* np)
+WireLayout wire_layout(size_t cells, size_t ns, const int32_t* np)
 {
-  WireLayout   w;
-  const size_t cells = d->cells_per_chunk;
-  size_t       a     = 0;
+  WireLayout w;
+  size_t     a = 0;
   w.order = a, a += 4;
   w.ns = a, a += 4;
   w.uf = a, a += cells * 6 * 8;
   w.uj = a, a += cells * 4 * 8;
-  for (size_t is = 0; is < d->sp.size(); is++) {
+  for (size_t is = 0; is < ns; is++) {
     WireSpecies s;
     s.np       = np[is];
     s.np_total = round_up_alloc(np[is]);
@@ -238,6 +243,23 @@ int nixb200_chunk_wire_size(nixb200_domain* dd, int k, int64_t* bytes)
   std::vector<int32_t> np(d->sp.size());
   for (size_t is = 0; is < np.size(); is++) np[is] = cb[is][k + 1] - cb[is][k];
   *bytes = (int64_t)wire_layout(d, np.data()).total;
+  return 0;
+}
+
+// the same from the chunk shape and the particle counts alone: host logic, no device
+int nixb200_wire_size_dims(const int* dims, int nb, int ns, const int* np, int64_t* bytes)
+{
+  if (!dims || !np || !bytes || nb < 0 || ns < 1 || dims[0] < 1 || dims[1] < 1 || dims[2] < 1) {
+    set_error("wire_size_dims: bad argument");
+    return 1;
+  }
+  for (int is = 0; is < ns; is++)
+    if (np[is] < 0) {
+      set_error("wire_size_dims: negative particle count");
+      return 1;
+    }
+  const size_t cells = (size_t)(dims[0] + 2 * nb) * (dims[1] + 2 * nb) * (dims[2] + 2 * nb);
+  *bytes             = (int64_t)wire_layout(cells, (size_t)ns, np).total;
   return 0;
 }
 

@@ -52,6 +52,30 @@ def test_chunkmap_order_is_a_space_filling_curve(demo, cdims):
     assert d2.max() <= 1
 
 
+@pytest.mark.parametrize("dims,nb,counts", [((8, 8, 8), 2, [100, 7]), ((16, 16, 16), 2, [262144, 262144]),
+                                            ((32, 32, 32), 3, [0, 1, 127, 128, 129]), ((6, 8, 10), 2, [4095])])
+def test_wire_payload_size_equals_the_reference_pack(demo, dims, nb, counts):
+    """Size of the chunk payload the DEVICE assembles (nixb200_chunk_wire_pack; layout arithmetic =
+    nixb200_wire_size_dims, host logic) against the reference's OWN pack() in query mode on containers of exactly
+    that many particles (`demo wiresize`: nix::Chunk::pack + XtensorParticle::pack, chunk.cpp:18-60,
+    xtensor_particle.hpp:128-169).  The CONTENT is compared on the GPU (test_demo_equals_oracle: the reference's
+    unpack reads the device-made record)."""
+    from nix_b200 import core
+    out = subprocess.run([demo, "wiresize"] + [str(v) for v in dims] + [str(nb), "2"] + [str(n) for n in counts],
+                         check=True, capture_output=True, text=True).stdout.split()
+    header, payload = int(out[0]), int(out[1])
+    assert header > 0
+    assert core.wire_size_dims(dims, nb, counts) == payload
+    # and the pieces, spelled out: order, ns, uf, uj, then per species 175 bytes of scalars, xu + xv [Np_total][7],
+    # gindex [Np_total], pindex [Ng + 1], pcount [Ng + 1][8] with Np_total = ((Np + 128) / 128) * 128
+    cells = int(np.prod([d + 2 * nb for d in dims]))
+    want = 8 + cells * 80
+    for n in counts:
+        npt = (n + 128) // 128 * 128
+        want += 175 + npt * (2 * 56 + 4) + (cells + 1) * 36
+    assert payload == want
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("order,cdims,n", [(2, (2, 2, 2), 8), (1, (2, 2, 4), 8), (3, (2, 2, 2), 8)])
 def test_demo_equals_oracle(demo, oracle_port, gpu_lib, tmp_path, order, cdims, n):
