@@ -208,3 +208,27 @@ def test_moments_halo_and_packers_bit_identical(oracle_port, oracle_ref, order):
         for s in range(prob.ns):
             ta, tb = a.pack_tracer(s), b.pack_tracer(s)
             assert len(ta) > 0 and np.array_equal(ta.view(np.int64), tb.view(np.int64))
+
+
+def test_baseline_config_1_at_its_stated_size(oracle_port, oracle_ref):
+    """BASELINE.json configs[0] -- "single chunk 32^3 cells, 64 ppc, 1st-order shape, periodic thermal electron-ion
+    plasma on CPU" -- at its stated size (4.2 M particles, one self-periodic chunk): the plain-C port equals the
+    reference's own templates bit for bit after a full step (push + Esirkepov deposit + halo + migration through
+    the chunk's own faces + count + sort)."""
+    prob = Problem((1, 1, 1), (32, 32, 32), 1, ppc=64, seed=1000, vth=(0.1, 0.02))
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    a.step(0.5, 1.0)
+    b.step(0.5, 1.0)
+    ca, cb = a.chunks[0], b.chunks[0]
+    assert np.array_equal(bits(ca.uj), bits(cb.uj))
+    for s in range(prob.ns):
+        assert ca.np(s) == cb.np(s) == 32 ** 3 * 64
+        assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s)))
+        assert np.array_equal(ca.pindex(s), cb.pindex(s))
+        assert np.array_equal(ca.pcount(s), cb.pcount(s))
+    # continuity of the deposit at this size (test_esirkepov.cpp:993-1028): sum of rho = total charge = 0 here,
+    # |rho| carries the scale
+    nb = prob.nb
+    rho = ca.uj[nb:-nb, nb:-nb, nb:-nb, 0]
+    assert abs(rho.sum()) <= 1e-12 * np.abs(rho).sum()
