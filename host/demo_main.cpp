@@ -90,6 +90,30 @@ int main(int argc, char** argv)
     std::printf("%d %d\n", hdr, all - hdr);
     return 0;
   }
+  if (argc == 17 && std::string(argv[1]) == "wirehdr") {
+    // demo wirehdr Nz Ny Nx nb delz dely delx oz oy ox gz gy gx q np : the first 175 bytes of the reference's OWN
+    // XtensorParticle::pack (xtensor_particle.hpp:130-159) for a chunk of that geometry, as hex.  Host only.
+    const int    d[3] = {atoi(argv[2]), atoi(argv[3]), atoi(argv[4])}, nb = atoi(argv[5]);
+    const double del[3] = {atof(argv[6]), atof(argv[7]), atof(argv[8])};
+    int          offset[3] = {atoi(argv[9]), atoi(argv[10]), atoi(argv[11])}, gdims[3] = {atoi(argv[12]), atoi(argv[13]), atoi(argv[14])};
+    const double q = atof(argv[15]);
+    const int    np = atoi(argv[16]);
+    GpuInterface factory;
+    auto         c = factory.create_chunk(nix::Dims3D{d[0], d[1], d[2]}, nix::Bool3D{true, true, true}, 0);
+    auto*        g = static_cast<GpuChunk*>(c.get());
+    g->set_boundary_margin(nb);
+    g->set_global_context(offset, gdims);
+    g->set_coordinate(del[0], del[1], del[2]);
+    nix::XtensorParticle p(np, *g);
+    p.Np = np;
+    p.q  = q;
+    p.m  = 25.0;
+    std::vector<uint8_t> buf(p.pack(nullptr, 0));
+    p.pack(buf.data(), 0);
+    for (int i = 0; i < 175; i++) std::printf("%02x", buf[i]);
+    std::printf("\n");
+    return 0;
+  }
   if (argc < 12 || std::string(argv[1]) != "run") {
     std::fprintf(stderr, "usage: demo coord Cz Cy Cx | demo run dir Cz Cy Cx N order nb ns ppc_max steps\n");
     return 2;

@@ -258,6 +258,10 @@ int nixb200_chunk_wire_size(nixb200_domain* d, int k, int64_t* bytes);
 /* the payload size from the chunk shape (Nz, Ny, Nx), the margin and the particle count of every species alone
  * (host logic, no device) */
 int nixb200_wire_size_dims(const int* dims3, int nb, int ns, const int* np, int64_t* bytes);
+/* the 175 scalar bytes XtensorParticle::pack opens a species with (xtensor_particle.hpp:130-159; host logic): offset3 /
+ * gdims3 in cells as Chunk::set_global_context takes them (chunk.cpp:239-247), triples in (z, y, x) order */
+int nixb200_wire_particle_header(const int* dims3, int nb, const double* del3, const int* offset3, const int* gdims3,
+                                 double q, double m, int np, void* out175);
 int nixb200_chunk_wire_pack(nixb200_domain* d, int k, void* buffer, int64_t bytes);
 int nixb200_domain_rebalance(nixb200_domain* d, int nrank, const int* boundary, int rank);
 /* host logic of it (no device needed): a rank that owned [b0, e0) and will own [b1, e1) sends [out0, out1) to rank-1 and

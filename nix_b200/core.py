@@ -39,6 +39,7 @@ SYMBOLS = [
     "nixb200_chunk_pack_field", "nixb200_chunk_pack_moment", "nixb200_chunk_pack_tracer", "nixb200_shape_eval",
     "nixb200_chunk_wire_size", "nixb200_chunk_wire_pack", "nixb200_domain_rebalance", "nixb200_domain_history_async",
     "nixb200_rebalance_moves", "nixb200_halo_layout_dims", "nixb200_wire_size_dims",
+    "nixb200_wire_particle_header",
 ]
 
 PHASES = ("push_deposit", "exchange_current", "exchange_field", "migrate_sort", "sort", "k_push", "k_deposit",
@@ -150,6 +151,7 @@ def load_library():
     sig("nixb200_shape_eval", I, I, I, I, I, PD, PD, D, D, D, PD)
     sig("nixb200_chunk_wire_size", I, P, I, PL)
     sig("nixb200_wire_size_dims", I, PI, I, I, PI, PL)
+    sig("nixb200_wire_particle_header", I, PI, I, PD, PI, PI, D, D, I, P)
     sig("nixb200_chunk_wire_pack", I, P, I, P, C.c_int64)
     sig("nixb200_domain_rebalance", I, P, I, PI, I)
     sig("nixb200_rebalance_moves", I, I, I, I, I, PI)
@@ -247,6 +249,18 @@ def wire_size_dims(dims, nb, np_species):
     if lib.nixb200_wire_size_dims(d, int(nb), len(np_species), n, C.byref(out)):
         raise NixB200Error(lib.nixb200_last_error().decode())
     return out.value
+
+
+def wire_particle_header(dims, nb, delh, offset, gdims, q, m, np_):
+    """the 175 scalar bytes XtensorParticle::pack opens a species with, as the device-made chunk record carries them"""
+    lib = load_library()
+    buf = (C.c_ubyte * 175)()
+    rc = lib.nixb200_wire_particle_header((C.c_int * 3)(*[int(v) for v in dims]), int(nb), (C.c_double * 3)(*[float(v) for v in delh]),
+                                          (C.c_int * 3)(*[int(v) for v in offset]), (C.c_int * 3)(*[int(v) for v in gdims]),
+                                          float(q), float(m), int(np_), C.cast(buf, C.c_void_p))
+    if rc:
+        raise NixB200Error(lib.nixb200_last_error().decode())
+    return bytes(buf)
 
 
 def uniform_boundary(nchunk, nrank):

@@ -72,31 +72,38 @@ WireLayout wire_layout(size_t cells, size_t ns, const int32_t* np)
   return w;
 }
 
-// the 175 scalar bytes of XtensorParticle::pack for species `is` of local chunk k
-void particle_header(const Domain* d, int k, int is, const WireSpecies& ws, unsigned char* out)
+// the 175 scalar bytes of XtensorParticle::pack (xtensor_particle.hpp:130-159) from plain numbers (host logic):
+// dims / del / origin / glo / ghi in (z, y, x) order; origin = the chunk's lower corner, offset * del (chunk.cpp:217-232)
+void particle_header_plain(const int* dims, int nb, const double* del, const double* origin, const double* glo,
+                           const double* ghi, double q, double m, int np, int np_total, unsigned char* out)
 {
-  const Geo&     g  = d->geo;
-  const double*  o  = &d->origin_host[3 * k]; // z, y, x
-  unsigned char* p  = out;
+  unsigned char* p = out;
   auto put = [&](const void* v, size_t n) {
     std::memcpy(p, v, n);
     p += n;
   };
-  const int    Ng = (int)d->cells_per_chunk;
-  const double q = d->sp[is].q, m = d->sp[is].m;
-  const bool   yes = true;
-  put(&ws.np_total, 4), put(&ws.np, 4), put(&Ng, 4), put(&q, 8), put(&m, 8);
+  const int  Ng  = (dims[0] + 2 * nb) * (dims[1] + 2 * nb) * (dims[2] + 2 * nb);
+  const bool yes = true;
+  put(&np_total, 4), put(&np, 4), put(&Ng, 4), put(&q, 8), put(&m, 8);
   put(&yes, 1), put(&yes, 1), put(&yes, 1);
   for (int a = 2; a >= 0; a--) { // Lbx Ubx Lby Uby Lbz Ubz
-    const int lb = g.nb, ub = g.nb + g.N[a] - 1;
+    const int lb = nb, ub = nb + dims[a] - 1;
     put(&lb, 4), put(&ub, 4);
   }
-  for (int a = 2; a >= 0; a--) put(&g.del[a], 8); // delx dely delz
-  for (int a = 2; a >= 0; a--) {                  // xmin xmax ymin ymax zmin zmax (chunk.cpp:217-232)
-    const double lo = o[a], hi = o[a] + g.N[a] * g.del[a];
+  for (int a = 2; a >= 0; a--) put(&del[a], 8); // delx dely delz
+  for (int a = 2; a >= 0; a--) {                // xmin xmax ymin ymax zmin zmax (chunk.cpp:217-232)
+    const double lo = origin[a], hi = origin[a] + dims[a] * del[a];
     put(&lo, 8), put(&hi, 8);
   }
-  for (int a = 2; a >= 0; a--) put(&g.glo[a], 8), put(&g.ghi[a], 8);
+  for (int a = 2; a >= 0; a--) put(&glo[a], 8), put(&ghi[a], 8);
+}
+
+// ... for species `is` of local chunk k
+void particle_header(const Domain* d, int k, int is, const WireSpecies& ws, unsigned char* out)
+{
+  const Geo& g = d->geo;
+  particle_header_plain(g.N, g.nb, g.del, &d->origin_host[3 * k], g.glo, g.ghi, d->sp[is].q, d->sp[is].m, ws.np, ws.np_total,
+                        out);
 }
 
 // pindex [Ng+1] / pcount [Ng+1][8] of one chunk in the reference's layout from the device's compact scan
@@ -260,6 +267,25 @@ int nixb200_wire_size_dims(const int* dims, int nb, int ns, const int* np, int64
     }
   const size_t cells = (size_t)(dims[0] + 2 * nb) * (dims[1] + 2 * nb) * (dims[2] + 2 * nb);
   *bytes             = (int64_t)wire_layout(cells, (size_t)ns, np).total;
+  return 0;
+}
+
+// the 175 scalar bytes that open a species' part of the record (host logic): offset / gdims in cells as
+// Chunk::set_global_context takes them (chunk.cpp:239-247), all triples in (z, y, x) order
+int nixb200_wire_particle_header(const int* dims, int nb, const double* del, const int* offset, const int* gdims, double q,
+                                 double m, int np, void* out175)
+{
+  if (!dims || !del || !offset || !gdims || !out175 || nb < 0 || np < 0) {
+    set_error("wire_particle_header: bad argument");
+    return 1;
+  }
+  double origin[3], glo[3], ghi[3];
+  for (int a = 0; a < 3; a++) {
+    origin[a] = offset[a] * del[a]; // domain.cu: origin_host, cg.lo
+    glo[a]    = 0.0;
+    ghi[a]    = gdims[a] * del[a]; // domain.cu: g.ghi = (cdims * dims) * del
+  }
+  particle_header_plain(dims, nb, del, origin, glo, ghi, q, m, np, round_up_alloc(np), reinterpret_cast<unsigned char*>(out175));
   return 0;
 }
 

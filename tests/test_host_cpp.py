@@ -76,6 +76,25 @@ def test_wire_payload_size_equals_the_reference_pack(demo, dims, nb, counts):
     assert payload == want
 
 
+@pytest.mark.parametrize("dims,nb,delh,offset,gdims,q,np_", [
+    ((8, 8, 8), 2, (1.0, 1.0, 1.0), (0, 0, 0), (16, 16, 16), -1.0, 0),
+    ((8, 6, 10), 2, (0.5, 1.25, 2.0), (16, 6, 30), (32, 24, 40), -1.0, 100),
+    ((32, 32, 32), 3, (0.1, 0.1, 0.1), (224, 96, 0), (256, 256, 256), 1.0, 524288),
+    ((16, 16, 16), 2, (1.0, 1.0, 1.0), (112, 0, 48), (128, 128, 128), 1.0, 127)])
+def test_wire_particle_header_equals_the_reference_pack(demo, dims, nb, delh, offset, gdims, q, np_):
+    """The 175 scalar bytes that open a species in the device-made chunk record (made on the host side of the
+    library: Np_total, Np, Ng, q, m, the three has_dim flags, Lb / Ub per axis, cell sizes, the chunk's and the box's
+    coordinate ranges) against the first 175 bytes of the reference's OWN XtensorParticle::pack
+    (xtensor_particle.hpp:130-159) for a chunk of the same geometry (`demo wirehdr`): byte for byte, including
+    anisotropic cells and a chunk away from the origin."""
+    from nix_b200 import core
+    args = [str(v) for v in dims] + [str(nb)] + [repr(float(v)) for v in delh] + [str(v) for v in offset] + \
+        [str(v) for v in gdims] + [repr(float(q)), str(np_)]
+    ref = subprocess.run([demo, "wirehdr"] + args, check=True, capture_output=True, text=True).stdout.strip()
+    assert len(ref) == 350
+    assert core.wire_particle_header(dims, nb, delh, offset, gdims, q, 25.0, np_).hex() == ref
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("order,cdims,n", [(2, (2, 2, 2), 8), (1, (2, 2, 4), 8), (3, (2, 2, 2), 8)])
 def test_demo_equals_oracle(demo, oracle_port, gpu_lib, tmp_path, order, cdims, n):
