@@ -61,6 +61,14 @@ namespace
 #define NIX_MOVER_AGGREGATE 0 // 1: sum the lanes of a mover flush that target the same nodes before the atomics
                                // (match_any + shuffles; measured slower: k_deposit 23.3 instead of 20.8 ms per step)
 #endif
+#ifndef NIX_J_FIXED
+#define NIX_J_FIXED 0 // 1 (EXPERIMENT, never run on a device: prepared after the round's GPU budget was spent): the fp64 J
+                      // tile of k_deposit holds 64-bit FIXED-POINT words and is added to with two NATIVE 32-bit shared-memory
+                      // atomics (low word, carry into the high word: exact and order-independent) instead of the
+                      // compare-and-swap loops an fp64 shared-memory atomicAdd compiles to (profiles/r02f_lines_dep_*.md:
+                      // 25.8 % of the stall samples of the electron launch); converted back once per CTA in the global
+                      // flush.  Resolution: 2^-45 of the largest per-particle contribution.  fp32 instantiations unchanged.
+#endif
 #ifndef NIX_MOV_FLUSH
 #define NIX_MOV_FLUSH NIX_MAXMOV // flush whole groups of XGROUP records: the expansion and face-node lanes stay busy
 #endif
@@ -314,6 +322,10 @@ __device__ __forceinline__ void deposit_round(const T* wq, int p, int plc, bool 
   plane_accumulate<O, T>(s0z, dsz, cpz, ty, tx, q, qd, acc);
 }
 
+#if NIX_J_FIXED
+#include "jfixed.cuh"
+#endif
+
 // N independent fp64 additions to shared memory.  fp64 shared-memory atomics are compare-and-swap
 // loops; running the N loops of a lane in lock step overlaps their round trips.
 template <int N, typename T>
@@ -427,7 +439,14 @@ __device__ __forceinline__ void flush_group(T* s_j, const T* myrec, int* myml, i
       const int st = (ax == 0) ? JY * JX : ((ax == 1) ? JX : 1);
       T* const  ad[5]   = {dst, dst + C::JC, dst + 2 * C::JC, dst + 3 * C::JC, dst + st + (3 - ax) * C::JC};
       bool      todo[5] = {val[0] != T(0.0), val[1] != T(0.0), val[2] != T(0.0), val[3] != T(0.0), low && val[4] != T(0.0)};
+#if NIX_J_FIXED
+      const T jsc = jt_scale<T>(q, qdz, qdy, qdx);
+#pragma unroll
+      for (int k = 0; k < 5; k++)
+        if (todo[k]) jt_add<T>(ad[k], val[k], jsc);
+#else
       atomic_add_batch<5, T>(ad, val, todo);
+#endif
     }
   }
   // multi-axis movers: the whole (O+3)^3 mesh minus what the register path already holds
@@ -444,10 +463,18 @@ __device__ __forceinline__ void flush_group(T* s_j, const T* myrec, int* myml, i
       node(r, jz, jy, jx, rho, wx, wy, wz);
       T*      dst = s_j + cbase + (jz * JY + jy) * JX + jx;
       const T vx = wx * r[8 * NS + jx], vy = wy * r[5 * NS + jy], vz = wz * r[2 * NS + jz];
+#if NIX_J_FIXED
+      const T jsc = jt_scale<T>(q, qdz, qdy, qdx);
+      if (!central && rho != T(0.0)) jt_add<T>(dst, rho, jsc);
+      if (!(central && jx >= 2) && vx != T(0.0)) jt_add<T>(dst + C::JC, vx, jsc);
+      if (!(central && jy >= 2) && vy != T(0.0)) jt_add<T>(dst + 2 * C::JC, vy, jsc);
+      if (!(central && jz >= 2) && vz != T(0.0)) jt_add<T>(dst + 3 * C::JC, vz, jsc);
+#else
       if (!central && rho != T(0.0)) atomicAdd(dst, rho);
       if (!(central && jx >= 2) && vx != T(0.0)) atomicAdd(dst + C::JC, vx);
       if (!(central && jy >= 2) && vy != T(0.0)) atomicAdd(dst + 2 * C::JC, vy);
       if (!(central && jz >= 2) && vz != T(0.0)) atomicAdd(dst + 3 * C::JC, vz);
+#endif
     }
   }
   __syncwarp();
@@ -1013,7 +1040,11 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : (sizeof(T) == 4 ? 4 :
           T        sum = T(0.0);
 #pragma unroll
           for (int q = 0; q < NPS; q++) sum += src[q * PLW];
+#if NIX_J_FIXED
+          if (sum != T(0.0)) jt_add<T>(s_j + cellbase + (plg + 1) * JY * JX + s_tbl[v], sum, jt_scale<T>(P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]));
+#else
           if (sum != T(0.0)) atomicAdd(s_j + cellbase + (plg + 1) * JY * JX + s_tbl[v], sum);
+#endif
         }
       }
     }
@@ -1197,7 +1228,11 @@ __global__ void __launch_bounds__(DTHREADS, (O >= 3) ? 2 : (sizeof(T) == 4 ? 4 :
   __syncthreads();
   T* __restrict__ ujc = P.uj + (size_t)ch * g.M[0] * g.M[1] * g.M[2] * 4;
   for (int t = tid; t < JZ * JY * JX * 4; t += DTHREADS) {
+#if NIX_J_FIXED
+    const T v = jt_read<T>(s_j + (t & 3) * C::JC + (t >> 2), T(1.0) / jt_scale<T>(P.q, P.qdxdt[0], P.qdxdt[1], P.qdxdt[2]));
+#else
     const T v = s_j[(t & 3) * C::JC + (t >> 2)];
+#endif
     if (v != T(0.0)) {
       const int k = t & 3, n = t >> 2;
       const int gx = jx0 + n % JX, gy = jy0 + (n / JX) % JY, gz = jz0 + n / (JX * JY);
