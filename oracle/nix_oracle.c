@@ -18,7 +18,7 @@
 #define NC 7          /* particle.hpp:18  */
 #define ALLOC_UNIT 128 /* particle.hpp:19  */
 #define LANES 8       /* nix.hpp:105-108  */
-#define MAXO 3
+#define MAXO 4
 #define HEAD_BYTE 4   /* xtensor_halo3d.hpp:258 */
 #define ELEM_BYTE 56  /* xtensor_halo3d.hpp:259 */
 

@@ -606,6 +606,10 @@ void nixo_deposit3d(int order, double dxdt, double dydt, double dzdt, double qs,
     esirkepov::deposit3d<3>(dxdt, dydt, dzdt, qs, reinterpret_cast<double(*)[3][6]>(ss),
                             reinterpret_cast<double(*)[6][6][4]>(cur));
     break;
+  case 4:
+    esirkepov::deposit3d<4>(dxdt, dydt, dzdt, qs, reinterpret_cast<double(*)[3][7]>(ss),
+                            reinterpret_cast<double(*)[7][7][4]>(cur));
+    break;
   default:
     break;
   }
@@ -692,6 +696,8 @@ double nixo_interp3d(int order, const double* eb, int my, int mx, int iz0, int i
     return interp::interp3d<2>(view, iz0, iy0, ix0, ik, z, y, x, dt);
   case 3:
     return interp::interp3d<3>(view, iz0, iy0, ix0, ik, z, y, x, dt);
+  case 4:
+    return interp::interp3d<4>(view, iz0, iy0, ix0, ik, z, y, x, dt);
   default:
     return 0;
   }
@@ -712,6 +718,9 @@ void nixo_chunk_push_deposit(nixo_chunk* c, double delt, double cc, int simd)
       case 3:
         r->push_deposit<3, true>(is, delt, cc);
         break;
+      case 4:
+        r->push_deposit<4, true>(is, delt, cc);
+        break;
       }
     } else {
       switch (r->order) {
@@ -723,6 +732,9 @@ void nixo_chunk_push_deposit(nixo_chunk* c, double delt, double cc, int simd)
         break;
       case 3:
         r->push_deposit<3, false>(is, delt, cc);
+        break;
+      case 4:
+        r->push_deposit<4, false>(is, delt, cc);
         break;
       }
     }
@@ -825,6 +837,7 @@ void nixo_chunk_deposit_moment(nixo_chunk* c, double cc)
   case 1: deposit_moment_t<1>(*r, cc); break;
   case 2: deposit_moment_t<2>(*r, cc); break;
   case 3: deposit_moment_t<3>(*r, cc); break;
+  case 4: deposit_moment_t<4>(*r, cc); break;
   }
 }
 

@@ -141,7 +141,7 @@ def test_lorentz_and_boris_energy(oracle_port):
         assert abs(g - np.sqrt(1 + np.dot(u, u))) < 1e-14 * g
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 def test_interp3d_equals_naive_sum(oracle_port, order):
     # test_interp.cpp:726-784: factorised result == naive triple sum, rel 1e-14
     rng = np.random.default_rng(order + 10)
@@ -173,7 +173,7 @@ def _weights(lib, order, x0, x1):
     return ss
 
 
-@pytest.mark.parametrize("order", [1, 2, 3])
+@pytest.mark.parametrize("order", [1, 2, 3, 4])
 @pytest.mark.parametrize("dt,dh", [(0.5, 1.0), (1.0, 1.0), (0.5, 2.0)])
 def test_deposit3d_continuity(oracle_port, order, dt, dh):
     """test_esirkepov.cpp:993-1106: (1) sum of weights = 1, (2) sum rho = q per particle,

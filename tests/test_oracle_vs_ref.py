@@ -232,3 +232,25 @@ def test_baseline_config_1_at_its_stated_size(oracle_port, oracle_ref):
     nb = prob.nb
     rho = ca.uj[nb:-nb, nb:-nb, nb:-nb, 0]
     assert abs(rho.sum()) <= 1e-12 * np.abs(rho).sum()
+
+
+def test_order_4_composed_step_bit_exact(oracle_port, oracle_ref):
+    """SURVEY.md 8f N4 ("order 4"): the reference's templates exist for Order = 4 throughout (shape_mc<4>, interp3d<4>,
+    deposit3d<4>, append_current3d<4>; three ghost layers), so the composed step of the checker does too -- port and
+    reference bit for bit over steps with migration, charge conserved.  (The GPU kernels are instantiated for orders
+    1-3 only, DESIGN.md section 0: this pins the ORACLE an order-4 kernel would be checked against.)"""
+    prob = Problem((2, 2, 2), (6, 6, 6), 4, ppc=5, seed=74, vth=(0.35, 0.08), nb=3)
+    a = oracle_domain(oracle_port, prob)
+    b = oracle_domain(oracle_ref, prob)
+    for step in range(3):
+        a.step(0.5, 1.0)
+        b.step(0.5, 1.0)
+        for ca, cb in zip(a.chunks, b.chunks):
+            assert np.array_equal(bits(ca.uj), bits(cb.uj)), f"step {step}: J"
+            for s in range(prob.ns):
+                assert np.array_equal(bits(ca.particles(s)), bits(cb.particles(s))), f"step {step}: particles"
+                assert np.array_equal(ca.pindex(s), cb.pindex(s))
+    assert a.total_particles() == b.total_particles() == prob.total_particles()
+    nb = prob.nb
+    rho = np.array([c.uj[nb:-nb, nb:-nb, nb:-nb, 0] for c in a.chunks])
+    assert abs(rho.sum()) <= 1e-12 * np.abs(rho).sum()
